@@ -1,0 +1,15 @@
+"""climaocean.jl_b200 — Blackwell-native surface-flux engine behind ClimaOcean's coupling API.
+
+Holds only what the hot path needs: `csrc/` (CUDA kernels + C ABI → lib/libcoflux.so), the ctypes
+mirror of include/coflux.h, and the host-side mirror of the reference's interface for this path
+(`OceanSeaIceModel`, `ComponentInterfaces`, `SimilarityTheoryFluxes`, `update_state`, `time_step`).
+Importing the package requires the built CUDA library; there is no CPU fallback.
+"""
+from . import _abi
+from ._abi import CofluxError, load_library, default_config
+from .fields import Field, FieldTimeSeries, LatitudeLongitudeGrid, fractional_indices
+from .state import SurfaceFluxData
+from .engine import Engine
+from .models import *  # noqa: F401,F403  (reference-facing names)
+
+load_library()   # fail loudly at import when lib/libcoflux.so has not been built

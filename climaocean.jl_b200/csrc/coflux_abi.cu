@@ -1,0 +1,989 @@
+// coflux_abi.cu — the C ABI (include/coflux.h) over the sm_100a kernels.
+//
+// Host responsibilities: parameter validation, conversion of the POD parameter mirrors to the
+// device parameter block (in FT arithmetic), translation of Oceananigans-style halo-padded array
+// descriptors to kernel views, kernel launches on the caller's stream, the HOST-buffer end-to-end
+// entry, and the multi-GPU seam.  There is no CPU compute path in this file: every entry point
+// either launches CUDA kernels or fails with a status code.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "coflux_kernels.cuh"
+
+using namespace coflux;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return fail(COFLUX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define COFLUX_STR_(x) #x
+#define COFLUX_STR(x) COFLUX_STR_(x)
+extern "C" const char* coflux_last_error(void) { return g_err; }
+extern "C" int coflux_abi_version(void) { return COFLUX_ABI_VERSION; }
+extern "C" const char* coflux_build_info(void) {
+  return "coflux abi 1; target sm_100a; nvcc " COFLUX_STR(__CUDACC_VER_MAJOR__) "." COFLUX_STR(__CUDACC_VER_MINOR__)
+         "; no CPU fallback";
+}
+
+extern "C" int coflux_sizeof(const char* name) {
+  if (!name) return -1;
+#define SZ(n) if (!strcmp(name, #n)) return (int)sizeof(coflux_##n)
+  SZ(array); SZ(air_viscosity); SZ(momentum_roughness); SZ(scalar_roughness); SZ(flux_params); SZ(thermodynamics);
+  SZ(atmosphere_properties); SZ(ocean_properties); SZ(radiation_properties); SZ(ice_ocean_params); SZ(grid_desc);
+  SZ(config); SZ(atmos_series); SZ(exchange_state); SZ(ocean_surface); SZ(interface_fluxes); SZ(sea_ice_state);
+  SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step);
+#undef SZ
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct HostStage {   // device staging planes for coflux_update_state_host
+  int halo = -1;
+  size_t plane_bytes = 0;
+  char* in[4] = {nullptr, nullptr, nullptr, nullptr};     // ocean u v T S
+  char* xch[8] = {};                                     // exchange state
+  char* ao[6] = {};                                      // Qv Qc Fv ρτx ρτy Ts
+  char* net[8] = {};                                     // τx τy JT JS Qu Qal Qts J0
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[4] = {}, ev_k = nullptr, ev_k2 = nullptr;
+};
+struct Seam {
+  bool attached = false;
+  int rank = 0, world = 1;
+  char* local = nullptr;        // this context's seam buffer (cudaMalloc): 2 parities × Ny elements + flags
+  char* east = nullptr;         // peer mapping of the east neighbour's buffer
+  char* west = nullptr;         // peer mapping of the west neighbour's buffer (for acks)
+  size_t bytes = 0;
+  unsigned long long step = 0;
+};
+struct Profile {
+  bool on = false;
+  static const int RING = 64;             // events are read back lazily; a ring bounds their number
+  cudaEvent_t ev[RING][3] = {};
+  int pending = 0;
+  double flux_ms = 0, stress_ms = 0;
+  long long calls = 0;
+};
+struct coflux_ctx {
+  coflux_config cfg;
+  Profile prof;
+  int device;
+  DevParams<double> P64;
+  DevParams<float> P32;
+  long long launches = 0;
+  HostStage stage;
+  Seam seam;
+};
+
+static bool finite_all(const double* v, int n) {
+  for (int k = 0; k < n; ++k)
+    if (!std::isfinite(v[k])) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// defaults (omip_simulation.jl:40-113 for the presets)
+// ---------------------------------------------------------------------------------------------
+static coflux_air_viscosity constant_viscosity(double nu) {
+  coflux_air_viscosity v;
+  memset(&v, 0, sizeof(v));
+  v.kind = COFLUX_VISCOSITY_CONSTANT;
+  v.nu = nu;
+  v.c0 = 1.326e-5; v.c1 = v.c0 * 6.542e-3; v.c2 = v.c0 * 8.301e-6; v.c3 = -v.c0 * 4.84e-9;
+  return v;
+}
+static coflux_air_viscosity temperature_dependent_viscosity() {
+  coflux_air_viscosity v = constant_viscosity(1.5e-5);
+  v.kind = COFLUX_VISCOSITY_TEMPERATURE_POLY;
+  return v;
+}
+static coflux_flux_params default_similarity_fluxes(int stability) {
+  coflux_flux_params f;
+  memset(&f, 0, sizeof(f));
+  f.formulation = COFLUX_FLUXES_SIMILARITY_THEORY;
+  f.stability_functions = stability;
+  f.similarity_form = COFLUX_PROFILE_LOGARITHMIC;
+  f.velocity_formulation = COFLUX_VELOCITY_RELATIVE;
+  f.stop_kind = COFLUX_STOP_CONVERGENCE;
+  f.max_iterations = 100;
+  f.interface_temperature = COFLUX_TEMPERATURE_BULK;
+  f.tolerance = 1e-8;
+  f.von_karman_constant = 0.4;
+  f.turbulent_prandtl_number = 1.0;
+  f.gustiness_parameter = 1.0;
+  f.minimum_gustiness = 0.0;
+  f.initial_scale = 1e-4;
+  f.ly_minimum_wind = 0.5;
+  f.skin_max_delta_T = 5.0;
+  coflux_momentum_roughness& m = f.momentum_roughness;
+  m.kind = COFLUX_ROUGHNESS_CHARNOCK;
+  m.wave_formulation = COFLUX_WAVES_CONSTANT;
+  m.fixed_length = 1e-4;
+  m.gravity_wave_parameter = 0.02;   // ":default — Edson/COARE with constant Charnock 0.02" (omip_simulation.jl:263)
+  m.wind_a1 = 0.0017; m.wind_a2 = -0.005; m.wind_umax = 19.0; m.wind_alpha_min = 0.0;
+  m.smooth_wall_parameter = 0.11;
+  m.maximum_length = 1.0;
+  m.gravitational_acceleration = 9.81;
+  m.viscosity = constant_viscosity(1.5e-5);
+  coflux_scalar_roughness s;
+  memset(&s, 0, sizeof(s));
+  s.kind = COFLUX_ROUGHNESS_REYNOLDS_SCALING;
+  s.fixed_length = 1e-4;
+  s.reynolds_A = 5.85e-5; s.reynolds_b = 0.72;
+  s.maximum_length = 1.6e-4;
+  s.viscosity = constant_viscosity(1.5e-5);
+  f.temperature_roughness = s;
+  f.water_vapor_roughness = s;
+  return f;
+}
+static void set_fixed_roughness(coflux_flux_params& f, double lu, double lt, double lq) {
+  f.momentum_roughness.kind = COFLUX_ROUGHNESS_FIXED; f.momentum_roughness.fixed_length = lu;
+  f.temperature_roughness.kind = COFLUX_ROUGHNESS_FIXED; f.temperature_roughness.fixed_length = lt;
+  f.water_vapor_roughness.kind = COFLUX_ROUGHNESS_FIXED; f.water_vapor_roughness.fixed_length = lq;
+}
+
+extern "C" int coflux_default_config(coflux_config* cfg, int32_t Nx, int32_t Ny, int32_t Nz, int32_t dtype) {
+  if (!cfg) return fail(COFLUX_ERR_INVALID_ARGUMENT, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->abi_version = COFLUX_ABI_VERSION;
+  cfg->dtype = dtype;
+  cfg->device = 0;
+  cfg->grid.Nx = Nx; cfg->grid.Ny = Ny; cfg->grid.Nz = Nz; cfg->grid.ring = 1; cfg->grid.periodic_x = 1;
+  cfg->atmosphere_ocean = default_similarity_fluxes(COFLUX_STABILITY_EDSON);
+  cfg->atmosphere_sea_ice = default_similarity_fluxes(COFLUX_STABILITY_SHEBA_PAULSON);
+  cfg->atmosphere_sea_ice.interface_temperature = COFLUX_TEMPERATURE_SKIN;
+  set_fixed_roughness(cfg->atmosphere_sea_ice, 1e-4, 1e-4, 1e-4);
+  coflux_ice_ocean_params& io = cfg->ice_ocean;
+  io.heat_flux = COFLUX_ICE_OCEAN_ICE_BATH;
+  io.friction_velocity = COFLUX_FRICTION_VELOCITY_CONSTANT;
+  io.characteristic_melting_speed = 1e-5;
+  io.liquidus_freshwater_melting_temperature = 0.0;
+  io.liquidus_slope = 0.054;
+  io.heat_transfer_coefficient = 0.0095;
+  io.salt_transfer_coefficient = 0.0095 / 35.0;
+  io.constant_friction_velocity = 0.002;
+  io.minimum_friction_velocity = 1e-4;
+  io.ice_density = 900.0;
+  io.ice_latent_heat = 334e3;
+  io.ice_ocean_drag_coefficient = 5.5e-3;
+  io.ice_conductivity = 2.0;
+  io.ice_consolidation_thickness = 0.05;
+  coflux_thermodynamics& t = cfg->atmosphere.thermodynamics;
+  t.gas_constant = 8.3144598; t.dry_air_molar_mass = 0.02897; t.water_molar_mass = 0.018015;
+  t.dry_air_adiabatic_exponent = 2.0 / 7.0;
+  t.water_vapor_heat_capacity = 1859; t.liquid_water_heat_capacity = 4181; t.ice_heat_capacity = 2100;
+  t.reference_vaporization_enthalpy = 2500800; t.reference_sublimation_enthalpy = 2834400;
+  t.reference_temperature = 273.16; t.triple_point_temperature = 273.16; t.triple_point_pressure = 611.657;
+  t.water_freezing_temperature = 273.15; t.total_ice_nucleation_temperature = 233;
+  cfg->atmosphere.surface_layer_height = 10.0;
+  cfg->atmosphere.boundary_layer_height = 512.0;
+  cfg->atmosphere.gravitational_acceleration = 9.81;
+  coflux_ocean_properties& o = cfg->ocean;
+  o.reference_density = 1026.0;             // visualize/common.jl:17
+  o.heat_capacity = 3991.86795711963;       // visualize/common.jl:18
+  o.freshwater_density = 1000.0;
+  o.minimum_salinity = 1.0;                 // omip_simulation.jl:125
+  o.temperature_units = COFLUX_TEMPERATURE_CELSIUS;
+  o.salt_water_molar_mass = 18.02;
+  const double mm[4] = {35.45, 22.99, 96.06, 24.31}, mf[4] = {0.56, 0.31, 0.08, 0.05};
+  for (int k = 0; k < 4; ++k) { o.constituent_molar_mass[k] = mm[k]; o.constituent_mass_fraction[k] = mf[k]; }
+  coflux_radiation_properties& r = cfg->radiation;
+  r.stefan_boltzmann_constant = 5.67e-8;
+  r.ocean_albedo = 0.06; r.ocean_emissivity = 1.0;   // atmosphere.jl:43 (OMIP-2 ocean surface)
+  r.sea_ice_emissivity = 1.0; r.sea_ice_albedo = 0.7;
+  r.shortwave_penetrates = 1;
+  return COFLUX_OK;
+}
+
+extern "C" int coflux_apply_flux_configuration(coflux_config* cfg, const char* name, int32_t velocity) {
+  if (!cfg || !name) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (velocity != COFLUX_VELOCITY_RELATIVE && velocity != COFLUX_VELOCITY_WIND)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "Unknown velocity_formulation: %d. Options: relative (0), wind (1)", velocity);
+  if (!strcmp(name, "default")) {
+    cfg->atmosphere_ocean = default_similarity_fluxes(COFLUX_STABILITY_EDSON);
+    cfg->atmosphere_sea_ice = default_similarity_fluxes(COFLUX_STABILITY_SHEBA_PAULSON);
+    cfg->atmosphere_sea_ice.interface_temperature = COFLUX_TEMPERATURE_SKIN;
+    set_fixed_roughness(cfg->atmosphere_sea_ice, 1e-4, 1e-4, 1e-4);
+    cfg->ice_ocean.heat_flux = COFLUX_ICE_OCEAN_ICE_BATH;
+    cfg->ice_ocean.friction_velocity = COFLUX_FRICTION_VELOCITY_CONSTANT;
+  } else if (!strcmp(name, "corrected")) {
+    // corrected_atmosphere_ocean_fluxes (omip_simulation.jl:40-50)
+    coflux_flux_params ao = default_similarity_fluxes(COFLUX_STABILITY_EDSON);
+    ao.similarity_form = COFLUX_PROFILE_COARE_LOGARITHMIC;
+    ao.minimum_gustiness = 0.5;
+    ao.momentum_roughness.wave_formulation = COFLUX_WAVES_WIND_DEPENDENT;
+    ao.momentum_roughness.viscosity = temperature_dependent_viscosity();
+    ao.temperature_roughness.viscosity = temperature_dependent_viscosity();
+    ao.water_vapor_roughness.viscosity = temperature_dependent_viscosity();
+    cfg->atmosphere_ocean = ao;
+    // corrected_atmosphere_sea_ice_fluxes (omip_simulation.jl:62-69)
+    coflux_flux_params ai = default_similarity_fluxes(COFLUX_STABILITY_SHEBA_PAULSON);
+    ai.similarity_form = COFLUX_PROFILE_COARE_LOGARITHMIC;
+    ai.minimum_gustiness = 0.2;
+    ai.interface_temperature = COFLUX_TEMPERATURE_SKIN;
+    set_fixed_roughness(ai, 5e-4, 5e-5, 5e-5);
+    cfg->atmosphere_sea_ice = ai;
+    // corrected_ice_ocean_heat_flux (omip_simulation.jl:77)
+    cfg->ice_ocean.heat_flux = COFLUX_ICE_OCEAN_THREE_EQUATION;
+    cfg->ice_ocean.friction_velocity = COFLUX_FRICTION_VELOCITY_MOMENTUM_BASED;
+  } else if (!strcmp(name, "ncar")) {
+    // ncar_atmosphere_ocean_fluxes (omip_simulation.jl:86-89)
+    coflux_flux_params ao = default_similarity_fluxes(COFLUX_STABILITY_LARGE_YEAGER);
+    ao.formulation = COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER;
+    ao.stop_kind = COFLUX_STOP_FIXED_ITERATIONS;
+    ao.max_iterations = 5;
+    cfg->atmosphere_ocean = ao;
+    // ncar_atmosphere_sea_ice_fluxes (omip_simulation.jl:105-113)
+    coflux_flux_params ai = default_similarity_fluxes(COFLUX_STABILITY_LARGE_YEAGER);
+    ai.similarity_form = COFLUX_PROFILE_COARE_LOGARITHMIC;
+    ai.gustiness_parameter = 0.0;
+    ai.minimum_gustiness = 0.5;
+    ai.interface_temperature = COFLUX_TEMPERATURE_SKIN;
+    set_fixed_roughness(ai, 5e-4, 5e-4, 5e-4);
+    cfg->atmosphere_sea_ice = ai;
+    cfg->ice_ocean.heat_flux = COFLUX_ICE_OCEAN_THREE_EQUATION;
+    cfg->ice_ocean.friction_velocity = COFLUX_FRICTION_VELOCITY_MOMENTUM_BASED;
+  } else {
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "Unknown flux_configuration: %s. Options: default, corrected, ncar", name);
+  }
+  cfg->atmosphere_ocean.velocity_formulation = velocity;
+  cfg->atmosphere_sea_ice.velocity_formulation = velocity;
+  return COFLUX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// validation + device parameter block
+// ---------------------------------------------------------------------------------------------
+static int validate_viscosity(const coflux_air_viscosity& v, const char* who) {
+  if (v.kind != COFLUX_VISCOSITY_CONSTANT && v.kind != COFLUX_VISCOSITY_TEMPERATURE_POLY)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown air viscosity kind %d", who, v.kind);
+  const double vals[5] = {v.nu, v.c0, v.c1, v.c2, v.c3};
+  if (!finite_all(vals, 5)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: non-finite air viscosity parameter", who);
+  if (v.kind == COFLUX_VISCOSITY_CONSTANT && !(v.nu > 0)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: viscosity must be > 0", who);
+  return COFLUX_OK;
+}
+static int validate_flux(const coflux_flux_params& f, const char* who) {
+  if (f.formulation < 0 || f.formulation > COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown flux formulation %d", who, f.formulation);
+  if (f.stability_functions < 0 || f.stability_functions > COFLUX_STABILITY_NEUTRAL)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown stability functions %d", who, f.stability_functions);
+  if (f.similarity_form < 0 || f.similarity_form > COFLUX_PROFILE_COARE_LOGARITHMIC)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown similarity form %d", who, f.similarity_form);
+  if (f.velocity_formulation < 0 || f.velocity_formulation > COFLUX_VELOCITY_WIND)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: Unknown velocity_formulation: %d. Options: relative (0), wind (1)", who, f.velocity_formulation);
+  if (f.stop_kind < 0 || f.stop_kind > COFLUX_STOP_FIXED_ITERATIONS)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown solver stop criteria %d", who, f.stop_kind);
+  if (f.interface_temperature < 0 || f.interface_temperature > COFLUX_TEMPERATURE_SKIN)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown interface temperature formulation %d", who, f.interface_temperature);
+  if (f.max_iterations < 0 || f.max_iterations > 100000)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: max_iterations out of range (%d)", who, f.max_iterations);
+  const double vals[8] = {f.tolerance, f.von_karman_constant, f.turbulent_prandtl_number, f.gustiness_parameter,
+                          f.minimum_gustiness, f.initial_scale, f.ly_minimum_wind, f.skin_max_delta_T};
+  if (!finite_all(vals, 8)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: non-finite scalar parameter", who);
+  if (!(f.von_karman_constant > 0)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: von_karman_constant must be > 0", who);
+  if (f.turbulent_prandtl_number != 1.0)
+    return fail(COFLUX_ERR_UNSUPPORTED, "%s: turbulent_prandtl_number != 1 is not supported", who);
+  if (f.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER && !(f.ly_minimum_wind > 0))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: ly_minimum_wind must be > 0", who);
+  const coflux_momentum_roughness& m = f.momentum_roughness;
+  if (m.kind != COFLUX_ROUGHNESS_FIXED && m.kind != COFLUX_ROUGHNESS_CHARNOCK)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown momentum roughness kind %d", who, m.kind);
+  if (m.wave_formulation < 0 || m.wave_formulation > COFLUX_WAVES_WIND_DEPENDENT)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown wave formulation %d", who, m.wave_formulation);
+  const double mv[10] = {m.fixed_length, m.gravity_wave_parameter, m.wind_a1, m.wind_a2, m.wind_umax, m.wind_alpha_min,
+                         m.smooth_wall_parameter, m.maximum_length, m.gravitational_acceleration, 0.0};
+  if (!finite_all(mv, 10)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: non-finite momentum roughness parameter", who);
+  if (m.kind == COFLUX_ROUGHNESS_FIXED && !(m.fixed_length > 0))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: fixed momentum roughness length must be > 0", who);
+  int rc = validate_viscosity(m.viscosity, who);
+  if (rc) return rc;
+  const coflux_scalar_roughness* ss[2] = {&f.temperature_roughness, &f.water_vapor_roughness};
+  for (int k = 0; k < 2; ++k) {
+    const coflux_scalar_roughness& s = *ss[k];
+    if (s.kind != COFLUX_ROUGHNESS_FIXED && s.kind != COFLUX_ROUGHNESS_REYNOLDS_SCALING)
+      return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown scalar roughness kind %d", who, s.kind);
+    const double sv[4] = {s.fixed_length, s.reynolds_A, s.reynolds_b, s.maximum_length};
+    if (!finite_all(sv, 4)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: non-finite scalar roughness parameter", who);
+    if (s.kind == COFLUX_ROUGHNESS_FIXED && !(s.fixed_length > 0))
+      return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: fixed scalar roughness length must be > 0", who);
+    rc = validate_viscosity(s.viscosity, who);
+    if (rc) return rc;
+  }
+  return COFLUX_OK;
+}
+static int validate_config(const coflux_config* c) {
+  if (c->abi_version != COFLUX_ABI_VERSION)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "abi_version %d != library %d", c->abi_version, COFLUX_ABI_VERSION);
+  if (c->dtype != COFLUX_F32 && c->dtype != COFLUX_F64) return fail(COFLUX_ERR_INVALID_ARGUMENT, "dtype must be 32 or 64 (got %d)", c->dtype);
+  if (c->grid.Nx < 1 || c->grid.Ny < 1 || c->grid.Nz < 1) return fail(COFLUX_ERR_INVALID_ARGUMENT, "grid size must be positive");
+  if (c->grid.ring != 0 && c->grid.ring != 1) return fail(COFLUX_ERR_INVALID_ARGUMENT, "grid.ring must be 0 or 1");
+  int rc = validate_flux(c->atmosphere_ocean, "atmosphere_ocean");
+  if (rc) return rc;
+  rc = validate_flux(c->atmosphere_sea_ice, "atmosphere_sea_ice");
+  if (rc) return rc;
+  if (c->atmosphere_ocean.interface_temperature != COFLUX_TEMPERATURE_BULK)
+    return fail(COFLUX_ERR_UNSUPPORTED, "atmosphere_ocean: only the bulk interface temperature is supported over the ocean");
+  const coflux_ice_ocean_params& io = c->ice_ocean;
+  if (io.heat_flux < 0 || io.heat_flux > COFLUX_ICE_OCEAN_THREE_EQUATION) return fail(COFLUX_ERR_INVALID_ARGUMENT, "unknown sea_ice_ocean_heat_flux %d", io.heat_flux);
+  if (io.friction_velocity < 0 || io.friction_velocity > COFLUX_FRICTION_VELOCITY_MOMENTUM_BASED)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "unknown friction velocity formulation %d", io.friction_velocity);
+  const double iv[12] = {io.characteristic_melting_speed, io.liquidus_freshwater_melting_temperature, io.liquidus_slope,
+                         io.heat_transfer_coefficient, io.salt_transfer_coefficient, io.constant_friction_velocity,
+                         io.minimum_friction_velocity, io.ice_density, io.ice_latent_heat, io.ice_ocean_drag_coefficient,
+                         io.ice_conductivity, io.ice_consolidation_thickness};
+  if (!finite_all(iv, 12)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite sea-ice–ocean parameter");
+  const coflux_thermodynamics& t = c->atmosphere.thermodynamics;
+  const double tv[14] = {t.gas_constant, t.dry_air_molar_mass, t.water_molar_mass, t.dry_air_adiabatic_exponent,
+                         t.water_vapor_heat_capacity, t.liquid_water_heat_capacity, t.ice_heat_capacity,
+                         t.reference_vaporization_enthalpy, t.reference_sublimation_enthalpy, t.reference_temperature,
+                         t.triple_point_temperature, t.triple_point_pressure, t.water_freezing_temperature,
+                         t.total_ice_nucleation_temperature};
+  if (!finite_all(tv, 14)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite thermodynamics parameter");
+  for (int k = 0; k < 14; ++k)
+    if (!(tv[k] > 0)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "thermodynamics parameters must be > 0");
+  const double av[3] = {c->atmosphere.surface_layer_height, c->atmosphere.boundary_layer_height, c->atmosphere.gravitational_acceleration};
+  if (!finite_all(av, 3) || !(av[0] > 0) || !(av[1] > 0) || !(av[2] > 0))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "atmosphere heights / gravity must be finite and > 0");
+  const coflux_ocean_properties& o = c->ocean;
+  const double ov[5] = {o.reference_density, o.heat_capacity, o.freshwater_density, o.minimum_salinity, o.salt_water_molar_mass};
+  if (!finite_all(ov, 5) || !(ov[0] > 0) || !(ov[1] > 0) || !(ov[2] > 0))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "ocean properties must be finite and > 0");
+  if (!finite_all(o.constituent_molar_mass, 4) || !finite_all(o.constituent_mass_fraction, 4))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite salinity constituent");
+  if (o.temperature_units != COFLUX_TEMPERATURE_CELSIUS && o.temperature_units != COFLUX_TEMPERATURE_KELVIN)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "unknown ocean temperature units %d", o.temperature_units);
+  const coflux_radiation_properties& r = c->radiation;
+  const double rv[5] = {r.stefan_boltzmann_constant, r.ocean_albedo, r.ocean_emissivity, r.sea_ice_emissivity, r.sea_ice_albedo};
+  if (!finite_all(rv, 5)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite radiation property");
+  return COFLUX_OK;
+}
+
+template <typename FT> static Visc<FT> to_dev(const coflux_air_viscosity& v) {
+  Visc<FT> d;
+  d.kind = v.kind; d.nu = (FT)v.nu; d.c0 = (FT)v.c0; d.c1 = (FT)v.c1; d.c2 = (FT)v.c2; d.c3 = (FT)v.c3;
+  return d;
+}
+static bool same_viscosity(const coflux_air_viscosity& a, const coflux_air_viscosity& b) {
+  return a.kind == b.kind && a.nu == b.nu && a.c0 == b.c0 && a.c1 == b.c1 && a.c2 == b.c2 && a.c3 == b.c3;
+}
+template <typename FT> static FluxP<FT> to_dev(const coflux_flux_params& f) {
+  FluxP<FT> d;
+  d.formulation = f.formulation; d.stability = f.stability_functions; d.form = f.similarity_form;
+  d.velocity = f.velocity_formulation; d.stop_kind = f.stop_kind; d.maxit = f.max_iterations; d.itemp = f.interface_temperature;
+  d.tol = (FT)f.tolerance; d.kappa = (FT)f.von_karman_constant; d.beta = (FT)f.gustiness_parameter;
+  d.ugmin = (FT)f.minimum_gustiness; d.init = (FT)f.initial_scale; d.ly_umin = (FT)f.ly_minimum_wind;
+  d.skin_max_dT = (FT)f.skin_max_delta_T;
+  const coflux_momentum_roughness& m = f.momentum_roughness;
+  d.mr.kind = m.kind; d.mr.waves = m.wave_formulation; d.mr.fixed = (FT)m.fixed_length; d.mr.alpha = (FT)m.gravity_wave_parameter;
+  d.mr.a1 = (FT)m.wind_a1; d.mr.a2 = (FT)m.wind_a2; d.mr.umax = (FT)m.wind_umax; d.mr.amin = (FT)m.wind_alpha_min;
+  d.mr.beta_s = (FT)m.smooth_wall_parameter; d.mr.lmax = (FT)m.maximum_length; d.mr.g = (FT)m.gravitational_acceleration;
+  d.mr.visc = to_dev<FT>(m.viscosity);
+  const coflux_scalar_roughness& t = f.temperature_roughness;
+  const coflux_scalar_roughness& q = f.water_vapor_roughness;
+  d.tr.kind = t.kind; d.tr.fixed = (FT)t.fixed_length; d.tr.A = (FT)t.reynolds_A; d.tr.b = (FT)t.reynolds_b; d.tr.lmax = (FT)t.maximum_length;
+  d.tr.visc = to_dev<FT>(t.viscosity);
+  d.qr.kind = q.kind; d.qr.fixed = (FT)q.fixed_length; d.qr.A = (FT)q.reynolds_A; d.qr.b = (FT)q.reynolds_b; d.qr.lmax = (FT)q.maximum_length;
+  d.qr.visc = to_dev<FT>(q.viscosity);
+  d.same_scalar = (t.kind == q.kind && t.fixed_length == q.fixed_length && t.reynolds_A == q.reynolds_A &&
+                   t.reynolds_b == q.reynolds_b && t.maximum_length == q.maximum_length && same_viscosity(t.viscosity, q.viscosity))
+                      ? 1 : 0;
+  return d;
+}
+template <typename FT> static DevParams<FT> make_dev_params(const coflux_config& c) {
+  DevParams<FT> P;
+  const coflux_thermodynamics& t = c.atmosphere.thermodynamics;
+  P.th.R_d = (FT)t.gas_constant / (FT)t.dry_air_molar_mass;
+  P.th.R_v = (FT)t.gas_constant / (FT)t.water_molar_mass;
+  P.th.eps = (FT)t.dry_air_molar_mass / (FT)t.water_molar_mass;
+  P.th.cp_d = P.th.R_d / (FT)t.dry_air_adiabatic_exponent;
+  P.th.cp_v = (FT)t.water_vapor_heat_capacity; P.th.cp_l = (FT)t.liquid_water_heat_capacity; P.th.cp_i = (FT)t.ice_heat_capacity;
+  P.th.LH_v0 = (FT)t.reference_vaporization_enthalpy; P.th.LH_s0 = (FT)t.reference_sublimation_enthalpy;
+  P.th.T_0 = (FT)t.reference_temperature; P.th.T_tr = (FT)t.triple_point_temperature; P.th.p_tr = (FT)t.triple_point_pressure;
+  P.th.T_fr = (FT)t.water_freezing_temperature; P.th.T_in = (FT)t.total_ice_nucleation_temperature;
+  P.th.Rd_over_Rv = P.th.R_d / P.th.R_v;
+  P.h = (FT)c.atmosphere.surface_layer_height; P.hbl = (FT)c.atmosphere.boundary_layer_height;
+  P.g = (FT)c.atmosphere.gravitational_acceleration;
+  P.rho0 = (FT)c.ocean.reference_density; P.c0 = (FT)c.ocean.heat_capacity; P.rhof = (FT)c.ocean.freshwater_density;
+  P.Smin = (FT)c.ocean.minimum_salinity;
+  FT alpha = (FT)0;
+  for (int k = 0; k < 4; ++k) alpha += (FT)c.ocean.constituent_mass_fraction[k] / (FT)c.ocean.constituent_molar_mass[k];
+  P.wmf_alpha = (FT)c.ocean.salt_water_molar_mass * alpha;
+  P.T_offset = (c.ocean.temperature_units == COFLUX_TEMPERATURE_CELSIUS) ? (FT)273.15 : (FT)0;
+  P.sigma = (FT)c.radiation.stefan_boltzmann_constant; P.alb_o = (FT)c.radiation.ocean_albedo; P.emis_o = (FT)c.radiation.ocean_emissivity;
+  P.emis_i = (FT)c.radiation.sea_ice_emissivity; P.alb_i = (FT)c.radiation.sea_ice_albedo; P.sw_pen = c.radiation.shortwave_penetrates;
+  P.ao = to_dev<FT>(c.atmosphere_ocean);
+  P.ai = to_dev<FT>(c.atmosphere_sea_ice);
+  const coflux_ice_ocean_params& io = c.ice_ocean;
+  P.io.heat_flux = io.heat_flux; P.io.friction = io.friction_velocity; P.io.um_star = (FT)io.characteristic_melting_speed;
+  P.io.T0 = (FT)io.liquidus_freshwater_melting_temperature; P.io.slope = (FT)io.liquidus_slope;
+  P.io.alpha_h = (FT)io.heat_transfer_coefficient; P.io.alpha_s = (FT)io.salt_transfer_coefficient;
+  P.io.ustar_const = (FT)io.constant_friction_velocity; P.io.ustar_min = (FT)io.minimum_friction_velocity;
+  P.io.rho_i = (FT)io.ice_density; P.io.L_f = (FT)io.ice_latent_heat; P.io.Cd = (FT)io.ice_ocean_drag_coefficient;
+  P.io.k_ice = (FT)io.ice_conductivity; P.io.h_c = (FT)io.ice_consolidation_thickness;
+  return P;
+}
+template <typename FT> static const DevParams<FT>& dev_params(const coflux_ctx* c);
+template <> const DevParams<double>& dev_params<double>(const coflux_ctx* c) { return c->P64; }
+template <> const DevParams<float>& dev_params<float>(const coflux_ctx* c) { return c->P32; }
+
+extern "C" int coflux_create(coflux_ctx** out, const coflux_config* cfg) {
+  if (!out || !cfg) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  int rc = validate_config(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(COFLUX_ERR_NO_DEVICE, "no CUDA device available (%s); coflux has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(COFLUX_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10)
+    return fail(COFLUX_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+  coflux_ctx* c = new (std::nothrow) coflux_ctx();
+  if (!c) return fail(COFLUX_ERR_ALLOC, "out of host memory");
+  c->cfg = *cfg;
+  c->device = cfg->device;
+  c->P64 = make_dev_params<double>(*cfg);
+  c->P32 = make_dev_params<float>(*cfg);
+  *out = c;
+  return COFLUX_OK;
+}
+
+static void free_stage(HostStage& s) {
+  for (char*& p : s.in) { if (p) cudaFree(p); p = nullptr; }
+  for (char*& p : s.xch) { if (p) cudaFree(p); p = nullptr; }
+  for (char*& p : s.ao) { if (p) cudaFree(p); p = nullptr; }
+  for (char*& p : s.net) { if (p) cudaFree(p); p = nullptr; }
+  if (s.stream) cudaStreamDestroy(s.stream);
+  if (s.copy_in) cudaStreamDestroy(s.copy_in);
+  if (s.copy_out) cudaStreamDestroy(s.copy_out);
+  for (cudaEvent_t& ev : s.ev_in) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  if (s.ev_k) cudaEventDestroy(s.ev_k);
+  if (s.ev_k2) cudaEventDestroy(s.ev_k2);
+  s = HostStage();
+}
+
+extern "C" int coflux_seam_detach(coflux_ctx* c);
+extern "C" int coflux_destroy(coflux_ctx* c) {
+  if (!c) return COFLUX_OK;
+  cudaSetDevice(c->device);
+  coflux_seam_detach(c);
+  if (c->seam.local) cudaFree(c->seam.local);
+  free_stage(c->stage);
+  for (auto& row : c->prof.ev)
+    for (cudaEvent_t& e : row) if (e) cudaEventDestroy(e);
+  delete c;
+  return COFLUX_OK;
+}
+
+static int profile_drain(coflux_ctx* c) {
+  Profile& p = c->prof;
+  for (int k = 0; k < p.pending; ++k) {
+    CUDA_TRY(cudaEventSynchronize(p.ev[k][2]));
+    float a = 0, b = 0;
+    CUDA_TRY(cudaEventElapsedTime(&a, p.ev[k][0], p.ev[k][1]));
+    CUDA_TRY(cudaEventElapsedTime(&b, p.ev[k][1], p.ev[k][2]));
+    p.flux_ms += a; p.stress_ms += b; p.calls += 1;
+  }
+  p.pending = 0;
+  return COFLUX_OK;
+}
+extern "C" int coflux_profile_enable(coflux_ctx* c, int32_t enable) {
+  if (!c) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Profile& p = c->prof;
+  if (enable && !p.ev[0][0])
+    for (auto& row : p.ev)
+      for (cudaEvent_t& e : row) CUDA_TRY(cudaEventCreate(&e));
+  if (!enable) { int rc = profile_drain(c); if (rc) return rc; }
+  p.on = enable != 0;
+  return COFLUX_OK;
+}
+extern "C" int coflux_profile_read(coflux_ctx* c, double* flux_ms, double* stress_ms, int64_t* calls) {
+  if (!c) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = profile_drain(c);
+  if (rc) return rc;
+  Profile& p = c->prof;
+  if (flux_ms) *flux_ms = p.flux_ms;
+  if (stress_ms) *stress_ms = p.stress_ms;
+  if (calls) *calls = p.calls;
+  p.flux_ms = p.stress_ms = 0; p.calls = 0;
+  return COFLUX_OK;
+}
+
+extern "C" int coflux_launch_count(coflux_ctx* c, int64_t* n) {
+  if (!c || !n) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL argument");
+  *n = c->launches;
+  return COFLUX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// time indexing (A8)
+// ---------------------------------------------------------------------------------------------
+extern "C" int coflux_time_indices(const double* times, int32_t Nt, int32_t mode, double period, double time, int32_t* n1,
+                                   int32_t* n2, double* frac) {
+  if (!times || !n1 || !n2 || !frac) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (Nt < 1) return fail(COFLUX_ERR_INVALID_ARGUMENT, "series has no time levels");
+  if (mode < COFLUX_TIME_LINEAR || mode > COFLUX_TIME_CLAMP) return fail(COFLUX_ERR_INVALID_ARGUMENT, "unknown time indexing %d", mode);
+  if (!std::isfinite(time)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite time");
+  if (Nt == 1) { *n1 = *n2 = 0; *frac = 0.0; return COFLUX_OK; }
+  for (int k = 1; k < Nt; ++k)
+    if (!(times[k] > times[k - 1])) return fail(COFLUX_ERR_INVALID_ARGUMENT, "series times must be strictly increasing");
+  double t = time;
+  if (mode == COFLUX_TIME_CYCLICAL) {
+    const double T = (period > 0.0) ? period : (times[Nt - 1] - times[0] + (times[Nt - 1] - times[Nt - 2]));
+    double rel = std::fmod(t - times[0], T);
+    if (rel < 0.0) rel += T;
+    t = times[0] + rel;
+    if (t >= times[Nt - 1]) {
+      *n1 = Nt - 1; *n2 = 0;
+      *frac = (t - times[Nt - 1]) / (times[0] + T - times[Nt - 1]);
+      return COFLUX_OK;
+    }
+  }
+  int lo = 0, hi = Nt - 2;   // largest n in [0, Nt-2] with times[n] <= t (binary search)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) / 2;
+    if (times[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  double f = (t - times[lo]) / (times[lo + 1] - times[lo]);
+  if (mode == COFLUX_TIME_CLAMP) f = f < 0.0 ? 0.0 : (f > 1.0 ? 1.0 : f);
+  *n1 = lo; *n2 = lo + 1; *frac = f;
+  return COFLUX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// descriptor → kernel views
+// ---------------------------------------------------------------------------------------------
+static inline DArr view2d(const coflux_array& a, int k, size_t esize) {
+  DArr d{nullptr, 0, 0};
+  if (!a.ptr) return d;
+  const int64_t off = (int64_t)a.off_i * a.stride_i + (int64_t)a.off_j * a.stride_j + (int64_t)(k + a.off_k) * a.stride_k;
+  d.p = static_cast<char*>(a.ptr) + off * (int64_t)esize;
+  d.si = a.stride_i; d.sj = a.stride_j;
+  return d;
+}
+static inline DArr view2d_opt(const coflux_array* a, int k, size_t esize) {
+  if (!a) return DArr{nullptr, 0, 0};
+  return view2d(*a, k, esize);
+}
+static inline DSeries view_series(const coflux_array& a, int n1, int n2, size_t esize) {
+  DSeries s{nullptr, nullptr, 0, 0};
+  if (!a.ptr) return s;
+  const int64_t off = (int64_t)a.off_i * a.stride_i + (int64_t)a.off_j * a.stride_j + (int64_t)a.off_k * a.stride_k;
+  s.p1 = static_cast<char*>(a.ptr) + (off + (int64_t)n1 * a.stride_n) * (int64_t)esize;
+  s.p2 = static_cast<char*>(a.ptr) + (off + (int64_t)n2 * a.stride_n) * (int64_t)esize;
+  s.si = a.stride_i; s.sj = a.stride_j;
+  return s;
+}
+static inline DCol view3d(const coflux_array& a, size_t esize) {
+  DCol d{nullptr, 0, 0, 0};
+  if (!a.ptr) return d;
+  const int64_t off = (int64_t)a.off_i * a.stride_i + (int64_t)a.off_j * a.stride_j + (int64_t)a.off_k * a.stride_k;
+  d.p = static_cast<char*>(a.ptr) + off * (int64_t)esize;
+  d.si = a.stride_i; d.sj = a.stride_j; d.sk = a.stride_k;
+  return d;
+}
+
+#define REQUIRE(cond, ...)                                            \
+  do {                                                                \
+    if (!(cond)) return fail(COFLUX_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+static int check_launch(coflux_ctx* c, int n) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(COFLUX_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  c->launches += n;
+  return COFLUX_OK;
+}
+
+template <typename FT> static void fill_geometry(const coflux_ctx* c, FluxArgs<FT>& a) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  a.ring = g.ring; a.Nx = g.Nx; a.Ny = g.Ny;
+  a.nxr = g.Nx + 2 * g.ring; a.nyr = g.Ny + 2 * g.ring;
+  a.ncell = (long long)a.nxr * a.nyr;
+  a.P = dev_params<FT>(c);
+  a.seam_east = nullptr;
+}
+
+template <typename FT>
+static int fill_interp(const coflux_ctx* c, const coflux_atmos_series* in, double time, coflux_exchange_state* out, FluxArgs<FT>& a) {
+  REQUIRE(in && out, "NULL atmosphere series / exchange state");
+  REQUIRE(in->u.ptr && in->v.ptr && in->T.ptr && in->q.ptr && in->p.ptr && in->Qs.ptr && in->Ql.ptr,
+          "atmosphere series u, v, T, q, p, Qs, Ql are required");
+  REQUIRE(in->fi.ptr && in->fj.ptr, "fractional indices fi, fj are required");
+  int32_t n1, n2; double frac;
+  int rc = coflux_time_indices(in->times, in->Nt, in->time_indexing, in->cycle_period, time, &n1, &n2, &frac);
+  if (rc) return rc;
+  const size_t es = sizeof(FT);
+  a.su = view_series(in->u, n1, n2, es); a.sv = view_series(in->v, n1, n2, es); a.sT = view_series(in->T, n1, n2, es);
+  a.sq = view_series(in->q, n1, n2, es); a.sp = view_series(in->p, n1, n2, es); a.sQs = view_series(in->Qs, n1, n2, es);
+  a.sQl = view_series(in->Ql, n1, n2, es); a.srain = view_series(in->rain, n1, n2, es); a.ssnow = view_series(in->snow, n1, n2, es);
+  a.fi = view2d(in->fi, 0, es); a.fj = view2d(in->fj, 0, es);
+  a.cs = view2d(in->cos_theta, 0, es); a.sn = view2d(in->sin_theta, 0, es);
+  a.nfrac = (FT)frac;
+  a.xu = view2d(out->u, 0, es); a.xv = view2d(out->v, 0, es); a.xT = view2d(out->T, 0, es); a.xp = view2d(out->p, 0, es);
+  a.xq = view2d(out->q, 0, es); a.xQs = view2d(out->Qs, 0, es); a.xQl = view2d(out->Ql, 0, es); a.xMp = view2d(out->Mp, 0, es);
+  return COFLUX_OK;
+}
+template <typename FT> static int fill_exchange_in(const coflux_exchange_state* x, FluxArgs<FT>& a) {
+  REQUIRE(x, "NULL exchange state");
+  REQUIRE(x->u.ptr && x->v.ptr && x->T.ptr && x->p.ptr && x->q.ptr && x->Qs.ptr && x->Ql.ptr,
+          "exchange state u, v, T, p, q, Qs, Ql are required");
+  const size_t es = sizeof(FT);
+  a.xu = view2d(x->u, 0, es); a.xv = view2d(x->v, 0, es); a.xT = view2d(x->T, 0, es); a.xp = view2d(x->p, 0, es);
+  a.xq = view2d(x->q, 0, es); a.xQs = view2d(x->Qs, 0, es); a.xQl = view2d(x->Ql, 0, es); a.xMp = view2d(x->Mp, 0, es);
+  return COFLUX_OK;
+}
+template <typename FT> static int fill_ocean(const coflux_ctx* c, const coflux_ocean_surface* o, FluxArgs<FT>& a) {
+  REQUIRE(o, "NULL ocean surface");
+  REQUIRE(o->u.ptr && o->v.ptr && o->T.ptr && o->S.ptr, "ocean u, v, T, S are required");
+  const int kN = c->cfg.grid.Nz - 1;
+  const size_t es = sizeof(FT);
+  a.ou = view2d(o->u, kN, es); a.ov = view2d(o->v, kN, es); a.oT = view2d(o->T, kN, es); a.oS = view2d(o->S, kN, es);
+  a.mask = view2d(o->mask, 0, 1);
+  return COFLUX_OK;
+}
+template <typename FT> static void fill_interface_out(coflux_interface_fluxes* f, FluxArgs<FT>& a) {
+  const size_t es = sizeof(FT);
+  a.Qv = view2d(f->latent_heat, 0, es); a.Qc = view2d(f->sensible_heat, 0, es); a.Fv = view2d(f->water_vapor, 0, es);
+  a.rtx = view2d(f->x_momentum, 0, es); a.rty = view2d(f->y_momentum, 0, es); a.Tsout = view2d(f->interface_temperature, 0, es);
+  a.ust = view2d(f->friction_velocity, 0, es); a.tst = view2d(f->temperature_scale, 0, es); a.qst = view2d(f->humidity_scale, 0, es);
+  a.iters = view2d(f->iterations, 0, sizeof(int32_t));
+}
+template <typename FT> static void zero_args(FluxArgs<FT>& a) { memset(&a, 0, sizeof(a)); }
+
+static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------
+// a3
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_interpolate(coflux_ctx* c, const coflux_atmos_series* in, double time, coflux_exchange_state* out, cudaStream_t st) {
+  FluxArgs<FT> a;
+  zero_args(a);
+  fill_geometry(c, a);
+  int rc = fill_interp<FT>(c, in, time, out, a);
+  if (rc) return rc;
+  flux_kernel<FT, 0, true, false, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_interpolate_atmosphere(coflux_ctx* c, const coflux_atmos_series* in, double time,
+                                             coflux_exchange_state* out, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_interpolate<double>(c, in, time, out, st) : do_interpolate<float>(c, in, time, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4–a6
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_ao(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, coflux_interface_fluxes* f, cudaStream_t st) {
+  REQUIRE(f, "NULL interface fluxes");
+  FluxArgs<FT> a;
+  zero_args(a);
+  fill_geometry(c, a);
+  int rc = fill_exchange_in<FT>(x, a);
+  if (rc) return rc;
+  rc = fill_ocean<FT>(c, o, a);
+  if (rc) return rc;
+  fill_interface_out<FT>(f, a);
+  flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_atmosphere_ocean_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,
+                                              coflux_interface_fluxes* f, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_ao<double>(c, x, o, f, st) : do_ao<float>(c, x, o, f, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, coflux_sea_ice_state* ice,
+                 coflux_interface_fluxes* f, cudaStream_t st) {
+  REQUIRE(f && ice, "NULL interface fluxes / sea ice state");
+  REQUIRE(ice->u.ptr && ice->v.ptr && ice->top_temperature.ptr && ice->thickness.ptr && ice->concentration.ptr && ice->salinity.ptr,
+          "sea ice u, v, top_temperature, thickness, concentration, salinity are required");
+  FluxArgs<FT> a;
+  zero_args(a);
+  fill_geometry(c, a);
+  int rc = fill_exchange_in<FT>(x, a);
+  if (rc) return rc;
+  const size_t es = sizeof(FT);
+  a.ou = view2d(ice->u, 0, es); a.ov = view2d(ice->v, 0, es); a.oT = view2d(ice->top_temperature, 0, es);
+  a.oS = DArr{nullptr, 0, 0};
+  a.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
+  a.ih = view2d(ice->thickness, 0, es); a.iS = view2d(ice->salinity, 0, es); a.ialb = view2d(ice->albedo, 0, es);
+  a.iconc = view2d(ice->concentration, 0, es);
+  fill_interface_out<FT>(f, a);
+  a.Ttop_out = view2d(ice->top_temperature, 0, es);
+  flux_kernel<FT, 1, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_atmosphere_sea_ice_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,
+                                                coflux_sea_ice_state* ice, coflux_interface_fluxes* f, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_ai<double>(c, x, o, ice, f, st) : do_ai<float>(c, x, o, ice, f, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* ice, double dt, coflux_ice_ocean_fluxes* f, cudaStream_t st) {
+  REQUIRE(oc && ice && f, "NULL argument");
+  REQUIRE(oc->T.ptr && oc->S.ptr && oc->dz.ptr && oc->u.ptr && oc->v.ptr, "ocean columns T, S, dz, u, v are required");
+  REQUIRE(ice->thickness.ptr && ice->previous_thickness.ptr && ice->concentration.ptr && ice->salinity.ptr && ice->u.ptr && ice->v.ptr,
+          "sea ice thickness, previous_thickness, concentration, salinity, u, v are required");
+  REQUIRE(std::isfinite(dt) && dt > 0, "dt must be finite and > 0");
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = sizeof(FT);
+  IceOceanArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.Nx = g.Nx; a.Ny = g.Ny; a.Nz = g.Nz;
+  a.T = view3d(oc->T, es); a.S = view3d(oc->S, es); a.dz = view3d(oc->dz, es);
+  a.ou = view2d(oc->u, g.Nz - 1, es); a.ov = view2d(oc->v, g.Nz - 1, es);
+  a.iu = view2d(ice->u, 0, es); a.iv = view2d(ice->v, 0, es); a.ih = view2d(ice->thickness, 0, es);
+  a.ihm = view2d(ice->previous_thickness, 0, es); a.iconc = view2d(ice->concentration, 0, es); a.iS = view2d(ice->salinity, 0, es);
+  a.Qf = view2d(f->frazil_heat, 0, es); a.Qio = view2d(f->interface_heat, 0, es); a.Js = view2d(f->salt, 0, es);
+  a.tx = view2d(f->x_momentum, 0, es); a.ty = view2d(f->y_momentum, 0, es);
+  a.dt = (FT)dt;
+  a.P = dev_params<FT>(c);
+  ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 128), 128, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_sea_ice_ocean_fluxes(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* ice, double dt,
+                                           coflux_ice_ocean_fluxes* f, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_io<double>(c, oc, ice, dt, f, st) : do_io<float>(c, oc, ice, dt, f, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static void fill_stress(const coflux_ctx* c, const coflux_ocean_surface* o, const coflux_interface_fluxes* ao,
+                        const coflux_sea_ice_state* ice, const coflux_ice_ocean_fluxes* io, coflux_net_ocean_fluxes* out,
+                        StressArgs<FT>& s) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = sizeof(FT);
+  s.Nx = g.Nx; s.Ny = g.Ny;
+  s.wrap_x = (g.ring == 0 && g.periodic_x && !c->seam.attached) ? 1 : 0;
+  s.rtx = view2d(ao->x_momentum, 0, es); s.rty = view2d(ao->y_momentum, 0, es);
+  s.conc = ice ? view2d(ice->concentration, 0, es) : DArr{nullptr, 0, 0};
+  s.tx_io = io ? view2d(io->x_momentum, 0, es) : DArr{nullptr, 0, 0};
+  s.ty_io = io ? view2d(io->y_momentum, 0, es) : DArr{nullptr, 0, 0};
+  s.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
+  s.taux = view2d(out->u, 0, es); s.tauy = view2d(out->v, 0, es);
+  s.seam_west = nullptr;
+  s.rho0 = dev_params<FT>(c).rho0;
+}
+template <typename FT>
+static int do_assemble(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, const coflux_interface_fluxes* ao,
+                       const coflux_sea_ice_state* ice, const coflux_ice_ocean_fluxes* io, coflux_net_ocean_fluxes* out, cudaStream_t st) {
+  REQUIRE(x && o && ao && out, "NULL argument");
+  REQUIRE(x->Qs.ptr && x->Ql.ptr && x->Mp.ptr, "exchange state Qs, Ql, Mp are required");
+  REQUIRE(ao->latent_heat.ptr && ao->sensible_heat.ptr && ao->water_vapor.ptr && ao->x_momentum.ptr && ao->y_momentum.ptr &&
+              ao->interface_temperature.ptr, "atmosphere-ocean interface fluxes are required");
+  REQUIRE(o->S.ptr, "ocean S is required");
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = sizeof(FT);
+  AssembleArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  fill_stress<FT>(c, o, ao, ice, io, out, a.s);
+  a.oS = view2d(o->S, g.Nz - 1, es); a.Ts = view2d(ao->interface_temperature, 0, es);
+  a.xQs = view2d(x->Qs, 0, es); a.xQl = view2d(x->Ql, 0, es); a.xMp = view2d(x->Mp, 0, es);
+  a.Qc = view2d(ao->sensible_heat, 0, es); a.Qv = view2d(ao->latent_heat, 0, es); a.Fv = view2d(ao->water_vapor, 0, es);
+  a.Qio = io ? view2d(io->interface_heat, 0, es) : DArr{nullptr, 0, 0};
+  a.salt_io = io ? view2d(io->salt, 0, es) : DArr{nullptr, 0, 0};
+  a.JT = view2d(out->T, 0, es); a.JS = view2d(out->S, 0, es); a.Qu = view2d(out->upwelling_longwave, 0, es);
+  a.Qal = view2d(out->downwelling_longwave, 0, es); a.Qts = view2d(out->downwelling_shortwave, 0, es);
+  a.J0 = view2d(out->penetrating_shortwave, 0, es);
+  a.P = dev_params<FT>(c);
+  assemble_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_assemble_net_ocean_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,
+                                                const coflux_interface_fluxes* ao, const coflux_sea_ice_state* ice,
+                                                const coflux_ice_ocean_fluxes* io, coflux_net_ocean_fluxes* out, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_assemble<double>(c, x, o, ao, ice, io, out, st) : do_assemble<float>(c, x, o, ao, ice, io, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2: fused update_state!
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_update_outputs* out, double time, cudaStream_t st) {
+  REQUIRE(in && out, "NULL argument");
+  REQUIRE(in->atmosphere && in->ocean, "atmosphere series and ocean surface are required");
+  REQUIRE(out->exchange && out->atmosphere_ocean && out->net_ocean, "exchange, atmosphere_ocean and net_ocean outputs are required");
+  REQUIRE(out->atmosphere_ocean->x_momentum.ptr && out->atmosphere_ocean->y_momentum.ptr,
+          "x_momentum / y_momentum outputs are required (the stress kernel reads them back)");
+  const size_t es = sizeof(FT);
+  FluxArgs<FT> a;
+  zero_args(a);
+  fill_geometry(c, a);
+  int rc = fill_interp<FT>(c, in->atmosphere, time, out->exchange, a);
+  if (rc) return rc;
+  rc = fill_ocean<FT>(c, in->ocean, a);
+  if (rc) return rc;
+  fill_interface_out<FT>(out->atmosphere_ocean, a);
+  const coflux_sea_ice_state* ice = in->sea_ice;
+  const coflux_ice_ocean_fluxes* io = in->ice_ocean;
+  a.conc = ice ? view2d(ice->concentration, 0, es) : DArr{nullptr, 0, 0};
+  a.Qio = io ? view2d(io->interface_heat, 0, es) : DArr{nullptr, 0, 0};
+  a.salt_io = io ? view2d(io->salt, 0, es) : DArr{nullptr, 0, 0};
+  coflux_net_ocean_fluxes* n = out->net_ocean;
+  a.JT = view2d(n->T, 0, es); a.JS = view2d(n->S, 0, es); a.Qu = view2d(n->upwelling_longwave, 0, es);
+  a.Qal = view2d(n->downwelling_longwave, 0, es); a.Qts = view2d(n->downwelling_shortwave, 0, es);
+  a.J0 = view2d(n->penetrating_shortwave, 0, es);
+  Profile& pf = c->prof;
+  if (pf.on && pf.pending == Profile::RING) { rc = profile_drain(c); if (rc) return rc; }
+  if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][0], st));
+  flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  rc = check_launch(c, 1);
+  if (rc) return rc;
+  if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][1], st));
+  StressArgs<FT> s;
+  memset(&s, 0, sizeof(s));
+  fill_stress<FT>(c, in->ocean, out->atmosphere_ocean, ice, io, n, s);
+  const coflux_grid_desc& g = c->cfg.grid;
+  stress_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(s);
+  rc = check_launch(c, 1);
+  if (rc) return rc;
+  if (pf.on) { CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][2], st)); pf.pending += 1; }
+  return COFLUX_OK;
+}
+extern "C" int coflux_update_state(coflux_ctx* c, const coflux_update_inputs* in, coflux_update_outputs* out, double time, void* stream) {
+  REQUIRE(c, "NULL context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_update<double>(c, in, out, time, st) : do_update<float>(c, in, out, time, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// end-to-end entry with HOST buffers
+// ---------------------------------------------------------------------------------------------
+static coflux_array plane_desc(void* p, int Nx, int halo) {
+  coflux_array a;
+  memset(&a, 0, sizeof(a));
+  a.ptr = p;
+  a.stride_i = 1; a.stride_j = Nx + 2 * halo; a.stride_k = 0; a.stride_n = 0;
+  a.off_i = halo; a.off_j = halo; a.off_k = 0;
+  return a;
+}
+extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series* atm, const coflux_host_step* step, double time,
+                                        int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  REQUIRE(c && atm && step, "NULL argument");
+  REQUIRE(step->ocean_u && step->ocean_v && step->ocean_T && step->ocean_S, "host ocean planes are required");
+  REQUIRE(step->net_u && step->net_v && step->net_T && step->net_S, "host net-flux planes are required");
+  REQUIRE(step->halo >= 2, "host planes need a halo of at least 2 cells");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = (c->cfg.dtype == COFLUX_F64) ? 8 : 4;
+  const int H = step->halo;
+  const size_t plane = (size_t)(g.Nx + 2 * H) * (size_t)(g.Ny + 2 * H) * es;
+  HostStage& s = c->stage;
+  if (s.halo != H || s.plane_bytes != plane) {
+    free_stage(s);
+    s.halo = H; s.plane_bytes = plane;
+    for (char*& p : s.in) CUDA_TRY(cudaMalloc(&p, plane));
+    for (char*& p : s.xch) CUDA_TRY(cudaMalloc(&p, plane));
+    for (char*& p : s.ao) CUDA_TRY(cudaMalloc(&p, plane));
+    for (char*& p : s.net) CUDA_TRY(cudaMalloc(&p, plane));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
+    for (cudaEvent_t& ev : s.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_k2, cudaEventDisableTiming));
+  }
+  const void* hin[4] = {step->ocean_u, step->ocean_v, step->ocean_T, step->ocean_S};
+  for (int k = 0; k < 4; ++k) CUDA_TRY(cudaMemcpyAsync(s.in[k], hin[k], plane, cudaMemcpyHostToDevice, s.stream));
+
+  coflux_ocean_surface ocean;
+  memset(&ocean, 0, sizeof(ocean));
+  // planes are the k = Nz-1 level: present them as 3-D parents with stride_k = 0
+  ocean.u = plane_desc(s.in[0], g.Nx, H); ocean.v = plane_desc(s.in[1], g.Nx, H);
+  ocean.T = plane_desc(s.in[2], g.Nx, H); ocean.S = plane_desc(s.in[3], g.Nx, H);
+  coflux_exchange_state xch;
+  coflux_array* xa[8] = {&xch.u, &xch.v, &xch.T, &xch.p, &xch.q, &xch.Qs, &xch.Ql, &xch.Mp};
+  for (int k = 0; k < 8; ++k) *xa[k] = plane_desc(s.xch[k], g.Nx, H);
+  coflux_interface_fluxes ao;
+  memset(&ao, 0, sizeof(ao));
+  ao.latent_heat = plane_desc(s.ao[0], g.Nx, H); ao.sensible_heat = plane_desc(s.ao[1], g.Nx, H);
+  ao.water_vapor = plane_desc(s.ao[2], g.Nx, H); ao.x_momentum = plane_desc(s.ao[3], g.Nx, H);
+  ao.y_momentum = plane_desc(s.ao[4], g.Nx, H); ao.interface_temperature = plane_desc(s.ao[5], g.Nx, H);
+  coflux_net_ocean_fluxes net;
+  coflux_array* na[8] = {&net.u, &net.v, &net.T, &net.S, &net.upwelling_longwave, &net.downwelling_longwave,
+                         &net.downwelling_shortwave, &net.penetrating_shortwave};
+  for (int k = 0; k < 8; ++k) *na[k] = plane_desc(s.net[k], g.Nx, H);
+  coflux_update_inputs in;
+  memset(&in, 0, sizeof(in));
+  in.atmosphere = atm; in.ocean = &ocean;
+  coflux_update_outputs out;
+  out.exchange = &xch; out.atmosphere_ocean = &ao; out.net_ocean = &net;
+  int rc = coflux_update_state(c, &in, &out, time, s.stream);
+  if (rc) return rc;
+  void* hout[4] = {step->net_u, step->net_v, step->net_T, step->net_S};
+  int64_t d2h = 0;
+  for (int k = 0; k < 4; ++k) { CUDA_TRY(cudaMemcpyAsync(hout[k], s.net[k], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
+  if (step->latent_heat) { CUDA_TRY(cudaMemcpyAsync(step->latent_heat, s.ao[0], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
+  if (step->sensible_heat) { CUDA_TRY(cudaMemcpyAsync(step->sensible_heat, s.ao[1], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
+  CUDA_TRY(cudaStreamSynchronize(s.stream));
+  if (h2d_bytes) *h2d_bytes = 4 * (int64_t)plane;
+  if (d2h_bytes) *d2h_bytes = d2h;
+  return COFLUX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU seam (implemented in a later milestone of this round)
+// ---------------------------------------------------------------------------------------------
+extern "C" int coflux_seam_export(coflux_ctx* c, void* handle_out) {
+  REQUIRE(c && handle_out, "NULL argument");
+  return fail(COFLUX_ERR_UNSUPPORTED, "seam push mode not built in this revision; use grid.ring = 1 (zero-message mode)");
+}
+extern "C" int coflux_seam_attach(coflux_ctx* c, const void* west, const void* east, int32_t rank, int32_t world) {
+  REQUIRE(c && west && east, "NULL argument");
+  (void)rank; (void)world;
+  return fail(COFLUX_ERR_UNSUPPORTED, "seam push mode not built in this revision; use grid.ring = 1 (zero-message mode)");
+}
+extern "C" int coflux_seam_detach(coflux_ctx* c) {
+  if (c) c->seam.attached = false;
+  return COFLUX_OK;
+}

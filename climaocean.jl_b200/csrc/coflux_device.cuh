@@ -1,0 +1,371 @@
+// coflux_device.cuh — device-side physics of the surface-flux path (sm_100a).
+//
+// One thread owns one surface cell; the whole similarity iteration lives in registers.
+// This is the product implementation (not shared with oracle/): compared with the literal
+// restatement it hoists everything that is invariant under the fixed-point iteration
+// (atmosphere/surface thermodynamic states, surface humidity, Δθ, Δq, ν(T_s), ln-free
+// constants), evaluates only the taken branch of each stability function, and evaluates the
+// scalar similarity profile once when the θ and q roughness parameterisations coincide.
+// None of these change a rounded value that the reference formulas (SURVEY.md Appendix A;
+// parameter surface /root/reference/src/OMIPConfigurations/omip_simulation.jl:40-113) define.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include "../../include/coflux.h"
+
+namespace coflux {
+
+// ---------------------------------------------------------------------------------------------
+// libm dispatch (IEEE-accurate CUDA math library entry points; no fast-math anywhere)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct M;
+template <> struct M<double> {
+  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double cbrt(double x) { return ::cbrt(x); }
+  static __device__ __forceinline__ double atan(double x) { return ::atan(x); }
+  static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
+  static __device__ __forceinline__ double trunc(double x) { return ::trunc(x); }
+  static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
+  static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+  static __device__ __forceinline__ double inf() { return CUDART_INF; }
+  static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
+};
+template <> struct M<float> {
+  static __device__ __forceinline__ float log(float x) { return ::logf(x); }
+  static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
+  static __device__ __forceinline__ float cbrt(float x) { return ::cbrtf(x); }
+  static __device__ __forceinline__ float atan(float x) { return ::atanf(x); }
+  static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+  static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+  static __device__ __forceinline__ float floor(float x) { return ::floorf(x); }
+  static __device__ __forceinline__ float trunc(float x) { return ::truncf(x); }
+  static __device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
+  static __device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
+  static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+  static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device parameter block (built once per context on the host, in FT arithmetic)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct ThermoC {
+  FT R_d, R_v, eps, cp_d, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_0, T_tr, p_tr, T_fr, T_in;
+  FT Rd_over_Rv;
+};
+template <typename FT> struct Visc { int kind; FT nu, c0, c1, c2, c3; };
+template <typename FT> struct MomRough {
+  int kind, waves;
+  FT fixed, alpha, a1, a2, umax, amin, beta_s, lmax, g;
+  Visc<FT> visc;
+};
+template <typename FT> struct ScaRough { int kind; FT fixed, A, b, lmax; Visc<FT> visc; };
+template <typename FT> struct FluxP {
+  int formulation, stability, form, velocity, stop_kind, maxit, itemp, same_scalar;
+  FT tol, kappa, beta, ugmin, init, ly_umin, skin_max_dT;
+  MomRough<FT> mr;
+  ScaRough<FT> tr, qr;
+};
+template <typename FT> struct IceOceanP {
+  int heat_flux, friction;
+  FT um_star, T0, slope, alpha_h, alpha_s, ustar_const, ustar_min, rho_i, L_f, Cd, k_ice, h_c;
+};
+template <typename FT> struct DevParams {
+  ThermoC<FT> th;
+  FT h, hbl, g;
+  FT rho0, c0, rhof, Smin, wmf_alpha, T_offset;  // T_offset: 273.15 if ocean T in °C else 0
+  FT sigma, alb_o, emis_o, emis_i, alb_i;
+  int sw_pen;
+  FluxP<FT> ao, ai;
+  IceOceanP<FT> io;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Thermodynamics (A1, A2)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct Thermo { FT rho, cp_m, q_vap, T_v; };
+
+template <typename FT>
+__device__ __forceinline__ FT psat_generic(const ThermoC<FT>& c, FT T, FT LH_0, FT dcp) {
+  return c.p_tr * M<FT>::pow(T / c.T_tr, dcp / c.R_v) *
+         M<FT>::exp((LH_0 - dcp * c.T_0) / c.R_v * (FT(1) / c.T_tr - FT(1) / T));
+}
+template <typename FT> __device__ __forceinline__ FT liquid_fraction(const ThermoC<FT>& c, FT T) {
+  if (T > c.T_fr) return FT(1);
+  if (T <= c.T_in) return FT(0);
+  return (T - c.T_in) / (c.T_fr - c.T_in);
+}
+template <typename FT> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q) {
+  FT lam = liquid_fraction(c, T);
+  FT LH_0 = lam * c.LH_v0 + (FT(1) - lam) * c.LH_s0;
+  FT dcp = lam * (c.cp_v - c.cp_l) + (FT(1) - lam) * (c.cp_v - c.cp_i);
+  FT ps = psat_generic(c, T, LH_0, dcp);
+  FT denom = p - ps;
+  FT q_vs = (denom > FT(0)) ? c.Rd_over_Rv * (FT(1) - q) * ps / denom : M<FT>::inf();
+  FT q_c = M<FT>::max(q - q_vs, FT(0));
+  FT q_liq = lam * q_c, q_ice = (FT(1) - lam) * q_c;
+  FT R_m = c.R_d * (FT(1) + (c.eps - FT(1)) * q - c.eps * q_c);
+  Thermo<FT> s;
+  s.rho = p / (R_m * T);
+  s.cp_m = c.cp_d + (c.cp_v - c.cp_d) * q + (c.cp_l - c.cp_v) * q_liq + (c.cp_i - c.cp_v) * q_ice;
+  s.q_vap = q - q_liq - q_ice;
+  s.T_v = T * R_m / c.R_d;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stability functions (A5) — only the taken branch is evaluated
+// ---------------------------------------------------------------------------------------------
+template <typename FT> __device__ __forceinline__ FT psi_conv_cbrt(FT y) {  // convective (cube-root) limb shared by Edson ψu, ψθ
+  const FT rt3 = M<FT>::sqrt(FT(3));
+  return FT(1.5) * M<FT>::log((FT(1) + y + y * y) / FT(3)) - rt3 * M<FT>::atan((FT(1) + FT(2) * y) / rt3) + M<FT>::pi() / rt3;
+}
+template <typename FT> __device__ __forceinline__ FT psi_businger_momentum(FT x) {  // Kansas limb, x = (1 − γ ζ)^{1/4}
+  return FT(2) * M<FT>::log((FT(1) + x) / FT(2)) + M<FT>::log((FT(1) + x * x) / FT(2)) - FT(2) * M<FT>::atan(x) + M<FT>::pi() / FT(2);
+}
+template <typename FT> __device__ FT psi_momentum(int kind, FT z) {
+  if (kind == COFLUX_STABILITY_EDSON) {
+    if (z >= FT(0)) {
+      FT dz = M<FT>::min(FT(50), FT(0.35) * z);
+      return -FT(0.7) * z - FT(0.75) * (z - FT(5) / FT(0.35)) * M<FT>::exp(-dz) - FT(0.75) * FT(5) / FT(0.35);
+    }
+    FT x = M<FT>::sqrt(M<FT>::sqrt(FT(1) - FT(15) * z));
+    FT psik = psi_businger_momentum(x);
+    FT psic = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(10.15) * z));
+    FT f = z * z / (FT(1) + z * z);
+    return (FT(1) - f) * psik + f * psic;
+  }
+  if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
+  // SHEBA_PAULSON and LARGE_YEAGER share the Paulson unstable limb
+  if (z < FT(0)) return psi_businger_momentum(M<FT>::sqrt(M<FT>::sqrt(FT(1) - FT(16) * z)));
+  if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
+  // Grachev et al. (2007) SHEBA, stable
+  const FT a = FT(5), b = FT(5) / FT(6.5);   // a_m, b_m = a_m/6.5
+  const FT rt3 = M<FT>::sqrt(FT(3));
+  FT x = M<FT>::cbrt(FT(1) + z);
+  FT B = M<FT>::cbrt((FT(1) - b) / b);
+  FT p1 = -FT(3) * a * (x - FT(1)) / b;
+  FT p2 = a * B / (FT(2) * b) *
+          (FT(2) * M<FT>::log((x + B) / (FT(1) + B)) - M<FT>::log((x * x - B * x + B * B) / (FT(1) - B + B * B)) +
+           FT(2) * rt3 * (M<FT>::atan((FT(2) * x - B) / (rt3 * B)) - M<FT>::atan((FT(2) - B) / (rt3 * B))));
+  return p1 + p2;
+}
+template <typename FT> __device__ FT psi_scalar(int kind, FT z) {
+  if (kind == COFLUX_STABILITY_EDSON) {
+    if (z >= FT(0)) {
+      FT dz = M<FT>::min(FT(50), FT(0.35) * z);
+      return -M<FT>::pow(FT(1) + FT(2) / FT(3) * z, FT(1.5)) - FT(2) / FT(3) * (z - FT(14.28)) * M<FT>::exp(-dz) - FT(8.525);
+    }
+    FT x = M<FT>::sqrt(FT(1) - FT(15) * z);
+    FT psik = FT(2) * M<FT>::log((FT(1) + x) / FT(2));
+    FT psic = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(34.15) * z));
+    FT f = z * z / (FT(1) + z * z);
+    return (FT(1) - f) * psik + f * psic;
+  }
+  if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
+  if (z < FT(0)) return FT(2) * M<FT>::log((FT(1) + M<FT>::sqrt(FT(1) - FT(16) * z)) / FT(2));
+  if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
+  const FT a = FT(5), b = FT(5), c = FT(3);
+  FT B = M<FT>::sqrt(c * c - FT(4));
+  FT p1 = -b / FT(2) * M<FT>::log(FT(1) + c * z + z * z);
+  FT p2 = (-a / B + b * c / (FT(2) * B)) *
+          (M<FT>::log((FT(2) * z + c - B) / (FT(2) * z + c + B)) - M<FT>::log((c - B) / (c + B)));
+  return p1 + p2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Roughness lengths (A6)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> __device__ __forceinline__ FT air_viscosity(const Visc<FT>& v, FT T) {
+  if (v.kind == COFLUX_VISCOSITY_CONSTANT) return v.nu;
+  FT Tp = T - FT(273.15);
+  return v.c0 + v.c1 * Tp + v.c2 * Tp * Tp + v.c3 * Tp * Tp * Tp;
+}
+template <typename FT>
+__device__ __forceinline__ FT momentum_roughness(const MomRough<FT>& r, FT ustar, FT U, FT nu) {
+  if (r.kind == COFLUX_ROUGHNESS_FIXED) return r.fixed;
+  FT alpha = r.alpha;
+  if (r.waves == COFLUX_WAVES_WIND_DEPENDENT) alpha = M<FT>::max(r.a1 * M<FT>::min(U, r.umax) + r.a2, r.amin);
+  FT lR = (ustar == FT(0)) ? r.lmax : r.beta_s * nu / ustar;
+  return M<FT>::min(alpha * ustar * ustar / r.g + lR, r.lmax);
+}
+template <typename FT>
+__device__ __forceinline__ FT scalar_roughness(const ScaRough<FT>& r, FT lu, FT ustar, FT nu) {
+  if (r.kind == COFLUX_ROUGHNESS_FIXED) return r.fixed;
+  FT Rstar = lu * ustar / nu;
+  FT lq = (Rstar == FT(0)) ? FT(0) : r.A / M<FT>::pow(Rstar, r.b);
+  return M<FT>::min(lq, r.lmax);
+}
+
+// χ = ln(h/ℓ) − ψ(h/L) [+ ψ(ℓ/L)], with ψ(h/L) supplied (it is shared between θ and q)
+template <typename FT, bool SCALAR>
+__device__ __forceinline__ FT similarity_profile(int form, int stab, FT h, FT l, FT L, FT psi_h) {
+  FT chi = M<FT>::log(h / l) - psi_h;
+  if (form == COFLUX_PROFILE_LOGARITHMIC) {
+    FT th = l / L;
+    chi += SCALAR ? psi_scalar(stab, th) : psi_momentum(stab, th);
+  }
+  return chi;
+}
+
+template <typename FT> __device__ __forceinline__ FT ly_cdn(FT U) {
+  if (U >= FT(33)) return FT(2.34e-3);
+  FT U2 = U * U, U6 = U2 * U2 * U2;
+  return FT(1e-3) * (FT(2.7) / U + FT(0.142) + U / FT(13.09) - FT(3.14807e-10) * U6);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cell interface solve (A3, A4, A7; a7 with SKIN temperature)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct CellIn {
+  FT ua, va, Ta, pa, qa, Qs, Ql;
+  FT us, vs;      // surface (ocean or ice) velocity at the cell centre
+  FT Ts0;         // initial interface temperature [K] (ocean: bulk T; ice: previous T_top)
+  FT So;          // ocean salinity (Raoult factor); unused over ice
+  FT h_ice, S_ice, albedo;
+};
+template <typename FT> struct CellOut {
+  FT ustar, tstar, qstar, Ts;
+  FT rho_a, cp_a, du, dv;
+  int it;
+};
+
+template <typename FT> struct SurfaceState { FT qs, dq, dtheta, T_v, q_vap, nu_m, nu_t, nu_q; };
+
+template <typename FT, int SURF>
+__device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P, const FluxP<FT>& F,
+                                                          const Thermo<FT>& atm, FT pa, FT theta_a, FT x, FT Ts) {
+  const ThermoC<FT>& c = P.th;
+  SurfaceState<FT> s;
+  FT ps = (SURF == 0) ? psat_generic(c, Ts, c.LH_v0, c.cp_v - c.cp_l) : psat_generic(c, Ts, c.LH_s0, c.cp_v - c.cp_i);
+  FT qstar = ps / (atm.rho * c.R_v * Ts);
+  s.qs = qstar * x;
+  s.dq = atm.q_vap - s.qs;
+  s.dtheta = theta_a - Ts;
+  Thermo<FT> surf = phase_equil_pTq(c, pa, Ts, s.qs);
+  s.T_v = surf.T_v;
+  s.q_vap = surf.q_vap;
+  s.nu_m = air_viscosity(F.mr.visc, Ts);
+  s.nu_t = air_viscosity(F.tr.visc, Ts);
+  s.nu_q = air_viscosity(F.qr.visc, Ts);
+  return s;
+}
+
+template <typename FT, int SURF>
+__device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const CellIn<FT>& in, CellOut<FT>& out) {
+  const ThermoC<FT>& c = P.th;
+  const FT g = P.g, h = P.h, kappa = F.kappa;
+  Thermo<FT> atm = phase_equil_pTq(c, in.pa, in.Ta, in.qa);
+  FT du, dv;
+  if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = in.ua - in.us; dv = in.va - in.vs; }
+  else { du = in.ua; dv = in.va; }
+  FT x = FT(1);
+  if (SURF == 0) { FT s = in.So / FT(1000); x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s); }
+  const FT theta_a = in.Ta + g * h / atm.cp_m;
+  const FT delta = c.eps - FT(1);
+  const FT du2dv2 = du * du + dv * dv;
+
+  FT Ts = in.Ts0;
+  SurfaceState<FT> S = surface_state<FT, SURF>(P, F, atm, in.pa, theta_a, x, Ts);
+
+  FT ustar = F.init, tstar = F.init, qstar = F.init;
+  const bool ly = (F.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER);
+  FT U_ly = FT(0), rcdn_ly = FT(0);
+  const FT lnh10 = ly ? M<FT>::log(h / FT(10)) : FT(0);
+  if (ly) {
+    U_ly = M<FT>::max(M<FT>::sqrt(du2dv2), F.ly_umin);
+    FT cdn = ly_cdn(U_ly);
+    FT rcdn = M<FT>::sqrt(cdn);
+    FT chn = ((S.dtheta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
+    FT cen = FT(34.6e-3) * rcdn;
+    rcdn_ly = rcdn;
+    ustar = rcdn * U_ly; tstar = chn / rcdn * S.dtheta; qstar = cen / rcdn * S.dq;
+  }
+
+  const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+  int it = 0;
+  bool go = fixed ? (F.maxit > 0) : true;
+  while (go) {
+    const FT u0 = ustar, t0 = tstar, q0 = qstar;
+    if (SURF == 1 && F.itemp == COFLUX_TEMPERATURE_SKIN) {
+      // conductive flux balance through the slab (row a7)
+      FT Tb = P.io.T0 - P.io.slope * in.S_ice + P.T_offset;
+      FT Tm = P.io.T0 + P.T_offset;
+      FT Ls = c.LH_s0 + (c.cp_v - c.cp_i) * (in.Ta - c.T_0);
+      FT Qu = P.emis_i * P.sigma * Ts * Ts * Ts * Ts;
+      FT Qd = -(FT(1) - in.albedo) * in.Qs - P.emis_i * in.Ql;
+      FT Qc = -atm.rho * atm.cp_m * u0 * t0;
+      FT Qv = -atm.rho * Ls * u0 * q0;
+      FT Qa = Qv + Qu + Qc + Qd;
+      FT Tstar = Tb - Qa * in.h_ice / P.io.k_ice;
+      if (Tstar != Tstar) Tstar = Ts;
+      Tstar = M<FT>::max(FT(0), Tstar);
+      FT Tnew = (in.h_ice >= P.io.h_c) ? Tstar : Tb;
+      FT dT = Tnew - Ts;
+      FT adT = M<FT>::min(F.skin_max_dT, M<FT>::abs(dT));
+      FT sgn = (dT > FT(0)) ? FT(1) : ((dT < FT(0)) ? FT(-1) : FT(0));
+      Ts = M<FT>::min(Ts + adT * sgn, Tm);
+      S = surface_state<FT, SURF>(P, F, atm, in.pa, theta_a, x, Ts);
+    }
+    const FT bstar = g / S.T_v * (t0 * (FT(1) + delta * S.q_vap) + delta * S.T_v * q0);
+    if (ly) {
+      FT zeta = kappa * bstar * h / (u0 * u0);
+      zeta = M<FT>::max(FT(-10), M<FT>::min(FT(10), zeta));
+      FT psim = psi_momentum(COFLUX_STABILITY_LARGE_YEAGER, zeta);
+      FT psih = psi_scalar(COFLUX_STABILITY_LARGE_YEAGER, zeta);
+      FT U10N = U_ly / (FT(1) + rcdn_ly / kappa * (lnh10 - psim));
+      U10N = M<FT>::max(U10N, F.ly_umin);
+      FT cdn = ly_cdn(U10N);
+      FT rcdn = M<FT>::sqrt(cdn);
+      FT cen = FT(34.6e-3) * rcdn;
+      FT chn = ((zeta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
+      FT xm = FT(1) + rcdn / kappa * (lnh10 - psim);
+      FT cd = cdn / (xm * xm);
+      FT rr = M<FT>::sqrt(cd / cdn);
+      FT ch = chn / (FT(1) + chn / (kappa * rcdn) * (lnh10 - psih)) * rr;
+      FT ce = cen / (FT(1) + cen / (kappa * rcdn) * (lnh10 - psih)) * rr;
+      rcdn_ly = rcdn;
+      FT rcd = M<FT>::sqrt(cd);
+      ustar = rcd * U_ly; tstar = ch / rcd * S.dtheta; qstar = ce / rcd * S.dq;
+    } else {
+      const FT Jb = -u0 * bstar;
+      FT UG = F.beta * M<FT>::cbrt(Jb * P.hbl);
+      UG = M<FT>::max(UG, F.ugmin);
+      const FT U = M<FT>::sqrt(du2dv2 + UG * UG);
+      if (U == FT(0)) {  // documented calm-cell guard
+        ustar = tstar = qstar = FT(0);
+      } else {
+        const FT lu = momentum_roughness(F.mr, u0, U, S.nu_m);
+        const FT lq = scalar_roughness(F.qr, lu, u0, S.nu_q);
+        const FT Lstar = (bstar == FT(0)) ? M<FT>::inf() : u0 * u0 / (kappa * bstar);
+        const FT zeta = h / Lstar;
+        const FT psi_hm = psi_momentum(F.stability, zeta);
+        const FT psi_hs = psi_scalar(F.stability, zeta);
+        const FT chi_u = kappa / similarity_profile<FT, false>(F.form, F.stability, h, lu, Lstar, psi_hm);
+        const FT chi_q = kappa / similarity_profile<FT, true>(F.form, F.stability, h, lq, Lstar, psi_hs);
+        FT chi_t = chi_q;
+        if (!F.same_scalar) {
+          const FT lt = scalar_roughness(F.tr, lu, u0, S.nu_t);
+          chi_t = kappa / similarity_profile<FT, true>(F.form, F.stability, h, lt, Lstar, psi_hs);
+        }
+        ustar = chi_u * U; tstar = chi_t * S.dtheta; qstar = chi_q * S.dq;
+      }
+    }
+    ++it;
+    if (fixed) {
+      go = it < F.maxit;
+    } else {
+      FT drift = M<FT>::abs(ustar - u0) + M<FT>::abs(tstar - t0) + M<FT>::abs(qstar - q0);
+      go = !((drift < F.tol) || (it >= F.maxit));
+    }
+  }
+  out.ustar = ustar; out.tstar = tstar; out.qstar = qstar; out.Ts = Ts;
+  out.rho_a = atm.rho; out.cp_a = atm.cp_m; out.du = du; out.dv = dv; out.it = it;
+}
+
+}  // namespace coflux

@@ -1,0 +1,385 @@
+// coflux_kernels.cuh — the CUDA kernels of the surface-flux path (sm_100a).
+//
+//   flux_kernel<FT, SURF, INTERP, SOLVE, ASSEMBLE>
+//       (·,0,1,0,0)  interpolate_atmosphere_state!           (row a3)
+//       (·,0,0,1,0)  compute_atmosphere_ocean_fluxes!        (rows a4–a6)
+//       (·,1,0,1,0)  compute_atmosphere_sea_ice_fluxes!      (row a7)
+//       (·,0,1,1,1)  fused update_state!: a3 + a4/a5 + tracer/radiative part of a9
+//   stress_kernel<FT>        centre→face momentum part of a9 (needs the neighbours' ρτ)
+//   assemble_kernel<FT>      stand-alone compute_net_ocean_fluxes! (row a9)
+//   ice_ocean_kernel<FT>     compute_sea_ice_ocean_fluxes! (row a8): frazil column sweep etc.
+//
+// Thread mapping: one thread per surface cell of the ring-extended surface, linearised with i
+// fastest, so a warp reads/writes 32 consecutive elements of every halo-padded column-major
+// parent (full 32 B sectors; the arbitrary halo offset of Julia-owned parents rules out 16 B
+// vector or TMA box loads: (Nx+2H)·sizeof(FT) is in general not a multiple of 16).  All input
+// loads of a cell are issued before the solve (ld.global.nc), the iteration runs in registers,
+// all outputs are written once at the end.
+#pragma once
+#include "coflux_device.cuh"
+
+namespace coflux {
+
+struct DArr {      // 2-D view: element (i,j) at p + (i*si + j*sj) elements; p == nullptr → absent
+  char* p;
+  int64_t si, sj;
+};
+struct DSeries {   // two bracketing time levels of a series
+  char* p1;
+  char* p2;
+  int64_t si, sj;
+};
+struct DCol {      // 3-D view for column sweeps
+  char* p;
+  int64_t si, sj, sk;
+};
+
+template <typename FT> __device__ __forceinline__ FT ldg(const DArr& a, int i, int j) {
+  return __ldg(reinterpret_cast<const FT*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj));
+}
+template <typename FT> __device__ __forceinline__ void stg(const DArr& a, int i, int j, FT v) {
+  if (a.p) reinterpret_cast<FT*>(a.p)[(int64_t)i * a.si + (int64_t)j * a.sj] = v;
+}
+__device__ __forceinline__ bool is_active(const DArr& m, int i, int j) {
+  if (!m.p) return true;
+  return __ldg(reinterpret_cast<const uint8_t*>(m.p) + ((int64_t)i * m.si + (int64_t)j * m.sj)) != 0;
+}
+
+template <typename FT> struct FluxArgs {
+  int nxr, nyr, ring, Nx, Ny;
+  long long ncell;
+  // a3 inputs
+  DSeries su, sv, sT, sq, sp, sQs, sQl, srain, ssnow;
+  DArr fi, fj, cs, sn;
+  FT nfrac;
+  // exchange state (written when INTERP, read otherwise)
+  DArr xu, xv, xT, xp, xq, xQs, xQl, xMp;
+  // surface state: ocean (u,v,T,S at k = Nz-1) or ice (u, v, T_top)
+  DArr ou, ov, oT, oS, mask;
+  DArr ih, iS, ialb, iconc;   // sea ice (SURF == 1)
+  // interface outputs
+  DArr Qv, Qc, Fv, rtx, rty, Tsout, ust, tst, qst, iters, Ttop_out;
+  // assembly (tracer / radiative part)
+  DArr conc, Qio, salt_io;
+  DArr JT, JS, Qu, Qal, Qts, J0;
+  // seam push (multi-GPU, ring == 0): last column of ρτx stored to the east neighbour
+  char* seam_east;     // peer pointer, Ny elements (or nullptr)
+  DevParams<FT> P;
+};
+
+template <typename FT>
+__device__ __forceinline__ FT interp_series(const DSeries& s, int i0, int j0, int i1, int j1, FT w00, FT w01, FT w10,
+                                            FT w11, FT nfrac) {
+  const int64_t o00 = (int64_t)i0 * s.si + (int64_t)j0 * s.sj, o01 = (int64_t)i0 * s.si + (int64_t)j1 * s.sj;
+  const int64_t o10 = (int64_t)i1 * s.si + (int64_t)j0 * s.sj, o11 = (int64_t)i1 * s.si + (int64_t)j1 * s.sj;
+  const FT* a1 = reinterpret_cast<const FT*>(s.p1);
+  const FT* a2 = reinterpret_cast<const FT*>(s.p2);
+  FT v100 = __ldg(a1 + o00), v101 = __ldg(a1 + o01), v110 = __ldg(a1 + o10), v111 = __ldg(a1 + o11);
+  FT v200 = __ldg(a2 + o00), v201 = __ldg(a2 + o01), v210 = __ldg(a2 + o10), v211 = __ldg(a2 + o11);
+  FT p1 = w00 * v100 + w01 * v101 + w10 * v110 + w11 * v111;
+  FT p2 = w00 * v200 + w01 * v201 + w10 * v210 + w11 * v211;
+  return p2 * nfrac + p1 * (FT(1) - nfrac);
+}
+
+// tracer / radiative part of the net ocean flux assembly for one interior cell (A9)
+template <typename FT>
+__device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool act, FT conc, FT So, FT TsK, FT Qs, FT Ql,
+                                                 FT Mp, FT Qc, FT Qv, FT Mv, FT Qio, FT salt_io, FT& JT, FT& JS, FT& Qu,
+                                                 FT& Qal, FT& Qts, FT& J0) {
+  const FT rho0inv = FT(1) / P.rho0, rhofinv = FT(1) / P.rhof;
+  Qu = P.emis_o * P.sigma * TsK * TsK * TsK * TsK;
+  Qal = -P.emis_o * Ql;
+  Qts = -(FT(1) - P.alb_o) * Qs;
+  const FT Qss = P.sw_pen ? FT(0) : Qts;
+  const FT SQ = Qu + Qc + Qv + Qal + Qss;
+  FT SF = -Mp * rhofinv;
+  SF += Mv * rhofinv;
+  const FT JTao = SQ * rho0inv / P.c0;
+  FT JSao = -So * SF;
+  if (So < P.Smin && JSao > FT(0)) JSao = FT(0);
+  JT = (FT(1) - conc) * JTao + Qio * rho0inv / P.c0;
+  JS = (FT(1) - conc) * JSao + salt_io * conc;
+  J0 = (FT(1) - conc) * Qts * rho0inv / P.c0;
+  if (!act) { JT = JS = J0 = FT(0); Qu = Qal = Qts = FT(0); }
+}
+
+template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE>
+__global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.ncell) return;
+  const int jj = (int)(idx / a.nxr);
+  const int ii = (int)(idx - (long long)jj * a.nxr);
+  const int i = ii - a.ring, j = jj - a.ring;
+
+  FT ua, va, Ta, pa, qa, Qs, Ql, Mp;
+  if (INTERP) {
+    const FT fi = ldg<FT>(a.fi, i, j), fj = ldg<FT>(a.fj, i, j);
+    const int i0 = (int)M<FT>::trunc(fi), j0 = (int)M<FT>::trunc(fj);
+    const int i1 = i0 + ((fi > FT(0)) - (fi < FT(0))), j1 = j0 + ((fj > FT(0)) - (fj < FT(0)));
+    const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
+    const FT w00 = (FT(1) - xi) * (FT(1) - eta), w01 = (FT(1) - xi) * eta, w10 = xi * (FT(1) - eta), w11 = xi * eta;
+    ua = interp_series<FT>(a.su, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    va = interp_series<FT>(a.sv, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    Ta = interp_series<FT>(a.sT, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    qa = interp_series<FT>(a.sq, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    pa = interp_series<FT>(a.sp, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    Qs = interp_series<FT>(a.sQs, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    Ql = interp_series<FT>(a.sQl, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    Mp = FT(0);
+    if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    if (a.cs.p && a.sn.p) {
+      const FT cs = ldg<FT>(a.cs, i, j), sn = ldg<FT>(a.sn, i, j);
+      const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
+      ua = ur; va = vr;
+    }
+    stg<FT>(a.xu, i, j, ua); stg<FT>(a.xv, i, j, va); stg<FT>(a.xT, i, j, Ta); stg<FT>(a.xp, i, j, pa);
+    stg<FT>(a.xq, i, j, qa); stg<FT>(a.xQs, i, j, Qs); stg<FT>(a.xQl, i, j, Ql); stg<FT>(a.xMp, i, j, Mp);
+  } else {
+    ua = ldg<FT>(a.xu, i, j); va = ldg<FT>(a.xv, i, j); Ta = ldg<FT>(a.xT, i, j); pa = ldg<FT>(a.xp, i, j);
+    qa = ldg<FT>(a.xq, i, j); Qs = ldg<FT>(a.xQs, i, j); Ql = ldg<FT>(a.xQl, i, j);
+    Mp = (ASSEMBLE && a.xMp.p) ? ldg<FT>(a.xMp, i, j) : FT(0);
+  }
+  if (!SOLVE) return;
+
+  const DevParams<FT>& P = a.P;
+  CellIn<FT> in;
+  in.ua = ua; in.va = va; in.Ta = Ta; in.pa = pa; in.qa = qa; in.Qs = Qs; in.Ql = Ql;
+  in.us = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+  in.vs = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+  const FT Tunits = ldg<FT>(a.oT, i, j);
+  in.Ts0 = Tunits + P.T_offset;
+  in.So = (SURF == 0) ? ldg<FT>(a.oS, i, j) : FT(0);
+  bool act = is_active(a.mask, i, j);
+  if (SURF == 1) {
+    in.h_ice = ldg<FT>(a.ih, i, j);
+    in.S_ice = ldg<FT>(a.iS, i, j);
+    in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+    const FT conc = ldg<FT>(a.iconc, i, j);
+    act = act && (conc > FT(0)) && (in.h_ice > FT(0));
+  } else {
+    in.h_ice = in.S_ice = in.albedo = FT(0);
+  }
+
+  FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0), Tsout = Tunits, us = FT(0), ts = FT(0), qs = FT(0);
+  int its = 0;
+  if (act) {
+    CellOut<FT> o;
+    if (SURF == 0) solve_cell<FT, 0>(P, P.ao, in, o);
+    else solve_cell<FT, 1>(P, P.ai, in, o);
+    const FT dU = M<FT>::sqrt(o.du * o.du + o.dv * o.dv);
+    const FT taux = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.du / dU;
+    const FT tauy = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.dv / dU;
+    const ThermoC<FT>& c = P.th;
+    const FT LH = (SURF == 0) ? c.LH_v0 + (c.cp_v - c.cp_l) * (Ta - c.T_0) : c.LH_s0 + (c.cp_v - c.cp_i) * (Ta - c.T_0);
+    Qv = -o.rho_a * o.ustar * o.qstar * LH;
+    Qc = -o.rho_a * o.cp_a * o.ustar * o.tstar;
+    Fv = -o.rho_a * o.ustar * o.qstar;
+    rtx = o.rho_a * taux; rty = o.rho_a * tauy;
+    Tsout = o.Ts - P.T_offset;
+    us = o.ustar; ts = o.tstar; qs = o.qstar; its = o.it;
+  }
+  stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
+  stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tsout);
+  stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
+  if (SURF == 1) stg<FT>(a.Ttop_out, i, j, Tsout);
+  if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = its;
+  if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
+
+  if (ASSEMBLE) {
+    if (i >= 0 && i < a.Nx && j >= 0 && j < a.Ny) {
+      const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
+      const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
+      const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
+      FT JT, JS, Qu, Qal, Qts, J0;
+      assemble_tracers<FT>(P, is_active(a.mask, i, j), conc, in.So, Tsout + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio,
+                           JT, JS, Qu, Qal, Qts, J0);
+      stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
+      stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// centre → face momentum fluxes (A9)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct StressArgs {
+  int Nx, Ny, wrap_x;      // wrap_x: i-1 at i == 0 → Nx-1 (single-slab periodic, ring == 0)
+  DArr rtx, rty, conc, tx_io, ty_io, mask;
+  DArr taux, tauy;
+  const char* seam_west;   // ρτx of the west neighbour's last column (Ny elements), or nullptr
+  FT rho0;
+};
+template <typename FT>
+__device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, int j, FT& tx, FT& ty) {
+  const FT rho0inv = FT(1) / a.rho0;
+  const int iw = (a.wrap_x && i == 0) ? a.Nx - 1 : i - 1;
+  const FT rtx_c = ldg<FT>(a.rtx, i, j);
+  const FT rtx_w = (a.seam_west && i == 0) ? __ldg(reinterpret_cast<const FT*>(a.seam_west) + j) : ldg<FT>(a.rtx, iw, j);
+  const FT rty_c = ldg<FT>(a.rty, i, j), rty_s = ldg<FT>(a.rty, i, j - 1);
+  FT cx = FT(0), cy = FT(0);
+  if (a.conc.p) {
+    const FT c = ldg<FT>(a.conc, i, j);
+    cx = FT(0.5) * (ldg<FT>(a.conc, iw, j) + c);
+    cy = FT(0.5) * (ldg<FT>(a.conc, i, j - 1) + c);
+  }
+  const FT txao = (rtx_w + rtx_c) * FT(0.5) * rho0inv;
+  const FT tyao = (rty_s + rty_c) * FT(0.5) * rho0inv;
+  const FT txio = a.tx_io.p ? ldg<FT>(a.tx_io, i, j) * rho0inv * cx : FT(0);
+  const FT tyio = a.ty_io.p ? ldg<FT>(a.ty_io, i, j) * rho0inv * cy : FT(0);
+  tx = (FT(1) - cx) * txao + txio;
+  ty = (FT(1) - cy) * tyao + tyio;
+  const bool act = is_active(a.mask, i, j);
+  if (!act || !is_active(a.mask, iw, j)) tx = FT(0);
+  if (!act || !is_active(a.mask, i, j - 1)) ty = FT(0);
+}
+template <typename FT> __global__ void __launch_bounds__(256) stress_kernel(const __grid_constant__ StressArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.Nx * a.Ny) return;
+  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  FT tx, ty;
+  assemble_stress<FT>(a, i, j, tx, ty);
+  stg<FT>(a.taux, i, j, tx);
+  stg<FT>(a.tauy, i, j, ty);
+}
+
+// stand-alone compute_net_ocean_fluxes! (reads the interface fluxes back from memory)
+template <typename FT> struct AssembleArgs {
+  StressArgs<FT> s;
+  DArr oS, Ts, xQs, xQl, xMp, Qc, Qv, Fv, Qio, salt_io;
+  DArr JT, JS, Qu, Qal, Qts, J0;
+  DevParams<FT> P;
+};
+template <typename FT> __global__ void __launch_bounds__(256) assemble_kernel(const __grid_constant__ AssembleArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.s.Nx * a.s.Ny) return;
+  const int j = (int)(idx / a.s.Nx), i = (int)(idx - (long long)j * a.s.Nx);
+  const FT conc = a.s.conc.p ? ldg<FT>(a.s.conc, i, j) : FT(0);
+  const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
+  const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
+  FT JT, JS, Qu, Qal, Qts, J0;
+  assemble_tracers<FT>(a.P, is_active(a.s.mask, i, j), conc, ldg<FT>(a.oS, i, j), ldg<FT>(a.Ts, i, j) + a.P.T_offset,
+                       ldg<FT>(a.xQs, i, j), ldg<FT>(a.xQl, i, j), ldg<FT>(a.xMp, i, j), ldg<FT>(a.Qc, i, j),
+                       ldg<FT>(a.Qv, i, j), ldg<FT>(a.Fv, i, j), Qio, sio, JT, JS, Qu, Qal, Qts, J0);
+  FT tx, ty;
+  assemble_stress<FT>(a.s, i, j, tx, ty);
+  stg<FT>(a.s.taux, i, j, tx); stg<FT>(a.s.tauy, i, j, ty);
+  stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
+  stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sea-ice–ocean fluxes (A10): quadratic stress at the faces, frazil column sweep, interface heat
+// (ice bath or three-equation), salt flux from thickness change.  HBM-bound: 2·Nz words/column.
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct IceOceanArgs {
+  int Nx, Ny, Nz;
+  DCol T, S;            // full columns; T is read and conditionally written
+  DCol dz;              // si = sj = 0 for a 1-D Δz(k)
+  DArr ou, ov;          // ocean u, v at k = Nz-1
+  DArr iu, iv, ih, ihm, iconc, iS;
+  DArr Qf, Qio, Js, tx, ty;
+  FT dt;
+  DevParams<FT> P;
+};
+template <typename FT>
+__device__ __forceinline__ FT io_stress_x(const IceOceanArgs<FT>& a, int i, int j) {
+  const FT dux = ldg<FT>(a.iu, i, j) - ldg<FT>(a.ou, i, j);
+  const FT viF = FT(0.25) * (ldg<FT>(a.iv, i - 1, j) + ldg<FT>(a.iv, i, j) + ldg<FT>(a.iv, i - 1, j + 1) + ldg<FT>(a.iv, i, j + 1));
+  const FT voF = FT(0.25) * (ldg<FT>(a.ov, i - 1, j) + ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i - 1, j + 1) + ldg<FT>(a.ov, i, j + 1));
+  const FT dvx = viF - voF;
+  return a.P.rho0 * a.P.io.Cd * M<FT>::sqrt(dux * dux + dvx * dvx) * dux;
+}
+template <typename FT>
+__device__ __forceinline__ FT io_stress_y(const IceOceanArgs<FT>& a, int i, int j) {
+  const FT dvy = ldg<FT>(a.iv, i, j) - ldg<FT>(a.ov, i, j);
+  const FT uiF = FT(0.25) * (ldg<FT>(a.iu, i, j - 1) + ldg<FT>(a.iu, i, j) + ldg<FT>(a.iu, i + 1, j - 1) + ldg<FT>(a.iu, i + 1, j));
+  const FT uoF = FT(0.25) * (ldg<FT>(a.ou, i, j - 1) + ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j - 1) + ldg<FT>(a.ou, i + 1, j));
+  const FT duy = uiF - uoF;
+  return a.P.rho0 * a.P.io.Cd * M<FT>::sqrt(duy * duy + dvy * dvy) * dvy;
+}
+
+template <typename FT> __global__ void __launch_bounds__(128) ice_ocean_kernel(const __grid_constant__ IceOceanArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.Nx * a.Ny) return;
+  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  const DevParams<FT>& P = a.P;
+  const FT rho0 = P.rho0, c0 = P.c0, T0 = P.io.T0, m = P.io.slope;
+
+  const FT taux = io_stress_x<FT>(a, i, j), tauy = io_stress_y<FT>(a, i, j);
+  stg<FT>(a.tx, i, j, taux);
+  stg<FT>(a.ty, i, j, tauy);
+
+  // frazil sweep, top to bottom; loads batched UNR levels at a time for memory-level parallelism
+  const int64_t base = (int64_t)i * a.T.si + (int64_t)j * a.T.sj;
+  const int64_t baseS = (int64_t)i * a.S.si + (int64_t)j * a.S.sj;
+  const int64_t basez = (int64_t)i * a.dz.si + (int64_t)j * a.dz.sj;
+  FT* Tp = reinterpret_cast<FT*>(a.T.p);
+  const FT* Sp = reinterpret_cast<const FT*>(a.S.p);
+  const FT* zp = reinterpret_cast<const FT*>(a.dz.p);
+  FT dQ = FT(0);
+  FT TN = FT(0), SN = FT(0);
+  constexpr int UNR = 8;
+  for (int k0 = a.Nz - 1; k0 >= 0; k0 -= UNR) {
+    FT Tk[UNR], Sk[UNR], zk[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int k = k0 - u;
+      if (k >= 0) {
+        Tk[u] = Tp[base + (int64_t)k * a.T.sk];
+        Sk[u] = __ldg(Sp + baseS + (int64_t)k * a.S.sk);
+        zk[u] = __ldg(zp + basez + (int64_t)k * a.dz.sk);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int k = k0 - u;
+      if (k >= 0) {
+        const FT Tm = T0 - m * Sk[u];
+        const bool freezing = Tk[u] < Tm;
+        const FT dE = rho0 * c0 * (Tm - Tk[u]);
+        if (freezing) {
+          Tp[base + (int64_t)k * a.T.sk] = Tm;
+          dQ -= dE * zk[u] / a.dt;
+        }
+        if (k == a.Nz - 1) { TN = freezing ? Tm : Tk[u]; SN = Sk[u]; }
+      }
+    }
+  }
+  const FT conc = ldg<FT>(a.iconc, i, j), Si = ldg<FT>(a.iS, i, j);
+  const FT Tm = T0 - m * SN;
+  FT Qio;
+  if (P.io.heat_flux == COFLUX_ICE_OCEAN_THREE_EQUATION) {
+    FT ustar;
+    if (P.io.friction == COFLUX_FRICTION_VELOCITY_MOMENTUM_BASED) {
+      const FT txe = (i + 1 < a.Nx) ? io_stress_x<FT>(a, i + 1, j) : taux;
+      const FT tyn = (j + 1 < a.Ny) ? io_stress_y<FT>(a, i, j + 1) : tauy;
+      const FT tx = FT(0.5) * (taux + txe), ty = FT(0.5) * (tauy + tyn);
+      ustar = M<FT>::sqrt(M<FT>::sqrt(tx * tx + ty * ty) / rho0);
+      ustar = M<FT>::max(ustar, P.io.ustar_min);
+    } else {
+      ustar = P.io.ustar_const;
+    }
+    const FT gT = P.io.alpha_h * ustar, gS = P.io.alpha_s * ustar;
+    const FT A = rho0 * c0 * gT / (P.io.rho_i * P.io.L_f);
+    const FT qa = A * m;
+    const FT qb = A * (TN - T0) - A * m * Si + gS;
+    const FT qc = -(A * (TN - T0) * Si + gS * SN);
+    const FT disc = qb * qb - FT(4) * qa * qc;
+    const FT Sb = (-qb + M<FT>::sqrt(M<FT>::max(disc, FT(0)))) / (FT(2) * qa);
+    const FT Tb = T0 - m * Sb;
+    Qio = rho0 * c0 * gT * (TN - Tb) * conc;
+  } else {
+    const FT dE = rho0 * c0 * (Tm - TN);
+    Qio = -dE * P.io.um_star * conc;
+  }
+  const FT h = ldg<FT>(a.ih, i, j);
+  const FT hm = reinterpret_cast<const FT*>(a.ihm.p)[(int64_t)i * a.ihm.si + (int64_t)j * a.ihm.sj];
+  const FT Js = (h - hm) / a.dt * (Si - SN);
+  stg<FT>(a.Qf, i, j, dQ);
+  stg<FT>(a.Qio, i, j, Qio);
+  stg<FT>(a.Js, i, j, Js);
+  stg<FT>(a.ihm, i, j, h);
+}
+
+}  // namespace coflux

@@ -1,0 +1,184 @@
+"""All arrays the surface-flux path touches on one (local) grid, as Fields on the host (numpy) or on
+a CUDA device (torch), plus builders of the ctypes bundles of include/coflux.h.
+
+Plumbing only: allocation, layout, descriptors.  No flux arithmetic happens in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, synth
+from .fields import Field, FieldTimeSeries, arr, fractional_indices
+
+ATM_NAMES = ("u", "v", "T", "q", "p", "Qs", "Ql", "rain", "snow")
+XCH_NAMES = ("u", "v", "T", "p", "q", "Qs", "Ql", "Mp")
+IFACE_NAMES = ("latent_heat", "sensible_heat", "water_vapor", "x_momentum", "y_momentum", "interface_temperature",
+               "friction_velocity", "temperature_scale", "humidity_scale")
+NET_NAMES = ("u", "v", "T", "S", "upwelling_longwave", "downwelling_longwave", "downwelling_shortwave",
+             "penetrating_shortwave")
+IO_NAMES = ("frazil_heat", "interface_heat", "salt", "x_momentum", "y_momentum")
+ICE_NAMES = ("thickness", "previous_thickness", "concentration", "salinity", "u", "v", "top_temperature")
+
+
+class SurfaceFluxData:
+    def __init__(self, grid, device=None):
+        self.grid = grid
+        self.device = device
+        self.dtype = grid.dtype
+        self.atmos = {}          # name -> FieldTimeSeries
+        self.times = None
+        self.time_indexing = _abi.TIME_LINEAR
+        self.fi = self.fj = None
+        self.ocean = {}          # u v T S (3-D)
+        self.dz = None           # 1-D Field (nk,1,1)
+        self.mask = None
+        self.ice = None          # dict or None
+        self.exchange = {}
+        self.ao = {}
+        self.ai = {}
+        self.io = {}
+        self.net = {}
+        self.iterations = None
+        self._keep = []
+
+    # ------------------------------------------------------------------------------------------
+    @classmethod
+    def synthetic(cls, grid, device=None, with_ice=False, land_fraction=0.0, frazil=False, Nt=8, atmos_size=(640, 320),
+                  atmos_halo=3, ring=1):
+        """Inputs per SURVEY §8d on the host; call .to(device) for the CUDA copy."""
+        self = cls(grid, None)
+        dt = grid.dtype
+        series, times = synth.atmosphere_series(atmos_size[0], atmos_size[1], Nt, atmos_halo, dt)
+        self.times = times
+        for n in ATM_NAMES:
+            self.atmos[n] = FieldTimeSeries(series[n], (atmos_halo, atmos_halo, 0), times, n)
+        FI, FJ = fractional_indices(grid, atmos_size[0], atmos_size[1], ring=ring)
+        self.fi = Field(FI, (ring, ring, 0), "fi")
+        self.fj = Field(FJ, (ring, ring, 0), "fj")
+        oc = synth.ocean_state(grid, dt, frazil=frazil)
+        for n in ("u", "v", "T", "S"):
+            self.ocean[n] = Field(oc[n], grid.halo, "ocean_" + n)
+        self.dz = Field(grid.dz().reshape(-1, 1, 1).copy(), (0, 0, grid.halo[2]), "dz")
+        if land_fraction > 0:
+            self.mask = Field(synth.land_mask(grid, land_fraction), (grid.halo[0], grid.halo[1], 0), "mask")
+        if with_ice:
+            ice = synth.sea_ice_state(grid, dt)
+            self.ice = {n: Field(ice[n], (grid.halo[0], grid.halo[1], 0), "ice_" + n) for n in ICE_NAMES}
+        self.allocate_outputs()
+        return self
+
+    def allocate_outputs(self):
+        g = self.grid
+        h2 = (g.halo[0], g.halo[1], 0)
+        size2 = (g.Nx, g.Ny, 1)
+        mk = lambda name: Field.zeros(size2, h2, self.dtype, self.device, name)
+        self.exchange = {n: mk("exchange_" + n) for n in XCH_NAMES}
+        self.ao = {n: mk("ao_" + n) for n in IFACE_NAMES}
+        self.net = {n: mk("net_" + n) for n in NET_NAMES}
+        self.iterations = Field.zeros(size2, h2, np.int32, self.device, "iterations")
+        if self.ice is not None:
+            self.ai = {n: mk("ai_" + n) for n in IFACE_NAMES}
+            self.io = {n: mk("io_" + n) for n in IO_NAMES}
+
+    def to(self, device):
+        o = SurfaceFluxData(self.grid, device)
+        o.times, o.time_indexing = self.times, self.time_indexing
+        o.atmos = {n: f.to(device) for n, f in self.atmos.items()}
+        o.fi, o.fj = self.fi.to(device), self.fj.to(device)
+        o.ocean = {n: f.to(device) for n, f in self.ocean.items()}
+        o.dz = self.dz.to(device)
+        o.mask = self.mask.to(device) if self.mask is not None else None
+        o.ice = {n: f.to(device) for n, f in self.ice.items()} if self.ice is not None else None
+        o.allocate_outputs()
+        return o
+
+    # ------------------------------------------------------------------------------------------
+    # ctypes bundles (the returned struct keeps python references alive through self._keep)
+    # ------------------------------------------------------------------------------------------
+    def atmos_series(self):
+        s = _abi.AtmosSeries()
+        for n in ATM_NAMES:
+            setattr(s, n, arr(self.atmos.get(n)))
+        self._times_c = (C.c_double * len(self.times))(*self.times)
+        s.times = C.cast(self._times_c, C.POINTER(C.c_double))
+        s.Nt = len(self.times)
+        s.time_indexing = self.time_indexing
+        s.cycle_period = 0.0
+        s.fi, s.fj = arr(self.fi), arr(self.fj)
+        s.cos_theta, s.sin_theta = arr(None), arr(None)
+        return s
+
+    def exchange_state(self):
+        s = _abi.ExchangeState()
+        for n in XCH_NAMES:
+            setattr(s, n, arr(self.exchange[n]))
+        return s
+
+    def ocean_surface(self):
+        s = _abi.OceanSurface()
+        for n in ("u", "v", "T", "S"):
+            setattr(s, n, arr(self.ocean[n]))
+        s.mask = arr(self.mask)
+        return s
+
+    def interface_fluxes(self, which="ao", with_iterations=True):
+        d = self.ao if which == "ao" else self.ai
+        s = _abi.InterfaceFluxes()
+        for n in IFACE_NAMES:
+            setattr(s, n, arr(d[n]))
+        s.iterations = arr(self.iterations) if (with_iterations and which == "ao") else arr(None)
+        return s
+
+    def sea_ice_state(self):
+        s = _abi.SeaIceState()
+        for n in ICE_NAMES:
+            setattr(s, n, arr(self.ice[n]))
+        s.snow_thickness, s.albedo = arr(None), arr(None)
+        return s
+
+    def ocean_columns(self):
+        s = _abi.OceanColumns()
+        s.T, s.S = arr(self.ocean["T"]), arr(self.ocean["S"])
+        dz = self.dz.array()
+        dz.stride_i = 0
+        dz.stride_j = 0
+        dz.stride_k = 1
+        s.dz = dz
+        s.u, s.v = arr(self.ocean["u"]), arr(self.ocean["v"])
+        return s
+
+    def ice_ocean_fluxes(self):
+        s = _abi.IceOceanFluxes()
+        for n in IO_NAMES:
+            setattr(s, n, arr(self.io[n]))
+        return s
+
+    def net_ocean_fluxes(self):
+        s = _abi.NetOceanFluxes()
+        for n in NET_NAMES:
+            setattr(s, n, arr(self.net[n]))
+        return s
+
+    def update_bundles(self, with_ice_terms=False):
+        """(UpdateInputs, UpdateOutputs) for coflux_update_state; keeps the sub-structs alive."""
+        a, o = self.atmos_series(), self.ocean_surface()
+        x, f, n = self.exchange_state(), self.interface_fluxes("ao"), self.net_ocean_fluxes()
+        inp = _abi.UpdateInputs(C.pointer(a), C.pointer(o), None, None)
+        keep = [a, o, x, f, n]
+        if with_ice_terms and self.ice is not None:
+            ice, io = self.sea_ice_state(), self.ice_ocean_fluxes()
+            inp.sea_ice, inp.ice_ocean = C.pointer(ice), C.pointer(io)
+            keep += [ice, io]
+        out = _abi.UpdateOutputs(C.pointer(x), C.pointer(f), C.pointer(n))
+        self._keep = keep
+        return inp, out
+
+    def outputs(self):
+        """name -> numpy interior (Ny, Nx) of every output field (copied to host)."""
+        res = {}
+        for grp, d in (("exchange", self.exchange), ("ao", self.ao), ("ai", self.ai), ("io", self.io), ("net", self.net)):
+            for n, f in d.items():
+                a = f.numpy()
+                Hx, Hy, _ = f.halo
+                res[f"{grp}.{n}"] = a[0, Hy:a.shape[1] - Hy, Hx:a.shape[2] - Hx].copy()
+        return res

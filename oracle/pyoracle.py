@@ -1,0 +1,78 @@
+"""ctypes loader for the CPU oracle (oracle/libcoflux_oracle.so).
+
+TEST INFRASTRUCTURE — PARITY UNPINNED (see oracle/coflux_oracle.c).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+The oracle consumes the same ctypes bundles as the CUDA library, pointing at HOST (numpy) arrays.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcoflux_oracle.so")
+_lib = None
+
+
+def load(build_if_missing=True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) and build_if_missing:
+        subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    _lib = C.CDLL(LIB_PATH)
+    _lib.oracle_time_indices.argtypes = [C.POINTER(C.c_double), C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    return _lib
+
+
+def _suffix(cfg):
+    return "_f64" if cfg.dtype == 64 else "_f32"
+
+
+def fn(name, cfg):
+    return getattr(load(), name + _suffix(cfg))
+
+
+def interpolate_atmosphere(cfg, series, time, exchange):
+    f = fn("oracle_interpolate_atmosphere", cfg)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    assert f(C.byref(cfg), C.byref(series), float(time), C.byref(exchange)) == 0
+
+
+def atmosphere_ocean_fluxes(cfg, exchange, ocean, fluxes):
+    f = fn("oracle_atmosphere_ocean_fluxes", cfg)
+    assert f(C.byref(cfg), C.byref(exchange), C.byref(ocean), C.byref(fluxes)) == 0
+
+
+def atmosphere_sea_ice_fluxes(cfg, exchange, ocean, ice, fluxes):
+    f = fn("oracle_atmosphere_sea_ice_fluxes", cfg)
+    assert f(C.byref(cfg), C.byref(exchange), C.byref(ocean), C.byref(ice), C.byref(fluxes)) == 0
+
+
+def sea_ice_ocean_fluxes(cfg, columns, ice, dt, fluxes):
+    f = fn("oracle_sea_ice_ocean_fluxes", cfg)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    assert f(C.byref(cfg), C.byref(columns), C.byref(ice), float(dt), C.byref(fluxes)) == 0
+
+
+def assemble_net_ocean_fluxes(cfg, exchange, ocean, ao, ice, io, net):
+    f = fn("oracle_assemble_net_ocean_fluxes", cfg)
+    assert f(C.byref(cfg), C.byref(exchange), C.byref(ocean), C.byref(ao), C.byref(ice) if ice is not None else None,
+             C.byref(io) if io is not None else None, C.byref(net)) == 0
+
+
+def update_state(cfg, inputs, outputs, time):
+    f = fn("oracle_update_state", cfg)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    assert f(C.byref(cfg), C.byref(inputs), C.byref(outputs), float(time)) == 0
+
+
+def set_threads(n):
+    """Limit / set OpenMP threads of the oracle through libgomp's omp_set_num_threads."""
+    gomp = C.CDLL("libgomp.so.1")
+    gomp.omp_set_num_threads(int(n))
+
+
+def max_threads():
+    gomp = C.CDLL("libgomp.so.1")
+    return int(gomp.omp_get_max_threads())
