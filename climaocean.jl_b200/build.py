@@ -10,7 +10,7 @@ SRC = os.path.join(HERE, "csrc", "coflux_abi.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "coflux_kernels.cuh"), os.path.join(HERE, "csrc", "coflux_device.cuh"),
         os.path.join(ROOT, "include", "coflux.h")]
 OUT = os.path.join(HERE, "lib", "libcoflux.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 
 

@@ -346,14 +346,21 @@ __device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const Cel
         const FT zeta = h / Lstar;
         const FT psi_hm = psi_momentum(F.stability, zeta);
         const FT psi_hs = psi_scalar(F.stability, zeta);
-        const FT chi_u = kappa / similarity_profile<FT, false>(F.form, F.stability, h, lu, Lstar, psi_hm);
-        const FT chi_q = kappa / similarity_profile<FT, true>(F.form, F.stability, h, lq, Lstar, psi_hs);
-        FT chi_t = chi_q;
-        if (!F.same_scalar) {
-          const FT lt = scalar_roughness(F.tr, lu, u0, S.nu_t);
-          chi_t = kappa / similarity_profile<FT, true>(F.form, F.stability, h, lt, Lstar, psi_hs);
+        const FT prof_u = similarity_profile<FT, false>(F.form, F.stability, h, lu, Lstar, psi_hm);
+        if (!(prof_u > FT(0))) {  // documented guard (COARE form only): reset to zero scales
+          ustar = tstar = qstar = FT(0);
+        } else {
+          const FT prof_q = similarity_profile<FT, true>(F.form, F.stability, h, lq, Lstar, psi_hs);
+          const FT chi_u = kappa / prof_u;
+          const FT chi_q = (prof_q > FT(0)) ? kappa / prof_q : FT(0);
+          FT chi_t = chi_q;
+          if (!F.same_scalar) {
+            const FT lt = scalar_roughness(F.tr, lu, u0, S.nu_t);
+            const FT prof_t = similarity_profile<FT, true>(F.form, F.stability, h, lt, Lstar, psi_hs);
+            chi_t = (prof_t > FT(0)) ? kappa / prof_t : FT(0);
+          }
+          ustar = chi_u * U; tstar = chi_t * S.dtheta; qstar = chi_q * S.dq;
         }
-        ustar = chi_u * U; tstar = chi_t * S.dtheta; qstar = chi_q * S.dq;
       }
     }
     ++it;

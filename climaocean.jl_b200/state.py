@@ -92,6 +92,41 @@ class SurfaceFluxData:
         o.allocate_outputs()
         return o
 
+    def to_device_columns(self, device, Nz, Hz=7, fill_columns=False):
+        """Device copy whose ocean u, v, T, S are full 3-D parents (Nz+2Hz levels) although this host
+        object only holds the surface plane (grid.Nz == 1): the plane is placed at k = Nz-1 and, when
+        fill_columns is set, T and S are extended downwards on the device (T relaxing to −1 °C with
+        bands of super-cooled water for the frazil sweep).  Used by bench.py for the 1/12° grid, where
+        generating 75 levels on the host would only cost time — the flux solve reads k = Nz-1 only."""
+        import torch
+        from .fields import LatitudeLongitudeGrid
+        g0 = self.grid
+        assert g0.Nz == 1 and g0.halo[2] == 0
+        g = LatitudeLongitudeGrid((g0.Nx, g0.Ny, Nz), g0.longitude, g0.latitude, g0.z, (g0.halo[0], g0.halo[1], Hz), g0.dtype)
+        g.i_offset, g.global_Nx = g0.i_offset, g0.global_Nx
+        o = self.to(device)
+        o.grid = g
+        tdt = torch.float64 if np.dtype(self.dtype) == np.float64 else torch.float32
+        nk = Nz + 2 * Hz
+        for n in ("u", "v", "T", "S"):
+            plane = o.ocean[n].data[0]
+            full = torch.zeros((nk,) + tuple(plane.shape), dtype=tdt, device=device)
+            if fill_columns and n in ("T", "S"):
+                k = torch.arange(nk, device=device, dtype=tdt).view(-1, 1, 1)
+                depth = ((Nz - 1 + Hz) - k).clamp(min=0) / max(Nz - 1, 1)
+                if n == "T":
+                    full[...] = plane[None] - depth * (plane[None] + 1.0) * 0.9
+                    jj = torch.arange(plane.shape[0], device=device).view(1, -1, 1)
+                    cold = ((jj + 3 * k.long()) % 16) >= 14
+                    full[...] = torch.where(cold, torch.full_like(full, -2.6) - 0.2 * depth, full)
+                else:
+                    full[...] = plane[None] + 0.5 * depth
+            else:
+                full[Nz - 1 + Hz] = plane
+            o.ocean[n] = Field(full, (g0.halo[0], g0.halo[1], Hz), "ocean_" + n)
+        o.dz = Field.from_numpy(g.dz().reshape(-1, 1, 1).copy(), (0, 0, Hz), device, "dz")
+        return o
+
     # ------------------------------------------------------------------------------------------
     # ctypes bundles (the returned struct keeps python references alive through self._keep)
     # ------------------------------------------------------------------------------------------

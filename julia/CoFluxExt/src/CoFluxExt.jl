@@ -1,0 +1,172 @@
+# CoFluxExt — Julia glue that routes ClimaOcean's surface-flux path through libcoflux.so.
+#
+# !!! UNEXECUTED !!!  No Julia toolchain exists in the build environment or on the GPU box this
+# repository is developed on.  This file is the binding a maintainer would add; it has never been
+# run.  Layouts are checked at load time against `coflux_sizeof`, so a drifted mirror fails loudly.
+#
+# Reference call sites this overrides (ClimaOcean v0.10.0 re-exports NumericalEarth,
+# src/ClimaOcean.jl:31-42): `update_state!(::OceanSeaIceModel)` and, through it,
+# interpolate_atmosphere_state!, compute_atmosphere_ocean_fluxes!, compute_sea_ice_ocean_fluxes!,
+# compute_net_ocean_fluxes!  (SURVEY.md §3.2).
+module CoFluxExt
+
+using CUDA
+using Oceananigans
+using Oceananigans.Architectures: architecture, GPU
+using NumericalEarth.EarthSystemModels: OceanSeaIceModel
+import NumericalEarth.EarthSystemModels: update_state!
+
+const libcoflux = get(ENV, "COFLUX_LIB", joinpath(@__DIR__, "..", "..", "..", "climaocean.jl_b200", "lib", "libcoflux.so"))
+
+# ---- struct mirrors of include/coflux.h -------------------------------------------------------
+struct CofluxArray
+    ptr      :: Ptr{Cvoid}
+    stride_i :: Int64
+    stride_j :: Int64
+    stride_k :: Int64
+    stride_n :: Int64
+    off_i    :: Int32
+    off_j    :: Int32
+    off_k    :: Int32
+    reserved :: Int32
+end
+const NULL_ARRAY = CofluxArray(C_NULL, 0, 0, 0, 0, 0, 0, 0, 0)
+
+"Descriptor of an Oceananigans Field's parent (halo-padded, column-major)."
+function CofluxArray(f::Oceananigans.Fields.AbstractField)
+    p  = parent(f)
+    Hx, Hy, Hz = Oceananigans.Grids.halo_size(f.grid)
+    sz = size(p)
+    hz = sz[3] == 1 ? 0 : Hz                      # reduced (2-D) fields have a singleton k, no halo
+    return CofluxArray(Ptr{Cvoid}(UInt(pointer(p))), 1, sz[1], sz[1] * sz[2], 0, Hx, Hy, hz, 0)
+end
+
+"Descriptor of a FieldTimeSeries window in memory (4-D parent, time last)."
+function CofluxArray(fts::Oceananigans.OutputReaders.FieldTimeSeries)
+    p  = parent(fts)
+    Hx, Hy, _ = Oceananigans.Grids.halo_size(fts.grid)
+    sz = size(p)
+    return CofluxArray(Ptr{Cvoid}(UInt(pointer(p))), 1, sz[1], sz[1] * sz[2], sz[1] * sz[2] * sz[3], Hx, Hy, 0, 0)
+end
+
+# coflux_config is large; it is filled by the library (coflux_default_config +
+# coflux_apply_flux_configuration) into an opaque, correctly sized buffer and then edited through
+# the handful of scalars ClimaOcean exposes (ocean_minimum_salinity, velocity formulation ...).
+struct CofluxConfigBuffer
+    bytes :: Vector{UInt8}
+end
+function CofluxConfigBuffer(Nx, Ny, Nz, FT; flux_configuration = :default, velocity_formulation = :relative)
+    n = ccall((:coflux_sizeof, libcoflux), Cint, (Cstring,), "config")
+    n > 0 || error("libcoflux does not know struct coflux_config")
+    buf = CofluxConfigBuffer(zeros(UInt8, n))
+    dtype = FT === Float64 ? 64 : 32
+    check(ccall((:coflux_default_config, libcoflux), Cint, (Ptr{UInt8}, Int32, Int32, Int32, Int32), buf.bytes, Nx, Ny, Nz, dtype))
+    vel = velocity_formulation === :relative ? 0 :
+          velocity_formulation === :wind     ? 1 :
+          error("Unknown velocity_formulation: $velocity_formulation. Options: :relative, :wind")
+    check(ccall((:coflux_apply_flux_configuration, libcoflux), Cint, (Ptr{UInt8}, Cstring, Int32), buf.bytes, String(flux_configuration), vel))
+    return buf
+end
+
+check(status) = status == 0 ? nothing :
+    error("coflux status $status: " * unsafe_string(ccall((:coflux_last_error, libcoflux), Cstring, ())))
+
+mutable struct CofluxContext
+    handle :: Ptr{Cvoid}
+end
+function CofluxContext(cfg::CofluxConfigBuffer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:coflux_create, libcoflux), Cint, (Ref{Ptr{Cvoid}}, Ptr{UInt8}), h, cfg.bytes))
+    ctx = CofluxContext(h[])
+    finalizer(c -> ccall((:coflux_destroy, libcoflux), Cint, (Ptr{Cvoid},), c.handle), ctx)
+    return ctx
+end
+
+# ---- bundles (field order as in include/coflux.h) --------------------------------------------
+struct AtmosSeries
+    u::CofluxArray; v::CofluxArray; T::CofluxArray; q::CofluxArray; p::CofluxArray
+    Qs::CofluxArray; Ql::CofluxArray; rain::CofluxArray; snow::CofluxArray
+    times::Ptr{Float64}; Nt::Int32; time_indexing::Int32; cycle_period::Float64
+    fi::CofluxArray; fj::CofluxArray; cos_theta::CofluxArray; sin_theta::CofluxArray
+end
+struct ExchangeState;   u::CofluxArray; v::CofluxArray; T::CofluxArray; p::CofluxArray; q::CofluxArray; Qs::CofluxArray; Ql::CofluxArray; Mp::CofluxArray; end
+struct OceanSurface;    u::CofluxArray; v::CofluxArray; T::CofluxArray; S::CofluxArray; mask::CofluxArray; end
+struct InterfaceFluxes; latent_heat::CofluxArray; sensible_heat::CofluxArray; water_vapor::CofluxArray; x_momentum::CofluxArray; y_momentum::CofluxArray
+                        interface_temperature::CofluxArray; friction_velocity::CofluxArray; temperature_scale::CofluxArray; humidity_scale::CofluxArray; iterations::CofluxArray; end
+struct NetOceanFluxes;  u::CofluxArray; v::CofluxArray; T::CofluxArray; S::CofluxArray; upwelling_longwave::CofluxArray; downwelling_longwave::CofluxArray
+                        downwelling_shortwave::CofluxArray; penetrating_shortwave::CofluxArray; end
+struct UpdateInputs;    atmosphere::Ptr{AtmosSeries}; ocean::Ptr{OceanSurface}; sea_ice::Ptr{Cvoid}; ice_ocean::Ptr{Cvoid}; end
+struct UpdateOutputs;   exchange::Ptr{ExchangeState}; atmosphere_ocean::Ptr{InterfaceFluxes}; net_ocean::Ptr{NetOceanFluxes}; end
+
+function __init__()
+    for (name, T) in (("array", CofluxArray), ("atmos_series", AtmosSeries), ("exchange_state", ExchangeState),
+                      ("ocean_surface", OceanSurface), ("interface_fluxes", InterfaceFluxes),
+                      ("net_ocean_fluxes", NetOceanFluxes), ("update_inputs", UpdateInputs), ("update_outputs", UpdateOutputs))
+        n = ccall((:coflux_sizeof, libcoflux), Cint, (Cstring,), name)
+        n == sizeof(T) || error("CoFluxExt: layout of $name drifted (Julia $(sizeof(T)) B, library $n B)")
+    end
+end
+
+# A per-model cache: context + the construction-time fractional indices (fi, fj) Fields.
+const CONTEXTS = IdDict{Any, Any}()
+
+"""
+    update_state!(model::OceanSeaIceModel{<:GPU ...})
+
+Ocean-only coupled model on a GPU: one `coflux_update_state` call (2 kernel launches) on CUDA.jl's
+task-local stream replaces interpolate_atmosphere_state! + compute_atmosphere_ocean_fluxes! +
+compute_net_ocean_fluxes!.  All arrays stay Julia-owned `Field`s; nothing is copied.
+(The exact field paths into `model.interfaces` must be adapted to the installed NumericalEarth version.)
+"""
+function coflux_update_state!(model::OceanSeaIceModel)
+    ocean, atmos, itf = model.ocean, model.atmosphere, model.interfaces
+    grid = ocean.model.grid
+    ctx, fi, fj = get!(CONTEXTS, model) do
+        Nx, Ny, Nz = size(grid)
+        cfg = CofluxConfigBuffer(Nx, Ny, Nz, eltype(grid))
+        CofluxContext(cfg), itf.exchanger.regridder.i, itf.exchanger.regridder.j    # construction-time fractional indices
+    end
+    times = collect(Float64, atmos.times)
+    u, v = ocean.model.velocities.u, ocean.model.velocities.v
+    T, S = ocean.model.tracers.T, ocean.model.tracers.S
+    series = Ref(AtmosSeries(CofluxArray(atmos.velocities.u), CofluxArray(atmos.velocities.v), CofluxArray(atmos.tracers.T),
+                             CofluxArray(atmos.tracers.q), CofluxArray(atmos.pressure),
+                             CofluxArray(model.radiation.downwelling_shortwave), CofluxArray(model.radiation.downwelling_longwave),
+                             CofluxArray(atmos.freshwater_flux.rain), CofluxArray(atmos.freshwater_flux.snow),
+                             pointer(times), length(times), 0, 0.0, CofluxArray(fi), CofluxArray(fj), NULL_ARRAY, NULL_ARRAY))
+    xs = itf.exchanger.exchange_atmosphere_state
+    xch = Ref(ExchangeState(CofluxArray(xs.u), CofluxArray(xs.v), CofluxArray(xs.T), CofluxArray(xs.p), CofluxArray(xs.q),
+                            CofluxArray(xs.Qs), CofluxArray(xs.Qℓ), CofluxArray(xs.Mp)))
+    oc = Ref(OceanSurface(CofluxArray(u), CofluxArray(v), CofluxArray(T), CofluxArray(S), NULL_ARRAY))
+    f = itf.atmosphere_ocean_interface.fluxes
+    ao = Ref(InterfaceFluxes(CofluxArray(f.latent_heat), CofluxArray(f.sensible_heat), CofluxArray(f.water_vapor),
+                             CofluxArray(f.x_momentum), CofluxArray(f.y_momentum),
+                             CofluxArray(itf.atmosphere_ocean_interface.temperature), NULL_ARRAY, NULL_ARRAY, NULL_ARRAY, NULL_ARRAY))
+    n = itf.net_fluxes.ocean
+    net = Ref(NetOceanFluxes(CofluxArray(n.u), CofluxArray(n.v), CofluxArray(n.T), CofluxArray(n.S),
+                             CofluxArray(f.upwelling_longwave), CofluxArray(f.downwelling_longwave), CofluxArray(f.downwelling_shortwave),
+                             NULL_ARRAY))
+    GC.@preserve times series xch oc ao net begin
+        inp = Ref(UpdateInputs(Base.unsafe_convert(Ptr{AtmosSeries}, series), Base.unsafe_convert(Ptr{OceanSurface}, oc), C_NULL, C_NULL))
+        out = Ref(UpdateOutputs(Base.unsafe_convert(Ptr{ExchangeState}, xch), Base.unsafe_convert(Ptr{InterfaceFluxes}, ao),
+                                Base.unsafe_convert(Ptr{NetOceanFluxes}, net)))
+        check(ccall((:coflux_update_state, libcoflux), Cint,
+                    (Ptr{Cvoid}, Ref{UpdateInputs}, Ref{UpdateOutputs}, Float64, Ptr{Cvoid}),
+                    ctx.handle, inp, out, Float64(model.clock.time), Ptr{Cvoid}(UInt(CUDA.stream().handle))))
+    end
+    return nothing
+end
+
+# Opt in per model:  CoFluxExt.enable!(model)  makes update_state!(model) take the coflux path.
+const ENABLED = IdDict{Any, Bool}()
+enable!(model)  = (ENABLED[model] = true; nothing)
+disable!(model) = (delete!(ENABLED, model); nothing)
+
+function update_state!(model::OceanSeaIceModel)
+    if get(ENABLED, model, false) && architecture(model.ocean.model.grid) isa GPU && isnothing(model.sea_ice)
+        return coflux_update_state!(model)
+    end
+    return invoke(update_state!, Tuple{Any}, model)     # the stock NumericalEarth method
+end
+
+end # module

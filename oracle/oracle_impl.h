@@ -267,9 +267,17 @@ static void SUF(iterate_similarity)(const coflux_flux_params* P, const coflux_at
 
   FT Lstar = (bstar == (FT)0) ? (FT)HUGE_VAL : ustar * ustar / (kappa * bstar);
 
-  FT chi_u = kappa / SUF(similarity_profile)(P->similarity_form, P->stability_functions, 0, h, lu, Lstar);
-  FT chi_t = kappa / SUF(similarity_profile)(P->similarity_form, P->stability_functions, 1, h, lt, Lstar);
-  FT chi_q = kappa / SUF(similarity_profile)(P->similarity_form, P->stability_functions, 1, h, lq, Lstar);
+  FT prof_u = SUF(similarity_profile)(P->similarity_form, P->stability_functions, 0, h, lu, Lstar);
+  FT prof_t = SUF(similarity_profile)(P->similarity_form, P->stability_functions, 1, h, lt, Lstar);
+  FT prof_q = SUF(similarity_profile)(P->similarity_form, P->stability_functions, 1, h, lq, Lstar);
+  /* documented guard: the profile function ∫φ dz/z is positive by construction in the standard form;
+   * the COARE form (no ψ(ℓ/L) term) can turn non-positive in wild transients (tiny u★, ℓ → ℓ_max).
+   * A non-positive momentum profile resets the iterate to zero scales (the next pass re-enters
+   * through the neutral log law, like a calm cell); a non-positive scalar profile zeroes that scale. */
+  if (!(prof_u > (FT)0)) { *us = (FT)0; *ts = (FT)0; *qs_ = (FT)0; return; }
+  FT chi_u = kappa / prof_u;
+  FT chi_t = (prof_t > (FT)0) ? kappa / prof_t : (FT)0;
+  FT chi_q = (prof_q > (FT)0) ? kappa / prof_q : (FT)0;
 
   *us = chi_u * U;
   *ts = chi_t * dtheta;

@@ -90,7 +90,7 @@ def test_sea_ice_ocean_fluxes_and_ice_aware_assembly(bits, flux_configuration):
     gpu = dev.outputs()
     compare(gpu, ref, bits)
     # the frazil sweep edits the ocean temperature in place: compare the whole column array
-    assert rel_err(dev.ocean["T"].numpy(), host.ocean["T"].numpy()) <= RTOL[bits]
+    assert rel_err(dev.ocean["T"].numpy(), host.ocean["T"].numpy(), bits) <= RTOL[bits]
     assert np.array_equal(dev.ice["previous_thickness"].numpy(), host.ice["previous_thickness"].numpy())
     assert np.any(gpu["io.frazil_heat"] != 0)
 
@@ -109,7 +109,7 @@ def test_atmosphere_sea_ice_fluxes(bits, flux_configuration):
     torch.cuda.synchronize()
     ref, gpu = host.outputs(), dev.outputs()
     compare(gpu, ref, bits, keys=[k for k in ref if k.startswith("ai.")])
-    assert rel_err(dev.ice["top_temperature"].numpy(), host.ice["top_temperature"].numpy()) <= RTOL[bits]
+    assert rel_err(dev.ice["top_temperature"].numpy(), host.ice["top_temperature"].numpy(), bits) <= RTOL[bits]
     assert np.any(gpu["ai.sensible_heat"] != 0)
 
 
@@ -191,4 +191,4 @@ def test_host_buffer_entry_matches_device_path(bits):
     assert h2d == 4 * plane_bytes and d2h == 6 * plane_bytes
     for n, key in (("u", "net.u"), ("v", "net.v"), ("T", "net.T"), ("S", "net.S"), ("Qv", "ao.latent_heat"), ("Qc", "ao.sensible_heat")):
         got = outs[n].numpy()[H:-H, H:-H]
-        assert rel_err(got, ref[key]) <= RTOL[bits], key
+        assert rel_err(got, ref[key], bits) <= RTOL[bits], key

@@ -1,0 +1,34 @@
+"""Diagnostic (run on the GPU box): per-field CUDA-vs-oracle error at several denominator floors,
+iteration-count agreement, and the cells carrying the largest errors."""
+import sys, os, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from tests.common import make_case, oracle_update, gpu_update
+
+def report(Nx, Ny, bits, cfgname):
+    grid, host, cfg = make_case(Nx, Ny, 4, bits, flux_configuration=cfgname)
+    ref = oracle_update(host, cfg)
+    gpu, dev = gpu_update(host, cfg)
+    its_ref = host.iterations.numpy()[0, 7:-7, 7:-7]
+    its_gpu = gpu["_iterations"][0, 7:-7, 7:-7]
+    print(f"== {Nx}x{Ny} f{bits} {cfgname}: iteration mismatches {(its_ref != its_gpu).sum()} of {its_ref.size}; mean its {its_ref.mean():.2f}")
+    for k, b in ref.items():
+        if k not in gpu or k.startswith("ai.") or k.startswith("io."):
+            continue
+        a = gpu[k].astype(np.float64); b = b.astype(np.float64)
+        scale = np.abs(b).max()
+        if scale == 0:
+            continue
+        d = np.abs(a - b)
+        row = [f"{k:30s} max|d|/max|b| {d.max()/scale:.2e}"]
+        for fl in (1e-6, 1e-3, 1e-2, 1e-1):
+            row.append(f"floor{fl:g}: {np.max(d/np.maximum(np.abs(b), fl*scale)):.2e}")
+        j, i = np.unravel_index(np.argmax(d / np.maximum(np.abs(b), 1e-3 * scale)), d.shape)
+        row.append(f"worst@({i},{j}) ref {b[j,i]:.6e} its {its_ref[j,i]}/{its_gpu[j,i]}")
+        print("  ".join(row))
+
+if __name__ == "__main__":
+    for bits in (64, 32):
+        for name in ("default", "corrected", "ncar"):
+            report(256, 128, bits, name)
