@@ -11,7 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
-#include "coflux_kernels.cuh"
+#include "coflux_solve_tile.cuh"
+#include <cstdlib>
 
 using namespace coflux;
 
@@ -406,6 +407,8 @@ template <typename FT> static FluxP<FT> to_dev(const coflux_flux_params& f) {
   d.same_scalar = (t.kind == q.kind && t.fixed_length == q.fixed_length && t.reynolds_A == q.reynolds_A &&
                    t.reynolds_b == q.reynolds_b && t.maximum_length == q.maximum_length && same_viscosity(t.viscosity, q.viscosity))
                       ? 1 : 0;
+  d.same_visc = (same_viscosity(m.viscosity, t.viscosity) && same_viscosity(m.viscosity, q.viscosity)) ? 1 : 0;
+  d.pad_ = 0;
   return d;
 }
 template <typename FT> static DevParams<FT> make_dev_params(const coflux_config& c) {
@@ -432,6 +435,21 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
   P.emis_i = (FT)c.radiation.sea_ice_emissivity; P.alb_i = (FT)c.radiation.sea_ice_albedo; P.sw_pen = c.radiation.shortwave_penetrates;
   P.ao = to_dev<FT>(c.atmosphere_ocean);
   P.ai = to_dev<FT>(c.atmosphere_sea_ice);
+  {
+    const FluxP<FT>& F = P.ao;
+    FastConsts<FT>& K = P.K;
+    K.lnh = std::log(P.h);
+    K.edson = (F.stability == COFLUX_STABILITY_EDSON) ? 1 : 0;
+    K.gust_skip = ((F.beta >= FT(0)) && (F.ugmin >= FT(0))) ? 1 : 0;
+    K.fast_q = ((F.qr.kind == COFLUX_ROUGHNESS_REYNOLDS_SCALING) && (F.qr.b > FT(0)) && (F.qr.A > FT(0)) && (F.qr.lmax > FT(0))) ? 1 : 0;
+    K.fast_t = ((F.tr.kind == COFLUX_ROUGHNESS_REYNOLDS_SCALING) && (F.tr.b > FT(0)) && (F.tr.A > FT(0)) && (F.tr.lmax > FT(0))) ? 1 : 0;
+    K.lnhA_q = K.fast_q ? std::log(P.h / F.qr.A) : FT(0);
+    K.lnhl_q = std::log(P.h / ((F.qr.kind == COFLUX_ROUGHNESS_FIXED) ? F.qr.fixed : F.qr.lmax));
+    K.lrclip_q = K.fast_q ? std::log(F.qr.A / F.qr.lmax) / F.qr.b : FT(0);
+    K.lnhA_t = K.fast_t ? std::log(P.h / F.tr.A) : FT(0);
+    K.lnhl_t = std::log(P.h / ((F.tr.kind == COFLUX_ROUGHNESS_FIXED) ? F.tr.fixed : F.tr.lmax));
+    K.lrclip_t = K.fast_t ? std::log(F.tr.A / F.tr.lmax) / F.tr.b : FT(0);
+  }
   const coflux_ice_ocean_params& io = c.ice_ocean;
   P.io.heat_flux = io.heat_flux; P.io.friction = io.friction_velocity; P.io.um_star = (FT)io.characteristic_melting_speed;
   P.io.T0 = (FT)io.liquidus_freshwater_melting_temperature; P.io.slope = (FT)io.liquidus_slope;
@@ -677,6 +695,46 @@ template <typename FT> static void zero_args(FluxArgs<FT>& a) { memset(&a, 0, si
 
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
+// The tile kernel (coflux_solve_tile.cuh) covers similarity theory over the ocean with a bulk interface
+// temperature and one viscosity law; everything else runs the one-cell-per-thread kernel.
+static bool force_v1() {
+  static const bool f = [] { const char* e = std::getenv("COFLUX_FORCE_V1"); return e && e[0] == '1'; }();
+  return f;
+}
+template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
+  const FluxP<FT>& F = dev_params<FT>(c).ao;
+  return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc;
+}
+constexpr int COFLUX_TILE = 512;
+// compile-time specialisation of the hot loop for the OMIP parameter sets (0 = generic)
+template <typename FT> static int tile_spec(const coflux_ctx* c) {
+  const DevParams<FT>& P = dev_params<FT>(c);
+  const FluxP<FT>& F = P.ao;
+  const bool common = P.K.edson && P.K.gust_skip && P.K.fast_q && F.same_scalar && F.mr.kind == COFLUX_ROUGHNESS_CHARNOCK;
+  if (common && F.form == COFLUX_PROFILE_LOGARITHMIC && F.mr.waves == COFLUX_WAVES_CONSTANT &&
+      F.mr.visc.kind == COFLUX_VISCOSITY_CONSTANT) return 1;   // SPEC 1 reads ν from the parameter block
+  if (common && F.form == COFLUX_PROFILE_COARE_LOGARITHMIC && F.mr.waves == COFLUX_WAVES_WIND_DEPENDENT) return 2;
+  return 0;
+}
+template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_tile_spec(const FluxArgs<FT>& a, cudaStream_t st) {
+  auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, COFLUX_TILE, SPEC>;
+  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, SPEC != 1>);
+  static bool configured = false;     // per instantiation
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<grid_for(a.ncell, COFLUX_TILE), 128, smem, st>>>(a);
+  return COFLUX_OK;
+}
+template <typename FT, bool INTERP, bool ASSEMBLE> static int launch_tile(const coflux_ctx* c, const FluxArgs<FT>& a, cudaStream_t st) {
+  switch (tile_spec<FT>(c)) {
+    case 1: return launch_tile_spec<FT, INTERP, ASSEMBLE, 1>(a, st);
+    case 2: return launch_tile_spec<FT, INTERP, ASSEMBLE, 2>(a, st);
+    default: return launch_tile_spec<FT, INTERP, ASSEMBLE, 0>(a, st);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a3
 // ---------------------------------------------------------------------------------------------
@@ -712,7 +770,12 @@ static int do_ao(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   rc = fill_ocean<FT>(c, o, a);
   if (rc) return rc;
   fill_interface_out<FT>(f, a);
-  flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  if (tile_eligible<FT>(c)) {
+    rc = launch_tile<FT, false, false>(c, a, st);
+    if (rc) return rc;
+  } else {
+    flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  }
   return check_launch(c, 1);
 }
 extern "C" int coflux_atmosphere_ocean_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,
@@ -854,6 +917,11 @@ static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_updat
   REQUIRE(out->exchange && out->atmosphere_ocean && out->net_ocean, "exchange, atmosphere_ocean and net_ocean outputs are required");
   REQUIRE(out->atmosphere_ocean->x_momentum.ptr && out->atmosphere_ocean->y_momentum.ptr,
           "x_momentum / y_momentum outputs are required (the stress kernel reads them back)");
+  {
+    const coflux_exchange_state* x = out->exchange;
+    REQUIRE(x->u.ptr && x->v.ptr && x->T.ptr && x->p.ptr && x->q.ptr && x->Qs.ptr && x->Ql.ptr && x->Mp.ptr,
+            "all eight exchange-state output arrays are required");
+  }
   const size_t es = sizeof(FT);
   FluxArgs<FT> a;
   zero_args(a);
@@ -875,7 +943,12 @@ static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_updat
   Profile& pf = c->prof;
   if (pf.on && pf.pending == Profile::RING) { rc = profile_drain(c); if (rc) return rc; }
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][0], st));
-  flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  if (tile_eligible<FT>(c)) {
+    rc = launch_tile<FT, true, true>(c, a, st);
+    if (rc) return rc;
+  } else {
+    flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  }
   rc = check_launch(c, 1);
   if (rc) return rc;
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][1], st));

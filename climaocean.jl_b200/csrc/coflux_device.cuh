@@ -17,16 +17,20 @@
 namespace coflux {
 
 // ---------------------------------------------------------------------------------------------
-// libm dispatch (IEEE-accurate CUDA math library entry points; no fast-math anywhere)
+// libm dispatch (IEEE-accurate CUDA math library entry points; no fast-math anywhere).
+// The transcendental entry points are deliberately NOT inlined: with every call site inlined the
+// similarity loop was 60+ KB of SASS and the kernel stalled on instruction fetch (ncu: stall
+// 'no_instruction' 4.6 per issue, profiles/r01_flux_tile_v2a_*); one shared copy of each keeps the
+// loop inside the instruction cache.
 // ---------------------------------------------------------------------------------------------
 template <typename FT> struct M;
 template <> struct M<double> {
-  static __device__ __forceinline__ double log(double x) { return ::log(x); }
-  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+  static __device__ __noinline__ double log(double x) { return ::log(x); }
+  static __device__ __noinline__ double exp(double x) { return ::exp(x); }
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static __device__ __forceinline__ double cbrt(double x) { return ::cbrt(x); }
-  static __device__ __forceinline__ double atan(double x) { return ::atan(x); }
-  static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+  static __device__ __noinline__ double cbrt(double x) { return ::cbrt(x); }
+  static __device__ __noinline__ double atan(double x) { return ::atan(x); }
+  static __device__ __noinline__ double pow(double x, double y) { return ::pow(x, y); }
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
   static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
   static __device__ __forceinline__ double trunc(double x) { return ::trunc(x); }
@@ -36,12 +40,12 @@ template <> struct M<double> {
   static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
 };
 template <> struct M<float> {
-  static __device__ __forceinline__ float log(float x) { return ::logf(x); }
-  static __device__ __forceinline__ float exp(float x) { return ::expf(x); }
+  static __device__ __noinline__ float log(float x) { return ::logf(x); }
+  static __device__ __noinline__ float exp(float x) { return ::expf(x); }
   static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
-  static __device__ __forceinline__ float cbrt(float x) { return ::cbrtf(x); }
-  static __device__ __forceinline__ float atan(float x) { return ::atanf(x); }
-  static __device__ __forceinline__ float pow(float x, float y) { return ::powf(x, y); }
+  static __device__ __noinline__ float cbrt(float x) { return ::cbrtf(x); }
+  static __device__ __noinline__ float atan(float x) { return ::atanf(x); }
+  static __device__ __noinline__ float pow(float x, float y) { return ::powf(x, y); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float floor(float x) { return ::floorf(x); }
   static __device__ __forceinline__ float trunc(float x) { return ::truncf(x); }
@@ -66,7 +70,7 @@ template <typename FT> struct MomRough {
 };
 template <typename FT> struct ScaRough { int kind; FT fixed, A, b, lmax; Visc<FT> visc; };
 template <typename FT> struct FluxP {
-  int formulation, stability, form, velocity, stop_kind, maxit, itemp, same_scalar;
+  int formulation, stability, form, velocity, stop_kind, maxit, itemp, same_scalar, same_visc, pad_;
   FT tol, kappa, beta, ugmin, init, ly_umin, skin_max_dT;
   MomRough<FT> mr;
   ScaRough<FT> tr, qr;
@@ -75,8 +79,16 @@ template <typename FT> struct IceOceanP {
   int heat_flux, friction;
   FT um_star, T0, slope, alpha_h, alpha_s, ustar_const, ustar_min, rho_i, L_f, Cd, k_ice, h_c;
 };
+// constants of the fast iteration (coflux_solve_tile.cuh), built on the host
+template <typename FT> struct FastConsts {
+  FT lnh;
+  FT lnhA_q, lnhl_q, lrclip_q;     // ln(h/A), ln(h/ℓmax or fixed), ln(A/ℓmax)/b  (water vapour)
+  FT lnhA_t, lnhl_t, lrclip_t;     // same for temperature
+  int edson, gust_skip, fast_q, fast_t;
+};
 template <typename FT> struct DevParams {
   ThermoC<FT> th;
+  FastConsts<FT> K;                // for the atmosphere–ocean parameters
   FT h, hbl, g;
   FT rho0, c0, rhof, Smin, wmf_alpha, T_offset;  // T_offset: 273.15 if ocean T in °C else 0
   FT sigma, alb_o, emis_o, emis_i, alb_i;

@@ -1,0 +1,421 @@
+// coflux_solve_tile.cuh — the production atmosphere–ocean flux kernel (similarity theory, bulk
+// interface temperature), organised to keep the FP64 pipe busy.
+//
+// The v1 kernel (coflux_kernels.cuh::flux_kernel, still used for the Large–Yeager and sea-ice
+// variants) runs one cell per thread start to finish.  Its ncu profile (profiles/r01_*_v1_*) shows
+// what limits it: 21 of 32 lanes active on average (cells of one warp need 9…25 iterations and take
+// different ψ branches), 128 registers → 16 warps/SM, FP64 pipe 37 % busy.  This kernel splits the
+// work of a tile of TILE cells into three convergent phases separated by __syncthreads():
+//
+//   A  per cell: coalesced loads, atmosphere interpolation, exchange-state stores, both
+//      thermodynamic states, and the FIRST similarity iteration (which is uniform: the reference's
+//      initial guess u★=θ★=q★=1e-4 always produces a stable first pass).  The few scalars the
+//      iteration needs go to shared memory as a "task"; tasks are queued sorted by stability class.
+//   B  lanes pop tasks from the shared queue and iterate; a lane whose cell has converged writes
+//      its result back and immediately pops the next task ("lane refill"), so a warp has no idle
+//      lanes until the tile's queue drains, and — because the queue is class-sorted and the first
+//      iteration is already done — all lanes of a warp take the same ψ branch.
+//   C  per cell: fluxes, net-flux assembly, coalesced stores.
+//
+// The iteration itself is algebraically the reference iteration (SURVEY Appendix A4–A6) with
+// rounding-level reformulations (each ≤ a few ulp, covered by the 1e-12 parity tests):
+//   * 1/L★ = κ b★/u★² once, then ζ = h/L★ and ℓ/L★ are products (three divisions fewer);
+//   * g/T_v, 1+δq_v, δT_v hoisted out of the loop (exactly the same values);
+//   * the gustiness cube root is skipped when the buoyancy flux is ≤ 0 (the floor wins anyway);
+//   * Reynolds-scaling scalar roughness ℓ = A·R★^(−b): ln(h/ℓ) = ln(h/A) + b·ln R★ — one log instead
+//     of pow + log; ℓ itself (needed only inside ψ(ℓ/L)) from one exp;
+//   * the Edson ψ_u/ψ_θ pair at the same ζ shares √(1−15ζ), ζ²/(1+ζ²), exp(−0.35ζ); x^1.5 = x·√x;
+//   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ (virtually always after the transient) by the Taylor series of the same
+//     function (tools/gen_psi_taylor.py; |error| < 3e-18) instead of 5–7 transcendental calls;
+//   * a period-2 limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the
+//     resolution) is detected and the state the reference reaches at maxiter is returned directly —
+//     bit-identical to iterating on.
+#pragma once
+#include "coflux_kernels.cuh"
+
+namespace coflux {
+
+template <typename FT> __device__ __forceinline__ FT fma_(FT a, FT b, FT c);
+template <> __device__ __forceinline__ double fma_<double>(double a, double b, double c) { return ::fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_<float>(float a, float b, float c) { return ::fmaf(a, b, c); }
+
+// Taylor series about 0 of the Edson et al. (2013) functions on each branch (coefficients from
+// tools/gen_psi_taylor.py; literals so that they fold into immediates in either precision)
+template <typename FT> __device__ __forceinline__ FT psi_series_m_unst(FT x) {
+  FT acc = FT(-5953014842481.911);
+  acc = fma_<FT>(acc, x, FT(-456221314784.8534));
+  acc = fma_<FT>(acc, x, FT(-35388422828.92556));
+  acc = fma_<FT>(acc, x, FT(-2784789427.619603));
+  acc = fma_<FT>(acc, x, FT(-222988725.74826965));
+  acc = fma_<FT>(acc, x, FT(-18243598.617862545));
+  acc = fma_<FT>(acc, x, FT(-1533783.4280264128));
+  acc = fma_<FT>(acc, x, FT(-133623.07255925206));
+  acc = fma_<FT>(acc, x, FT(-12220.416809168435));
+  acc = fma_<FT>(acc, x, FT(-1198.931685655382));
+  acc = fma_<FT>(acc, x, FT(-131.46927083333333));
+  acc = fma_<FT>(acc, x, FT(-17.578125));
+  acc = fma_<FT>(acc, x, FT(-3.75));
+  acc = fma_<FT>(acc, x, FT(0.0));
+  return acc;
+}
+template <typename FT> __device__ __forceinline__ FT psi_series_m_stab(FT x) {
+  FT acc = FT(-3.2826171875e-06);
+  acc = fma_<FT>(acc, x, FT(6.018131510416667e-05));
+  acc = fma_<FT>(acc, x, FT(-0.000937890625));
+  acc = fma_<FT>(acc, x, FT(0.01205859375));
+  acc = fma_<FT>(acc, x, FT(-0.1225));
+  acc = fma_<FT>(acc, x, FT(0.91875));
+  acc = fma_<FT>(acc, x, FT(-5.2));
+  acc = fma_<FT>(acc, x, FT(0.0));
+  return acc;
+}
+template <typename FT> __device__ __forceinline__ FT psi_series_s_unst(FT x) {
+  FT acc = FT(-4.460966866604527e+17);
+  acc = fma_<FT>(acc, x, FT(-1.5085597225417256e+16));
+  acc = fma_<FT>(acc, x, FT(-522821942131960.25));
+  acc = fma_<FT>(acc, x, FT(-18867805615839.246));
+  acc = fma_<FT>(acc, x, FT(-728767553788.2886));
+  acc = fma_<FT>(acc, x, FT(-31347223918.678947));
+  acc = fma_<FT>(acc, x, FT(-1562843283.4957829));
+  acc = fma_<FT>(acc, x, FT(-91771923.36737002));
+  acc = fma_<FT>(acc, x, FT(-6233166.161298048));
+  acc = fma_<FT>(acc, x, FT(-473686.6082199878));
+  acc = fma_<FT>(acc, x, FT(-39314.5732184928));
+  acc = fma_<FT>(acc, x, FT(-3548.0861371527776));
+  acc = fma_<FT>(acc, x, FT(-355.4458333333333));
+  acc = fma_<FT>(acc, x, FT(-42.1875));
+  acc = fma_<FT>(acc, x, FT(-7.5));
+  acc = fma_<FT>(acc, x, FT(0.0));
+  return acc;
+}
+template <typename FT> __device__ __forceinline__ FT psi_series_s_stab(FT x) {
+  FT acc = FT(0.00025428425045974796);
+  acc = fma_<FT>(acc, x, FT(-0.0005466523981695816));
+  acc = fma_<FT>(acc, x, FT(0.0007096960570987654));
+  acc = fma_<FT>(acc, x, FT(0.006086738425925926));
+  acc = fma_<FT>(acc, x, FT(-0.09034314814814814));
+  acc = fma_<FT>(acc, x, FT(0.6497666666666667));
+  acc = fma_<FT>(acc, x, FT(-4.998666666666667));
+  acc = fma_<FT>(acc, x, FT(-0.005));
+  return acc;
+}
+#define COFLUX_PSI_SMALL 0.001953125 /* 2^-9 */
+
+// Edson ψ_u(z), ψ_θ(z) at the same argument
+template <typename FT> __device__ __forceinline__ void psi_edson_pair(FT z, FT& pm, FT& ps) {
+  if (z >= FT(0)) {
+    const FT dz = M<FT>::min(FT(50), FT(0.35) * z);
+    const FT e = M<FT>::exp(-dz);
+    pm = -FT(0.7) * z - FT(0.75) * (z - FT(5) / FT(0.35)) * e - FT(0.75) * FT(5) / FT(0.35);
+    const FT w = FT(1) + FT(2) / FT(3) * z;
+    ps = -(w * M<FT>::sqrt(w)) - FT(2) / FT(3) * (z - FT(14.28)) * e - FT(8.525);
+  } else {
+    const FT s = M<FT>::sqrt(FT(1) - FT(15) * z);      // (1−15ζ)^{1/2}: x_θ, and x_u²
+    const FT xu = M<FT>::sqrt(s);
+    const FT lg = M<FT>::log((FT(1) + s) / FT(2));
+    const FT pku = FT(2) * M<FT>::log((FT(1) + xu) / FT(2)) + lg - FT(2) * M<FT>::atan(xu) + M<FT>::pi() / FT(2);
+    const FT pks = FT(2) * lg;
+    const FT pcu = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(10.15) * z));
+    const FT pcs = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(34.15) * z));
+    const FT f = z * z / (FT(1) + z * z);
+    pm = (FT(1) - f) * pku + f * pcu;
+    ps = (FT(1) - f) * pks + f * pcs;
+  }
+}
+template <typename FT, int SPEC> __device__ __forceinline__ FT psi_small_momentum(bool edson, int stab, FT x) {
+  if (edson && M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_m_stab<FT>(x) : psi_series_m_unst<FT>(x);
+  return psi_momentum(SPEC ? (int)COFLUX_STABILITY_EDSON : stab, x);
+}
+template <typename FT, int SPEC> __device__ __forceinline__ FT psi_small_scalar(bool edson, int stab, FT x) {
+  if (edson && M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_s_stab<FT>(x) : psi_series_s_unst<FT>(x);
+  return psi_scalar(SPEC ? (int)COFLUX_STABILITY_EDSON : stab, x);
+}
+
+// ln(h/ℓ) and ℓ of one scalar roughness length.  Returns false when ℓ = 0 (profile = +∞ ⇒ χ = 0).
+// SPEC != 0: the parameterisation is known at compile time to be Reynolds scaling with A, b, ℓmax > 0.
+template <typename FT, int SPEC>
+__device__ __forceinline__ bool scalar_log_roughness(const ScaRough<FT>& r, bool fast, FT lnhA, FT lnhl, FT lrclip, bool need_l, FT lnh,
+                                                     FT lu, FT u0, FT nu, FT& ln_h_l, FT& l) {
+  if (!SPEC && r.kind == COFLUX_ROUGHNESS_FIXED) { ln_h_l = lnhl; l = r.fixed; return true; }
+  const FT Rstar = lu * u0 / nu;
+  if (Rstar == FT(0)) { l = FT(0); ln_h_l = M<FT>::inf(); return false; }
+  if ((SPEC || fast) && Rstar > FT(0)) {
+    const FT lr = M<FT>::log(Rstar);
+    if (lr > lrclip) {                       // A·R★^(−b) < ℓ_max
+      ln_h_l = fma_<FT>(r.b, lr, lnhA);
+      l = need_l ? r.A * M<FT>::exp(-r.b * lr) : FT(0);
+    } else {
+      ln_h_l = lnhl; l = r.lmax;
+    }
+    return true;
+  }
+  if (SPEC) { l = FT(0); ln_h_l = M<FT>::inf(); return false; }   // R★ < 0 or NaN: unreachable for sane iterates
+  l = M<FT>::min(r.A / M<FT>::pow(Rstar, r.b), r.lmax);
+  ln_h_l = lnh - M<FT>::log(l);
+  return true;
+}
+
+// One fixed-point pass (A4), fast formulation.  Inputs: invariants of the cell; in/out: the scales.
+// SPEC selects a compile-time specialisation so that the hot loop carries no dead generic code:
+//   0  everything decided at run time (any parameter set the tile kernel is eligible for)
+//   1  `:default`   — Edson ψ, standard log profile, constant Charnock, Reynolds-scaling scalars (θ ≡ q)
+//   2  `:corrected` — Edson ψ, COARE log profile, wind-dependent Charnock, Reynolds-scaling scalars (θ ≡ q)
+template <typename FT, int SPEC>
+__device__ __forceinline__ void iterate_fast(const DevParams<FT>& P, const FluxP<FT>& F, const FastConsts<FT>& K, FT U2, FT dth, FT dq,
+                                             FT gTv, FT a1, FT a2, FT nu, FT& us, FT& ts, FT& qs) {
+  const bool edson = SPEC ? true : (K.edson != 0);
+  const bool logform = (SPEC == 1) ? true : ((SPEC == 2) ? false : (F.form == COFLUX_PROFILE_LOGARITHMIC));
+  const bool gust_skip = SPEC ? true : (K.gust_skip != 0);
+  const bool same_scalar = SPEC ? true : (F.same_scalar != 0);
+  const FT u0 = us, t0 = ts, q0 = qs;
+  const FT kappa = F.kappa, h = P.h;
+  const FT bstar = gTv * (t0 * a1 + a2 * q0);
+  const FT Jb = -u0 * bstar;
+  FT UG = F.ugmin;
+  if (!gust_skip || Jb > FT(0)) UG = M<FT>::max(F.beta * M<FT>::cbrt(Jb * P.hbl), F.ugmin);
+  const FT U = M<FT>::sqrt(U2 + UG * UG);
+  if (U == FT(0)) { us = ts = qs = FT(0); return; }
+  FT lu;
+  if (SPEC) {
+    FT alpha = F.mr.alpha;
+    if (SPEC == 2) alpha = M<FT>::max(F.mr.a1 * M<FT>::min(U, F.mr.umax) + F.mr.a2, F.mr.amin);
+    const FT lR = (u0 == FT(0)) ? F.mr.lmax : F.mr.beta_s * nu / u0;
+    lu = M<FT>::min(alpha * u0 * u0 / F.mr.g + lR, F.mr.lmax);
+  } else {
+    lu = momentum_roughness(F.mr, u0, U, nu);
+  }
+  const FT invL = (bstar == FT(0)) ? FT(0) : kappa * bstar / (u0 * u0);
+  const FT zeta = h * invL;
+  FT psi_hm, psi_hs;
+  if (edson) psi_edson_pair<FT>(zeta, psi_hm, psi_hs);
+  else { psi_hm = psi_momentum(F.stability, zeta); psi_hs = psi_scalar(F.stability, zeta); }
+  FT prof_u = (K.lnh - M<FT>::log(lu)) - psi_hm;
+  if (logform) prof_u += psi_small_momentum<FT, SPEC>(edson, F.stability, lu * invL);
+  if (!(prof_u > FT(0))) { us = ts = qs = FT(0); return; }
+  FT lnq, lq;
+  FT chi_q = FT(0);
+  if (scalar_log_roughness<FT, SPEC>(F.qr, K.fast_q != 0, K.lnhA_q, K.lnhl_q, K.lrclip_q, logform, K.lnh, lu, u0, nu, lnq, lq)) {
+    FT prof_q = lnq - psi_hs;
+    if (logform) prof_q += psi_small_scalar<FT, SPEC>(edson, F.stability, lq * invL);
+    chi_q = (prof_q > FT(0)) ? kappa / prof_q : FT(0);
+  }
+  FT chi_t = chi_q;
+  if (!same_scalar) {
+    FT lnt, lt;
+    chi_t = FT(0);
+    if (scalar_log_roughness<FT, 0>(F.tr, K.fast_t != 0, K.lnhA_t, K.lnhl_t, K.lrclip_t, logform, K.lnh, lu, u0, nu, lnt, lt)) {
+      FT prof_t = lnt - psi_hs;
+      if (logform) prof_t += psi_small_scalar<FT, 0>(edson, F.stability, lt * invL);
+      chi_t = (prof_t > FT(0)) ? kappa / prof_t : FT(0);
+    }
+  }
+  const FT chi_u = kappa / prof_u;
+  us = chi_u * U; ts = chi_t * dth; qs = chi_q * dq;
+}
+
+template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT>& F, int it, FT us, FT ts, FT qs, FT u0, FT t0, FT q0) {
+  if (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS) return it < F.maxit;
+  const FT drift = M<FT>::abs(us - u0) + M<FT>::abs(ts - t0) + M<FT>::abs(qs - q0);
+  return !((drift < F.tol) || (it >= F.maxit));
+}
+
+// shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
+template <typename FT, int TILE, bool VARNU> struct TileSmem {
+  FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
+  FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
+  FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
+  FT rho[TILE], cp[TILE];                                 // carried to phase C
+  int it[TILE];
+  unsigned short queue[TILE];
+  int n_front, n_back, head;
+};
+#ifndef COFLUX_TILE_MIN_BLOCKS
+#define COFLUX_TILE_MIN_BLOCKS 5
+#endif
+
+template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
+__global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
+  TileSmem<FT, TILE, VARNU>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU>*>(smem_raw);
+  const DevParams<FT>& P = a.P;
+  const FluxP<FT>& F = P.ao;
+  const ThermoC<FT>& c = P.th;
+  const int tid = threadIdx.x;
+  const long long tile0 = (long long)blockIdx.x * TILE;
+  if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
+  __syncthreads();
+  const FastConsts<FT>& K = P.K;
+  const FT delta = c.eps - FT(1);
+  const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+
+  // ------------------------------------------------------------------ phase A
+  for (int cidx = tid; cidx < TILE; cidx += 128) {
+    const long long idx = tile0 + cidx;
+    if (idx >= a.ncell) { sm.it[cidx] = -1; continue; }
+    const int jj = (int)(idx / a.nxr);
+    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const int i = ii - a.ring, j = jj - a.ring;
+    FT ua, va, Ta, pa, qa;
+    if (INTERP) {
+      const FT fi = ldg<FT>(a.fi, i, j), fj = ldg<FT>(a.fj, i, j);
+      const int i0 = (int)M<FT>::trunc(fi), j0 = (int)M<FT>::trunc(fj);
+      const int i1 = i0 + ((fi > FT(0)) - (fi < FT(0))), j1 = j0 + ((fj > FT(0)) - (fj < FT(0)));
+      const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
+      const FT w00 = (FT(1) - xi) * (FT(1) - eta), w01 = (FT(1) - xi) * eta, w10 = xi * (FT(1) - eta), w11 = xi * eta;
+      ua = interp_series<FT>(a.su, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      va = interp_series<FT>(a.sv, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      Ta = interp_series<FT>(a.sT, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      qa = interp_series<FT>(a.sq, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      pa = interp_series<FT>(a.sp, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      const FT Qs = interp_series<FT>(a.sQs, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      const FT Ql = interp_series<FT>(a.sQl, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      FT Mp = FT(0);
+      if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      if (a.cs.p && a.sn.p) {
+        const FT cs = ldg<FT>(a.cs, i, j), sn = ldg<FT>(a.sn, i, j);
+        const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
+        ua = ur; va = vr;
+      }
+      stg<FT>(a.xu, i, j, ua); stg<FT>(a.xv, i, j, va); stg<FT>(a.xT, i, j, Ta); stg<FT>(a.xp, i, j, pa);
+      stg<FT>(a.xq, i, j, qa); stg<FT>(a.xQs, i, j, Qs); stg<FT>(a.xQl, i, j, Ql); stg<FT>(a.xMp, i, j, Mp);
+    } else {
+      ua = ldg<FT>(a.xu, i, j); va = ldg<FT>(a.xv, i, j); Ta = ldg<FT>(a.xT, i, j); pa = ldg<FT>(a.xp, i, j);
+      qa = ldg<FT>(a.xq, i, j);
+    }
+    FT us = FT(0), ts = FT(0), qs = FT(0);
+    int it = 0;
+    if (is_active(a.mask, i, j)) {
+      const FT uo = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+      const FT vo = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+      const FT Ts = ldg<FT>(a.oT, i, j) + P.T_offset;
+      const FT So = ldg<FT>(a.oS, i, j);
+      const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
+      FT du, dv;
+      if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = ua - uo; dv = va - vo; } else { du = ua; dv = va; }
+      const FT s = So / FT(1000);
+      const FT x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s);
+      const FT theta_a = Ta + P.g * P.h / atm.cp_m;
+      const SurfaceState<FT> S = surface_state<FT, 0>(P, F, atm, pa, theta_a, x, Ts);
+      const FT U2 = du * du + dv * dv, gTv = P.g / S.T_v, a1 = FT(1) + delta * S.q_vap, a2 = delta * S.T_v;
+      sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
+      us = ts = qs = F.init;
+      bool go = fixed ? (F.maxit > 0) : true;
+      if (go) {
+        iterate_fast<FT, SPEC>(P, F, K, U2, S.dtheta, S.dq, gTv, a1, a2, S.nu_m, us, ts, qs);
+        it = 1;
+        go = keep_going<FT>(F, it, us, ts, qs, F.init, F.init, F.init);
+      }
+      if (go) {
+        sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.Tv[cidx] = S.T_v; sm.qv[cidx] = S.q_vap;
+        if (VARNU) sm.nu[cidx] = S.nu_m;
+        // stability class of every later pass: sign of the buoyancy scale ∝ Δθ·a1 + a2·Δq (χ_θ = χ_q > 0)
+        const bool unstable = (S.dtheta * a1 + a2 * S.dq) < FT(0);
+        if (unstable) sm.queue[atomicAdd(&sm.n_front, 1)] = (unsigned short)cidx;
+        else sm.queue[TILE - 1 - atomicAdd(&sm.n_back, 1)] = (unsigned short)cidx;
+      }
+    }
+    sm.us[cidx] = us; sm.ts[cidx] = ts; sm.qs[cidx] = qs; sm.it[cidx] = it;
+  }
+  __syncthreads();
+
+  const int n_front = sm.n_front, n_total = sm.n_front + sm.n_back;
+
+  // ------------------------------------------------------------------ phase B: lane refill
+  {
+    int slot = -1, it = 0;
+    FT U2 = 0, dth = 0, dq = 0, gTv = 0, a1 = 0, a2 = 0, nu = 0, us = 0, ts = 0, qs = 0, pu = 0, pt = 0, pq = 0;
+    auto pop = [&]() {
+      int pos = atomicAdd(&sm.head, 1);
+      slot = -1;
+      while (pos < n_total) {
+        const int sl = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
+        const int it0 = sm.it[sl];
+        slot = sl;
+        U2 = sm.U2[slot]; dth = sm.dth[slot]; dq = sm.dq[slot];
+        { const FT Tv = sm.Tv[slot], qv = sm.qv[slot]; gTv = P.g / Tv; a1 = FT(1) + delta * qv; a2 = delta * Tv; }
+        nu = VARNU ? sm.nu[slot] : F.mr.visc.nu;
+        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = it0;
+        pu = pt = pq = M<FT>::inf();
+        break;
+      }
+    };
+    pop();
+    while (__any_sync(0xffffffffu, slot >= 0)) {
+      if (slot >= 0) {
+        const FT u0 = us, t0 = ts, q0 = qs;
+        iterate_fast<FT, SPEC>(P, F, K, U2, dth, dq, gTv, a1, a2, nu, us, ts, qs);
+        ++it;
+        bool go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
+        if (go && !fixed && us == pu && ts == pt && qs == pq) {
+          // period-2 limit cycle (…, A, B, A): the reference keeps alternating until maxiter
+          if (((F.maxit - it) & 1) != 0) { us = u0; ts = t0; qs = q0; }
+          it = F.maxit;
+          go = false;
+        }
+        pu = u0; pt = t0; pq = q0;
+        if (!go) {
+          sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
+          pop();
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase C
+  for (int cidx = tid; cidx < TILE; cidx += 128) {
+    const long long idx = tile0 + cidx;
+    if (idx >= a.ncell) continue;
+    const int jj = (int)(idx / a.nxr);
+    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const int i = ii - a.ring, j = jj - a.ring;
+    const FT Tunits = ldg<FT>(a.oT, i, j);
+    const bool act = is_active(a.mask, i, j);
+    FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0);
+    const FT us = sm.us[cidx], ts = sm.ts[cidx], qs = sm.qs[cidx];
+    if (act) {
+      // the exchange state was written by this very thread in phase A (or is an input): plain loads
+      const FT ua = reinterpret_cast<const FT*>(a.xu.p)[(int64_t)i * a.xu.si + (int64_t)j * a.xu.sj];
+      const FT va = reinterpret_cast<const FT*>(a.xv.p)[(int64_t)i * a.xv.si + (int64_t)j * a.xv.sj];
+      const FT Ta = reinterpret_cast<const FT*>(a.xT.p)[(int64_t)i * a.xT.si + (int64_t)j * a.xT.sj];
+      FT du, dv;
+      if (F.velocity == COFLUX_VELOCITY_RELATIVE) {
+        du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+        dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+      } else { du = ua; dv = va; }
+      const FT rho = sm.rho[cidx], cp = sm.cp[cidx];
+      const FT dU = M<FT>::sqrt(du * du + dv * dv);
+      const FT taux = (dU == FT(0)) ? dU : -us * us * du / dU;
+      const FT tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
+      const FT LH = c.LH_v0 + (c.cp_v - c.cp_l) * (Ta - c.T_0);
+      Qv = -rho * us * qs * LH;
+      Qc = -rho * cp * us * ts;
+      Fv = -rho * us * qs;
+      rtx = rho * taux; rty = rho * tauy;
+    }
+    stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
+    stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tunits);
+    stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
+    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? sm.it[cidx] : 0;
+    if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
+    if (ASSEMBLE) {
+      if (i >= 0 && i < a.Nx && j >= 0 && j < a.Ny) {
+        const FT Qs = reinterpret_cast<const FT*>(a.xQs.p)[(int64_t)i * a.xQs.si + (int64_t)j * a.xQs.sj];
+        const FT Ql = reinterpret_cast<const FT*>(a.xQl.p)[(int64_t)i * a.xQl.si + (int64_t)j * a.xQl.sj];
+        const FT Mp = reinterpret_cast<const FT*>(a.xMp.p)[(int64_t)i * a.xMp.si + (int64_t)j * a.xMp.sj];
+        const FT So = ldg<FT>(a.oS, i, j);
+        const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
+        const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
+        const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
+        FT JT, JS, Qu, Qal, Qts, J0;
+        assemble_tracers<FT>(P, act, conc, So, Tunits + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio, JT, JS, Qu, Qal, Qts, J0);
+        stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
+        stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
+      }
+    }
+  }
+}
+
+}  // namespace coflux
