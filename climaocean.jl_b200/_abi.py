@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcoflux.so")
+LIB_PATH = os.environ.get("COFLUX_LIB") or os.path.join(_HERE, "lib", "libcoflux.so")   # COFLUX_LIB: tuning variants
 
 ABI_VERSION = 1
 F32, F64 = 32, 64

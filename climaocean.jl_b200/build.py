@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SRC = os.path.join(HERE, "csrc", "coflux_abi.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "coflux_kernels.cuh"), os.path.join(HERE, "csrc", "coflux_device.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "coflux_kernels.cuh"), os.path.join(HERE, "csrc", "coflux_solve_tile.cuh"), os.path.join(HERE, "csrc", "coflux_device.cuh"),
         os.path.join(ROOT, "include", "coflux.h")]
 OUT = os.path.join(HERE, "lib", "libcoflux.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -21,12 +21,13 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_cuda(force=False, verbose=False):
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if force or _stale(OUT, DEPS):
-        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+def build_cuda(force=False, verbose=False, out=OUT, defines=()):
+    """nvcc → lib/libcoflux.so.  `out`/`defines` build tuning variants (tools/ab_variants.py)."""
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _stale(out, DEPS):
+        cmd = [NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
         subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 def build_oracle(force=False):

@@ -56,16 +56,17 @@ extern "C" int coflux_sizeof(const char* name) {
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-struct HostStage {   // device staging planes for coflux_update_state_host
+struct HostStage {   // device staging planes + pipeline resources for coflux_update_state_host
+  static const int MAX_CHUNKS = 8;
   int halo = -1;
   size_t plane_bytes = 0;
   char* in[4] = {nullptr, nullptr, nullptr, nullptr};     // ocean u v T S
   char* xch[8] = {};                                     // exchange state
   char* ao[6] = {};                                      // Qv Qc Fv ρτx ρτy Ts
   char* net[8] = {};                                     // τx τy JT JS Qu Qal Qts J0
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_in = nullptr, copy_out = nullptr;
-  cudaEvent_t ev_in[4] = {}, ev_k = nullptr, ev_k2 = nullptr;
+  cudaStream_t stream = nullptr;                         // compute
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;    // H2D / D2H
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
 };
 struct Seam {
   bool attached = false;
@@ -497,8 +498,7 @@ static void free_stage(HostStage& s) {
   if (s.copy_in) cudaStreamDestroy(s.copy_in);
   if (s.copy_out) cudaStreamDestroy(s.copy_out);
   for (cudaEvent_t& ev : s.ev_in) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-  if (s.ev_k) cudaEventDestroy(s.ev_k);
-  if (s.ev_k2) cudaEventDestroy(s.ev_k2);
+  for (cudaEvent_t& ev : s.ev_k) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
   s = HostStage();
 }
 
@@ -641,6 +641,7 @@ template <typename FT> static void fill_geometry(const coflux_ctx* c, FluxArgs<F
   const coflux_grid_desc& g = c->cfg.grid;
   a.ring = g.ring; a.Nx = g.Nx; a.Ny = g.Ny;
   a.nxr = g.Nx + 2 * g.ring; a.nyr = g.Ny + 2 * g.ring;
+  a.cell0 = 0;
   a.ncell = (long long)a.nxr * a.nyr;
   a.P = dev_params<FT>(c);
   a.seam_east = nullptr;
@@ -724,7 +725,7 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<grid_for(a.ncell, COFLUX_TILE), 128, smem, st>>>(a);
+  kern<<<grid_for(a.ncell - a.cell0, COFLUX_TILE), 128, smem, st>>>(a);
   return COFLUX_OK;
 }
 template <typename FT, bool INTERP, bool ASSEMBLE> static int launch_tile(const coflux_ctx* c, const FluxArgs<FT>& a, cudaStream_t st) {
@@ -774,7 +775,7 @@ static int do_ao(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
     rc = launch_tile<FT, false, false>(c, a, st);
     if (rc) return rc;
   } else {
-    flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+    flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
   }
   return check_launch(c, 1);
 }
@@ -872,6 +873,7 @@ static void fill_stress(const coflux_ctx* c, const coflux_ocean_surface* o, cons
   s.taux = view2d(out->u, 0, es); s.tauy = view2d(out->v, 0, es);
   s.seam_west = nullptr;
   s.rho0 = dev_params<FT>(c).rho0;
+  s.cell0 = 0; s.cell1 = (long long)g.Nx * g.Ny;
 }
 template <typename FT>
 static int do_assemble(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, const coflux_interface_fluxes* ao,
@@ -911,7 +913,8 @@ extern "C" int coflux_assemble_net_ocean_fluxes(coflux_ctx* c, const coflux_exch
 // a2: fused update_state!
 // ---------------------------------------------------------------------------------------------
 template <typename FT>
-static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_update_outputs* out, double time, cudaStream_t st) {
+static int build_update_args(coflux_ctx* c, const coflux_update_inputs* in, coflux_update_outputs* out, double time, FluxArgs<FT>& a,
+                             StressArgs<FT>& s) {
   REQUIRE(in && out, "NULL argument");
   REQUIRE(in->atmosphere && in->ocean, "atmosphere series and ocean surface are required");
   REQUIRE(out->exchange && out->atmosphere_ocean && out->net_ocean, "exchange, atmosphere_ocean and net_ocean outputs are required");
@@ -923,7 +926,6 @@ static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_updat
             "all eight exchange-state output arrays are required");
   }
   const size_t es = sizeof(FT);
-  FluxArgs<FT> a;
   zero_args(a);
   fill_geometry(c, a);
   int rc = fill_interp<FT>(c, in->atmosphere, time, out->exchange, a);
@@ -940,24 +942,44 @@ static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_updat
   a.JT = view2d(n->T, 0, es); a.JS = view2d(n->S, 0, es); a.Qu = view2d(n->upwelling_longwave, 0, es);
   a.Qal = view2d(n->downwelling_longwave, 0, es); a.Qts = view2d(n->downwelling_shortwave, 0, es);
   a.J0 = view2d(n->penetrating_shortwave, 0, es);
+  memset(&s, 0, sizeof(s));
+  fill_stress<FT>(c, in->ocean, out->atmosphere_ocean, ice, io, n, s);
+  return COFLUX_OK;
+}
+// flux kernel over rows jj ∈ [jj_lo, jj_hi) of the ring-extended surface
+template <typename FT> static int launch_flux_rows(coflux_ctx* c, FluxArgs<FT> a, int jj_lo, int jj_hi, cudaStream_t st) {
+  a.cell0 = (long long)jj_lo * a.nxr;
+  a.ncell = (long long)jj_hi * a.nxr;
+  if (a.ncell <= a.cell0) return COFLUX_OK;
+  if (tile_eligible<FT>(c)) {
+    int rc = launch_tile<FT, true, true>(c, a, st);
+    if (rc) return rc;
+  } else {
+    flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
+  }
+  return check_launch(c, 1);
+}
+// stress kernel over interior rows j ∈ [j_lo, j_hi)
+template <typename FT> static int launch_stress_rows(coflux_ctx* c, StressArgs<FT> s, int j_lo, int j_hi, cudaStream_t st) {
+  s.cell0 = (long long)j_lo * s.Nx;
+  s.cell1 = (long long)j_hi * s.Nx;
+  if (s.cell1 <= s.cell0) return COFLUX_OK;
+  stress_kernel<FT><<<grid_for(s.cell1 - s.cell0, 256), 256, 0, st>>>(s);
+  return check_launch(c, 1);
+}
+template <typename FT>
+static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_update_outputs* out, double time, cudaStream_t st) {
+  FluxArgs<FT> a;
+  StressArgs<FT> s;
+  int rc = build_update_args<FT>(c, in, out, time, a, s);
+  if (rc) return rc;
   Profile& pf = c->prof;
   if (pf.on && pf.pending == Profile::RING) { rc = profile_drain(c); if (rc) return rc; }
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][0], st));
-  if (tile_eligible<FT>(c)) {
-    rc = launch_tile<FT, true, true>(c, a, st);
-    if (rc) return rc;
-  } else {
-    flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
-  }
-  rc = check_launch(c, 1);
+  rc = launch_flux_rows<FT>(c, a, 0, a.nyr, st);
   if (rc) return rc;
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][1], st));
-  StressArgs<FT> s;
-  memset(&s, 0, sizeof(s));
-  fill_stress<FT>(c, in->ocean, out->atmosphere_ocean, ice, io, n, s);
-  const coflux_grid_desc& g = c->cfg.grid;
-  stress_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(s);
-  rc = check_launch(c, 1);
+  rc = launch_stress_rows<FT>(c, s, 0, s.Ny, st);
   if (rc) return rc;
   if (pf.on) { CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][2], st)); pf.pending += 1; }
   return COFLUX_OK;
@@ -980,17 +1002,14 @@ static coflux_array plane_desc(void* p, int Nx, int halo) {
   a.off_i = halo; a.off_j = halo; a.off_k = 0;
   return a;
 }
-extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series* atm, const coflux_host_step* step, double time,
-                                        int64_t* h2d_bytes, int64_t* d2h_bytes) {
-  REQUIRE(c && atm && step, "NULL argument");
-  REQUIRE(step->ocean_u && step->ocean_v && step->ocean_T && step->ocean_S, "host ocean planes are required");
-  REQUIRE(step->net_u && step->net_v && step->net_T && step->net_S, "host net-flux planes are required");
-  REQUIRE(step->halo >= 2, "host planes need a halo of at least 2 cells");
-  CUDA_TRY(cudaSetDevice(c->device));
+template <typename FT>
+static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const coflux_host_step* step, double time, int64_t* h2d_bytes,
+                          int64_t* d2h_bytes) {
   const coflux_grid_desc& g = c->cfg.grid;
-  const size_t es = (c->cfg.dtype == COFLUX_F64) ? 8 : 4;
+  const size_t es = sizeof(FT);
   const int H = step->halo;
-  const size_t plane = (size_t)(g.Nx + 2 * H) * (size_t)(g.Ny + 2 * H) * es;
+  const int ni = g.Nx + 2 * H, nj = g.Ny + 2 * H;
+  const size_t row = (size_t)ni * es, plane = row * (size_t)nj;
   HostStage& s = c->stage;
   if (s.halo != H || s.plane_bytes != plane) {
     free_stage(s);
@@ -999,16 +1018,15 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
     for (char*& p : s.xch) CUDA_TRY(cudaMalloc(&p, plane));
     for (char*& p : s.ao) CUDA_TRY(cudaMalloc(&p, plane));
     for (char*& p : s.net) CUDA_TRY(cudaMalloc(&p, plane));
+    for (char* p : s.net) CUDA_TRY(cudaMemset(p, 0, plane));
+    for (char* p : s.ao) CUDA_TRY(cudaMemset(p, 0, plane));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
     for (cudaEvent_t& ev : s.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&s.ev_k2, cudaEventDisableTiming));
+    for (cudaEvent_t& ev : s.ev_k) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaDeviceSynchronize());
   }
-  const void* hin[4] = {step->ocean_u, step->ocean_v, step->ocean_T, step->ocean_S};
-  for (int k = 0; k < 4; ++k) CUDA_TRY(cudaMemcpyAsync(s.in[k], hin[k], plane, cudaMemcpyHostToDevice, s.stream));
-
   coflux_ocean_surface ocean;
   memset(&ocean, 0, sizeof(ocean));
   // planes are the k = Nz-1 level: present them as 3-D parents with stride_k = 0
@@ -1031,17 +1049,69 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
   in.atmosphere = atm; in.ocean = &ocean;
   coflux_update_outputs out;
   out.exchange = &xch; out.atmosphere_ocean = &ao; out.net_ocean = &net;
-  int rc = coflux_update_state(c, &in, &out, time, s.stream);
+  FluxArgs<FT> a;
+  StressArgs<FT> sa;
+  int rc = build_update_args<FT>(c, &in, &out, time, a, sa);
   if (rc) return rc;
-  void* hout[4] = {step->net_u, step->net_v, step->net_T, step->net_S};
-  int64_t d2h = 0;
-  for (int k = 0; k < 4; ++k) { CUDA_TRY(cudaMemcpyAsync(hout[k], s.net[k], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
-  if (step->latent_heat) { CUDA_TRY(cudaMemcpyAsync(step->latent_heat, s.ao[0], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
-  if (step->sensible_heat) { CUDA_TRY(cudaMemcpyAsync(step->sensible_heat, s.ao[1], plane, cudaMemcpyDeviceToHost, s.stream)); d2h += (int64_t)plane; }
+
+  // Row-chunk pipeline: H2D(c+1) ‖ kernels(c) ‖ D2H(c-1) on three streams.  Chunk c of the flux kernel
+  // covers ring-extended rows [f[c], f[c+1]); it reads ocean rows up to one past its last row, i.e. the
+  // first parent row of H2D chunk c+1, so it waits for that chunk.  The stress rows that became
+  // computable (they need ρτy of the previous row) follow, then their D2H.
+  const int ring = g.ring, nyr = a.nyr;
+  int nch = HostStage::MAX_CHUNKS;
+  if (g.Ny < 8 * nch) nch = 1;
+  int f[HostStage::MAX_CHUNKS + 1], r[HostStage::MAX_CHUNKS + 1], sj[HostStage::MAX_CHUNKS + 1];
+  for (int k = 0; k <= nch; ++k) f[k] = (int)((long long)nyr * k / nch);
+  r[0] = 0; r[nch] = nj;
+  for (int k = 1; k < nch; ++k) r[k] = f[k] - ring + H;            // parent row of surface row jj = f[k]
+  sj[0] = 0; sj[nch] = g.Ny;
+  for (int k = 1; k < nch; ++k) { int v = f[k] - ring - 1; sj[k] = v < 0 ? 0 : (v > g.Ny ? g.Ny : v); }
+  const void* hin[4] = {step->ocean_u, step->ocean_v, step->ocean_T, step->ocean_S};
+  void* hout[6] = {step->net_u, step->net_v, step->net_T, step->net_S, step->latent_heat, step->sensible_heat};
+  char* dout[6] = {s.net[0], s.net[1], s.net[2], s.net[3], s.ao[0], s.ao[1]};
+  int64_t h2d = 0, d2h = 0;
+  for (int k = 0; k < nch; ++k) {
+    const size_t off = (size_t)r[k] * row, len = (size_t)(r[k + 1] - r[k]) * row;
+    for (int q = 0; q < 4; ++q)
+      CUDA_TRY(cudaMemcpyAsync(s.in[q] + off, static_cast<const char*>(hin[q]) + off, len, cudaMemcpyHostToDevice, s.copy_in));
+    h2d += 4 * (int64_t)len;
+    CUDA_TRY(cudaEventRecord(s.ev_in[k], s.copy_in));
+  }
+  for (int k = 0; k < nch; ++k) {
+    CUDA_TRY(cudaStreamWaitEvent(s.stream, s.ev_in[(k + 1 < nch) ? k + 1 : k], 0));
+    rc = launch_flux_rows<FT>(c, a, f[k], f[k + 1], s.stream);
+    if (rc) return rc;
+    rc = launch_stress_rows<FT>(c, sa, sj[k], sj[k + 1], s.stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s.ev_k[k], s.stream));
+    CUDA_TRY(cudaStreamWaitEvent(s.copy_out, s.ev_k[k], 0));
+    // D2H: the interior rows just completed; the first / last chunk also carry the (untouched) halo rows
+    const int p0 = (k == 0) ? 0 : sj[k] + H, p1 = (k == nch - 1) ? nj : sj[k + 1] + H;
+    if (p1 > p0) {
+      const size_t off = (size_t)p0 * row, len = (size_t)(p1 - p0) * row;
+      for (int q = 0; q < 6; ++q) {
+        if (!hout[q]) continue;
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(hout[q]) + off, dout[q] + off, len, cudaMemcpyDeviceToHost, s.copy_out));
+        d2h += (int64_t)len;
+      }
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s.copy_out));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
-  if (h2d_bytes) *h2d_bytes = 4 * (int64_t)plane;
+  if (h2d_bytes) *h2d_bytes = h2d;
   if (d2h_bytes) *d2h_bytes = d2h;
   return COFLUX_OK;
+}
+extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series* atm, const coflux_host_step* step, double time,
+                                        int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  REQUIRE(c && atm && step, "NULL argument");
+  REQUIRE(step->ocean_u && step->ocean_v && step->ocean_T && step->ocean_S, "host ocean planes are required");
+  REQUIRE(step->net_u && step->net_v && step->net_T && step->net_S, "host net-flux planes are required");
+  REQUIRE(step->halo >= 2, "host planes need a halo of at least 2 cells");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return c->cfg.dtype == COFLUX_F64 ? do_update_host<double>(c, atm, step, time, h2d_bytes, d2h_bytes)
+                                    : do_update_host<float>(c, atm, step, time, h2d_bytes, d2h_bytes);
 }
 
 // ---------------------------------------------------------------------------------------------

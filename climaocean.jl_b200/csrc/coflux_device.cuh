@@ -23,14 +23,42 @@ namespace coflux {
 // 'no_instruction' 4.6 per issue, profiles/r01_flux_tile_v2a_*); one shared copy of each keeps the
 // loop inside the instruction cache.
 // ---------------------------------------------------------------------------------------------
+#ifndef COFLUX_MATH_INLINE_MASK
+#define COFLUX_MATH_INLINE_MASK 0      /* bit0 log, bit1 exp, bit2 cbrt, bit3 atan, bit4 pow: 1 = force inline (tuning) */
+#endif
+#if COFLUX_MATH_INLINE_MASK & 1
+#define COFLUX_INL_LOG __forceinline__
+#else
+#define COFLUX_INL_LOG __noinline__
+#endif
+#if COFLUX_MATH_INLINE_MASK & 2
+#define COFLUX_INL_EXP __forceinline__
+#else
+#define COFLUX_INL_EXP __noinline__
+#endif
+#if COFLUX_MATH_INLINE_MASK & 4
+#define COFLUX_INL_CBRT __forceinline__
+#else
+#define COFLUX_INL_CBRT __noinline__
+#endif
+#if COFLUX_MATH_INLINE_MASK & 8
+#define COFLUX_INL_ATAN __forceinline__
+#else
+#define COFLUX_INL_ATAN __noinline__
+#endif
+#if COFLUX_MATH_INLINE_MASK & 16
+#define COFLUX_INL_POW __forceinline__
+#else
+#define COFLUX_INL_POW __noinline__
+#endif
 template <typename FT> struct M;
 template <> struct M<double> {
-  static __device__ __noinline__ double log(double x) { return ::log(x); }
-  static __device__ __noinline__ double exp(double x) { return ::exp(x); }
+  static __device__ COFLUX_INL_LOG double log(double x) { return ::log(x); }
+  static __device__ COFLUX_INL_EXP double exp(double x) { return ::exp(x); }
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static __device__ __noinline__ double cbrt(double x) { return ::cbrt(x); }
-  static __device__ __noinline__ double atan(double x) { return ::atan(x); }
-  static __device__ __noinline__ double pow(double x, double y) { return ::pow(x, y); }
+  static __device__ COFLUX_INL_CBRT double cbrt(double x) { return ::cbrt(x); }
+  static __device__ COFLUX_INL_ATAN double atan(double x) { return ::atan(x); }
+  static __device__ COFLUX_INL_POW double pow(double x, double y) { return ::pow(x, y); }
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
   static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
   static __device__ __forceinline__ double trunc(double x) { return ::trunc(x); }
@@ -40,12 +68,12 @@ template <> struct M<double> {
   static __device__ __forceinline__ double pi() { return 3.14159265358979323846; }
 };
 template <> struct M<float> {
-  static __device__ __noinline__ float log(float x) { return ::logf(x); }
-  static __device__ __noinline__ float exp(float x) { return ::expf(x); }
+  static __device__ COFLUX_INL_LOG float log(float x) { return ::logf(x); }
+  static __device__ COFLUX_INL_EXP float exp(float x) { return ::expf(x); }
   static __device__ __forceinline__ float sqrt(float x) { return ::sqrtf(x); }
-  static __device__ __noinline__ float cbrt(float x) { return ::cbrtf(x); }
-  static __device__ __noinline__ float atan(float x) { return ::atanf(x); }
-  static __device__ __noinline__ float pow(float x, float y) { return ::powf(x, y); }
+  static __device__ COFLUX_INL_CBRT float cbrt(float x) { return ::cbrtf(x); }
+  static __device__ COFLUX_INL_ATAN float atan(float x) { return ::atanf(x); }
+  static __device__ COFLUX_INL_POW float pow(float x, float y) { return ::powf(x, y); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float floor(float x) { return ::floorf(x); }
   static __device__ __forceinline__ float trunc(float x) { return ::truncf(x); }

@@ -47,7 +47,7 @@ __device__ __forceinline__ bool is_active(const DArr& m, int i, int j) {
 
 template <typename FT> struct FluxArgs {
   int nxr, nyr, ring, Nx, Ny;
-  long long ncell;
+  long long cell0, ncell;   // linear cell range [cell0, ncell) of the ring-extended surface handled by this launch
   // a3 inputs
   DSeries su, sv, sT, sq, sp, sQs, sQl, srain, ssnow;
   DArr fi, fj, cs, sn;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool ac
 
 template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE>
 __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxArgs<FT> a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long idx = a.cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.ncell) return;
   const int jj = (int)(idx / a.nxr);
   const int ii = (int)(idx - (long long)jj * a.nxr);
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
 // ---------------------------------------------------------------------------------------------
 template <typename FT> struct StressArgs {
   int Nx, Ny, wrap_x;      // wrap_x: i-1 at i == 0 → Nx-1 (single-slab periodic, ring == 0)
+  long long cell0, cell1;  // linear interior cell range [cell0, cell1) handled by this launch
   DArr rtx, rty, conc, tx_io, ty_io, mask;
   DArr taux, tauy;
   const char* seam_west;   // ρτx of the west neighbour's last column (Ny elements), or nullptr
@@ -234,8 +235,8 @@ __device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, 
   if (!act || !is_active(a.mask, i, j - 1)) ty = FT(0);
 }
 template <typename FT> __global__ void __launch_bounds__(256) stress_kernel(const __grid_constant__ StressArgs<FT> a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)a.Nx * a.Ny) return;
+  const long long idx = a.cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.cell1) return;
   const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
   FT tx, ty;
   assemble_stress<FT>(a, i, j, tx, ty);

@@ -27,9 +27,9 @@
 //   * the Edson ψ_u/ψ_θ pair at the same ζ shares √(1−15ζ), ζ²/(1+ζ²), exp(−0.35ζ); x^1.5 = x·√x;
 //   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ (virtually always after the transient) by the Taylor series of the same
 //     function (tools/gen_psi_taylor.py; |error| < 3e-18) instead of 5–7 transcendental calls;
-//   * a period-2 limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the
-//     resolution) is detected and the state the reference reaches at maxiter is returned directly —
-//     bit-identical to iterating on.
+//   * a limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the resolution:
+//     8 % of the cells never "converge") is detected exactly (Brent) and the state the reference
+//     reaches at maxiter is produced after < period extra passes — bit-identical to iterating on.
 #pragma once
 #include "coflux_kernels.cuh"
 
@@ -219,19 +219,28 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
   return !((drift < F.tol) || (it >= F.maxit));
 }
 
+// Occupancy knobs.  COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every cell in shared memory between
+// phase A and phase C (5 CTAs/SM fit); 0 recomputes the atmosphere state in phase C from the exchange
+// state (one extra pow+exp per cell, bit-identical) and frees room for a 6th CTA per SM.
+#ifndef COFLUX_TILE_CARRY
+#define COFLUX_TILE_CARRY 1
+#endif
+#ifndef COFLUX_TILE_MIN_BLOCKS
+#define COFLUX_TILE_MIN_BLOCKS 5
+#endif
+
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
 template <typename FT, int TILE, bool VARNU> struct TileSmem {
   FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
+#if COFLUX_TILE_CARRY
   FT rho[TILE], cp[TILE];                                 // carried to phase C
+#endif
   int it[TILE];
   unsigned short queue[TILE];
   int n_front, n_back, head;
 };
-#ifndef COFLUX_TILE_MIN_BLOCKS
-#define COFLUX_TILE_MIN_BLOCKS 5
-#endif
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
 __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
-  const long long tile0 = (long long)blockIdx.x * TILE;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
   __syncthreads();
   const FastConsts<FT>& K = P.K;
@@ -299,7 +308,9 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
       const FT theta_a = Ta + P.g * P.h / atm.cp_m;
       const SurfaceState<FT> S = surface_state<FT, 0>(P, F, atm, pa, theta_a, x, Ts);
       const FT U2 = du * du + dv * dv, gTv = P.g / S.T_v, a1 = FT(1) + delta * S.q_vap, a2 = delta * S.T_v;
+#if COFLUX_TILE_CARRY
       sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
+#endif
       us = ts = qs = F.init;
       bool go = fixed ? (F.maxit > 0) : true;
       if (go) {
@@ -325,20 +336,23 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
   // ------------------------------------------------------------------ phase B: lane refill
   {
     int slot = -1, it = 0;
-    FT U2 = 0, dth = 0, dq = 0, gTv = 0, a1 = 0, a2 = 0, nu = 0, us = 0, ts = 0, qs = 0, pu = 0, pt = 0, pq = 0;
+    FT U2 = 0, dth = 0, dq = 0, gTv = 0, a1 = 0, a2 = 0, nu = 0, us = 0, ts = 0, qs = 0;
+    // Brent cycle detection: (su, st, sq) is a snapshot of the iterate taken at pass `snap_it`; it is
+    // refreshed after 1, 2, 4, 8 … passes.  When the iterate returns EXACTLY to the snapshot the orbit
+    // is periodic with period λ = it − snap_it; the reference keeps iterating until maxiter, i.e. it
+    // ends (maxiter − it) mod λ passes further along the same orbit — run just those and stop.
+    FT su = 0, st = 0, sq = 0;
+    int snap_it = 0, window = 1, stop_at = 0;
     auto pop = [&]() {
       int pos = atomicAdd(&sm.head, 1);
       slot = -1;
-      while (pos < n_total) {
-        const int sl = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
-        const int it0 = sm.it[sl];
-        slot = sl;
+      if (pos < n_total) {
+        slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
         U2 = sm.U2[slot]; dth = sm.dth[slot]; dq = sm.dq[slot];
         { const FT Tv = sm.Tv[slot], qv = sm.qv[slot]; gTv = P.g / Tv; a1 = FT(1) + delta * qv; a2 = delta * Tv; }
         nu = VARNU ? sm.nu[slot] : F.mr.visc.nu;
-        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = it0;
-        pu = pt = pq = M<FT>::inf();
-        break;
+        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
+        su = us; st = ts; sq = qs; snap_it = it; window = 1; stop_at = -1;
       }
     };
     pop();
@@ -347,14 +361,23 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
         const FT u0 = us, t0 = ts, q0 = qs;
         iterate_fast<FT, SPEC>(P, F, K, U2, dth, dq, gTv, a1, a2, nu, us, ts, qs);
         ++it;
-        bool go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
-        if (go && !fixed && us == pu && ts == pt && qs == pq) {
-          // period-2 limit cycle (…, A, B, A): the reference keeps alternating until maxiter
-          if (((F.maxit - it) & 1) != 0) { us = u0; ts = t0; qs = q0; }
-          it = F.maxit;
-          go = false;
+        bool go;
+        if (stop_at >= 0) {                       // finishing a detected cycle
+          go = it < stop_at;
+          if (!go) it = F.maxit;
+        } else {
+          go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
+          if (go && !fixed) {
+            if (us == su && ts == st && qs == sq) {
+              const int lambda = it - snap_it;
+              stop_at = it + (F.maxit - it) % lambda;
+              go = it < stop_at;
+              if (!go) it = F.maxit;
+            } else if (it - snap_it == window) {
+              su = us; st = ts; sq = qs; snap_it = it; window *= 2;
+            }
+          }
         }
-        pu = u0; pt = t0; pq = q0;
         if (!go) {
           sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
           pop();
@@ -385,7 +408,14 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
         du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
         dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
       } else { du = ua; dv = va; }
+#if COFLUX_TILE_CARRY
       const FT rho = sm.rho[cidx], cp = sm.cp[cidx];
+#else
+      const FT pa = reinterpret_cast<const FT*>(a.xp.p)[(int64_t)i * a.xp.si + (int64_t)j * a.xp.sj];
+      const FT qa = reinterpret_cast<const FT*>(a.xq.p)[(int64_t)i * a.xq.si + (int64_t)j * a.xq.sj];
+      const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
+      const FT rho = atm.rho, cp = atm.cp_m;
+#endif
       const FT dU = M<FT>::sqrt(du * du + dv * dv);
       const FT taux = (dU == FT(0)) ? dU : -us * us * du / dU;
       const FT tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
