@@ -13,6 +13,7 @@
 #include <new>
 #include "coflux_solve_tile.cuh"
 #include <cstdlib>
+#include <unistd.h>
 
 using namespace coflux;
 
@@ -68,15 +69,25 @@ struct HostStage {   // device staging planes + pipeline resources for coflux_up
   cudaStream_t copy_in = nullptr, copy_out = nullptr;    // H2D / D2H
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
 };
+// Multi-GPU seam (mode B): this context's buffer, IPC-mapped by both neighbours.
+//   [0]   uint32 data_flag[2]  — written by the WEST neighbour: step id whose ρτx column (parity) is complete
+//   [8]   uint32 ack           — written by the EAST neighbour: last step whose column it has consumed
+//   [256] data[2][Ny]          — ρτx of the west neighbour's last interior column, double-buffered by step parity
 struct Seam {
   bool attached = false;
   int rank = 0, world = 1;
-  char* local = nullptr;        // this context's seam buffer (cudaMalloc): 2 parities × Ny elements + flags
-  char* east = nullptr;         // peer mapping of the east neighbour's buffer
-  char* west = nullptr;         // peer mapping of the west neighbour's buffer (for acks)
+  char* local = nullptr;        // cudaMalloc'd
+  char* east = nullptr;         // peer mapping of the east neighbour's buffer (we store our column + flag there)
+  char* west = nullptr;         // peer mapping of the west neighbour's buffer (we store our ack there)
+  bool east_is_ipc = false, west_is_ipc = false;
   size_t bytes = 0;
-  unsigned long long step = 0;
+  unsigned int step = 0;
 };
+static const size_t SEAM_DATA_OFFSET = 256;
+// cuStreamWriteValue32 / cuStreamWaitValue32, resolved at run time through cudaGetDriverEntryPoint
+typedef int (*cuStreamMemOp32_t)(void* stream, unsigned long long addr, unsigned int value, unsigned int flags);
+static cuStreamMemOp32_t g_write32 = nullptr, g_wait32 = nullptr;
+static const unsigned int COFLUX_WAIT_GEQ = 0x0;   // CU_STREAM_WAIT_VALUE_GEQ: (int32)(*addr - value) >= 0
 struct Profile {
   bool on = false;
   static const int RING = 64;             // events are read back lazily; a ring bounds their number
@@ -975,12 +986,29 @@ static int do_update(coflux_ctx* c, const coflux_update_inputs* in, coflux_updat
   if (rc) return rc;
   Profile& pf = c->prof;
   if (pf.on && pf.pending == Profile::RING) { rc = profile_drain(c); if (rc) return rc; }
+  Seam& sm = c->seam;
+  unsigned int step = 0, parity = 0;
+  if (sm.attached) {
+    step = ++sm.step; parity = step & 1u;
+    const size_t col = (size_t)s.Ny * sizeof(FT);
+    // the east neighbour must have consumed this parity's previous column (step − 2) before we overwrite it
+    if (step > 2 && g_wait32(st, (unsigned long long)(uintptr_t)(sm.local + 8), step - 2, COFLUX_WAIT_GEQ) != 0)
+      return fail(COFLUX_ERR_SEAM, "cuStreamWaitValue32 (ack) failed");
+    a.seam_east = sm.east + SEAM_DATA_OFFSET + parity * col;
+    s.seam_west = sm.local + SEAM_DATA_OFFSET + parity * col;
+  }
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][0], st));
   rc = launch_flux_rows<FT>(c, a, 0, a.nyr, st);
   if (rc) return rc;
+  if (sm.attached) {
+    // publish: our column for `step` is in the east neighbour's buffer; then wait for the west neighbour's
+    if (g_write32(st, (unsigned long long)(uintptr_t)(sm.east + 4 * parity), step, 0) != 0) return fail(COFLUX_ERR_SEAM, "cuStreamWriteValue32 failed");
+    if (g_wait32(st, (unsigned long long)(uintptr_t)(sm.local + 4 * parity), step, COFLUX_WAIT_GEQ) != 0) return fail(COFLUX_ERR_SEAM, "cuStreamWaitValue32 failed");
+  }
   if (pf.on) CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][1], st));
   rc = launch_stress_rows<FT>(c, s, 0, s.Ny, st);
   if (rc) return rc;
+  if (sm.attached && g_write32(st, (unsigned long long)(uintptr_t)(sm.west + 8), step, 0) != 0) return fail(COFLUX_ERR_SEAM, "cuStreamWriteValue32 (ack) failed");
   if (pf.on) { CUDA_TRY(cudaEventRecord(pf.ev[pf.pending][2], st)); pf.pending += 1; }
   return COFLUX_OK;
 }
@@ -1115,18 +1143,107 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
 }
 
 // ---------------------------------------------------------------------------------------------
-// multi-GPU seam (implemented in a later milestone of this round)
+// multi-GPU seam, mode B: fused compute + exchange over NVLink peer memory.
+// The flux kernel stores the last interior column of ρτx straight into the east neighbour's seam
+// buffer (peer store), a stream write-value publishes it, the neighbour's stream wait-value orders
+// its stress kernel behind it.  No host round trip, no separate message, no NCCL call per step.
 // ---------------------------------------------------------------------------------------------
+static int load_stream_memops() {
+  if (g_write32 && g_wait32) return COFLUX_OK;
+  cudaDriverEntryPointQueryResult qr;
+  void* fw = nullptr; void* fq = nullptr;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWriteValue32", &fw, cudaEnableDefault, &qr));
+  CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fq, cudaEnableDefault, &qr));
+  if (!fw || !fq) return fail(COFLUX_ERR_SEAM, "driver does not export cuStreamWriteValue32 / cuStreamWaitValue32");
+  g_write32 = reinterpret_cast<cuStreamMemOp32_t>(fw);
+  g_wait32 = reinterpret_cast<cuStreamMemOp32_t>(fq);
+  return COFLUX_OK;
+}
+static int ensure_seam_buffer(coflux_ctx* c) {
+  if (c->seam.local) return COFLUX_OK;
+  const size_t es = (c->cfg.dtype == COFLUX_F64) ? 8 : 4;
+  c->seam.bytes = SEAM_DATA_OFFSET + 2 * (size_t)c->cfg.grid.Ny * es;
+  CUDA_TRY(cudaMalloc(&c->seam.local, c->seam.bytes));
+  CUDA_TRY(cudaMemset(c->seam.local, 0, c->seam.bytes));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return COFLUX_OK;
+}
+struct SeamHandleWire {          // what travels between ranks (≤ COFLUX_SEAM_HANDLE_BYTES)
+  cudaIpcMemHandle_t ipc;        // 64 bytes
+  int32_t Ny, dtype, device, pid;
+  uint64_t local_ptr;            // for the same-process case (world == 1 or several contexts per process)
+};
+static_assert(sizeof(SeamHandleWire) <= COFLUX_SEAM_HANDLE_BYTES, "seam handle too large");
+
 extern "C" int coflux_seam_export(coflux_ctx* c, void* handle_out) {
   REQUIRE(c && handle_out, "NULL argument");
-  return fail(COFLUX_ERR_UNSUPPORTED, "seam push mode not built in this revision; use grid.ring = 1 (zero-message mode)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_seam_buffer(c);
+  if (rc) return rc;
+  SeamHandleWire w;
+  memset(&w, 0, sizeof(w));
+  CUDA_TRY(cudaIpcGetMemHandle(&w.ipc, c->seam.local));
+  w.Ny = c->cfg.grid.Ny; w.dtype = c->cfg.dtype; w.device = c->device; w.pid = (int32_t)getpid();
+  w.local_ptr = (uint64_t)(uintptr_t)c->seam.local;
+  memset(handle_out, 0, COFLUX_SEAM_HANDLE_BYTES);
+  memcpy(handle_out, &w, sizeof(w));
+  return COFLUX_OK;
+}
+static int open_peer(coflux_ctx* c, const SeamHandleWire& w, char** out, bool* is_ipc) {
+  if (w.Ny != c->cfg.grid.Ny || w.dtype != c->cfg.dtype)
+    return fail(COFLUX_ERR_SEAM, "neighbour slab has Ny=%d dtype=%d, this slab Ny=%d dtype=%d", w.Ny, w.dtype, c->cfg.grid.Ny, c->cfg.dtype);
+  if (w.pid == (int32_t)getpid()) {            // same process: the pointer is directly usable (peer access enabled below)
+    *out = reinterpret_cast<char*>((uintptr_t)w.local_ptr);
+    *is_ipc = false;
+    if (w.device != c->device) {
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->device, w.device));
+      if (!can) return fail(COFLUX_ERR_SEAM, "device %d cannot access peer device %d", c->device, w.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(COFLUX_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+    return COFLUX_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, w.ipc, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(COFLUX_ERR_SEAM, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+  *out = static_cast<char*>(p);
+  *is_ipc = true;
+  return COFLUX_OK;
 }
 extern "C" int coflux_seam_attach(coflux_ctx* c, const void* west, const void* east, int32_t rank, int32_t world) {
   REQUIRE(c && west && east, "NULL argument");
-  (void)rank; (void)world;
-  return fail(COFLUX_ERR_UNSUPPORTED, "seam push mode not built in this revision; use grid.ring = 1 (zero-message mode)");
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+  REQUIRE(c->cfg.grid.ring == 0, "seam mode needs grid.ring == 0 (ring == 1 is the zero-message mode)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = load_stream_memops();
+  if (rc) return rc;
+  rc = ensure_seam_buffer(c);
+  if (rc) return rc;
+  coflux_seam_detach(c);
+  SeamHandleWire ww, we;
+  memcpy(&ww, west, sizeof(ww));
+  memcpy(&we, east, sizeof(we));
+  Seam& s = c->seam;
+  rc = open_peer(c, we, &s.east, &s.east_is_ipc);
+  if (rc) return rc;
+  if (memcmp(&ww, &we, sizeof(ww)) == 0) { s.west = s.east; s.west_is_ipc = false; }   // two slabs: the same neighbour on both sides
+  else { rc = open_peer(c, ww, &s.west, &s.west_is_ipc); if (rc) return rc; }
+  s.rank = rank; s.world = world; s.step = 0; s.attached = true;
+  CUDA_TRY(cudaMemset(s.local, 0, SEAM_DATA_OFFSET));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return COFLUX_OK;
 }
 extern "C" int coflux_seam_detach(coflux_ctx* c) {
-  if (c) c->seam.attached = false;
+  if (!c) return COFLUX_OK;
+  Seam& s = c->seam;
+  if (s.attached) {
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (s.west_is_ipc && s.west && s.west != s.east) cudaIpcCloseMemHandle(s.west);
+    if (s.east_is_ipc && s.east) cudaIpcCloseMemHandle(s.east);
+  }
+  s.east = s.west = nullptr; s.east_is_ipc = s.west_is_ipc = false; s.attached = false;
   return COFLUX_OK;
 }

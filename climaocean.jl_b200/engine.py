@@ -48,6 +48,20 @@ class Engine:
         _abi.check(self.lib.coflux_profile_read(self._ctx, C.byref(a), C.byref(b), C.byref(n)), self.lib)
         return a.value, b.value, n.value
 
+    # --- multi-GPU seam (mode B) ---
+    def seam_export(self):
+        buf = C.create_string_buffer(_abi.SEAM_HANDLE_BYTES)
+        _abi.check(self.lib.coflux_seam_export(self._ctx, buf), self.lib)
+        return bytes(buf.raw)
+
+    def seam_attach(self, west_handle, east_handle, rank, world):
+        w = C.create_string_buffer(west_handle, _abi.SEAM_HANDLE_BYTES)
+        e = C.create_string_buffer(east_handle, _abi.SEAM_HANDLE_BYTES)
+        _abi.check(self.lib.coflux_seam_attach(self._ctx, w, e, int(rank), int(world)), self.lib)
+
+    def seam_detach(self):
+        _abi.check(self.lib.coflux_seam_detach(self._ctx), self.lib)
+
     # --- entry points (names follow the reference's generic functions) ---
     def interpolate_atmosphere_state(self, series, time, exchange, stream=None):
         _abi.check(self.lib.coflux_interpolate_atmosphere(self._ctx, C.byref(series), float(time), C.byref(exchange),

@@ -47,3 +47,19 @@ def gather_interior(field, dist, world):
     parts = [torch.empty_like(loc) for _ in range(world)]
     dist.all_gather(parts, loc)
     return torch.cat(parts, dim=1).cpu().numpy()
+
+
+def attach_seam(engine, dist, rank, world):
+    """Mode B set-up: all-gather every rank's seam handle and attach the west / east neighbours
+    (periodic ring).  After this, coflux_update_state pushes the seam column over NVLink itself."""
+    import torch
+    h = engine.seam_export()
+    if world == 1:
+        engine.seam_attach(h, h, 0, 1)
+        return
+    mine = torch.tensor(list(h), dtype=torch.uint8, device=f"cuda:{torch.cuda.current_device()}")
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    handles = [bytes(p.cpu().tolist()) for p in parts]
+    engine.seam_attach(handles[(rank - 1) % world], handles[(rank + 1) % world], rank, world)
+    dist.barrier()

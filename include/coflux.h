@@ -403,10 +403,14 @@ int coflux_profile_read(coflux_ctx*, double* flux_kernel_ms, double* stress_kern
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU longitude slabs.  One context per GPU/process.  The only cross-slab
  * datum produced by this path is the last column of ρτx needed by the east neighbour's
- * centre→face stress average.  Mode A (ring=1) needs no exchange at all.  Mode B (ring=0 in x):
- * the flux kernel stores its seam column straight into the east neighbour's context-owned seam
- * buffer over NVLink (peer mapping via CUDA IPC), ordered by stream write/wait-value operations —
- * no host round trip, no separate message.
+ * centre→face stress average.  Mode A (grid.ring = 1) needs no exchange at all.  Mode B
+ * (grid.ring = 0): the flux kernel stores its seam column straight into the east neighbour's
+ * context-owned seam buffer over NVLink (peer mapping via CUDA IPC), published / awaited with
+ * stream write-value / wait-value operations on the caller's stream — no host round trip, no
+ * separate message.  Protocol: every rank calls coflux_seam_export, the handles are exchanged by
+ * the host (torch.distributed / MPI all-gather), every rank calls coflux_seam_attach with its west
+ * and east neighbours' handles (periodic ring); afterwards all ranks must call coflux_update_state
+ * the same number of times.  With world == 1 a context may attach to itself (periodic single slab).
  * ---------------------------------------------------------------------------------------------- */
 #define COFLUX_SEAM_HANDLE_BYTES 128
 int coflux_seam_export(coflux_ctx*, void* handle_out /* COFLUX_SEAM_HANDLE_BYTES */);
