@@ -44,6 +44,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(cells):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the flux kernel from the committed `ncu --set full`
+    capture (profiles/r01_traffic.json, bytes per cell on the same 1/12° grid) scaled to this launch."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return float(json.load(open(p))["flux_tile_kernel_f64_dram_bytes_per_cell"]) * cells
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -304,9 +314,9 @@ def main():
     cells_local = grid.Nx * grid.Ny
     value = cells_global / (ms * 1e-3) / 1e6
     its = dev.iterations.numpy()[0, 7:-7, 7:-7]
-    roof = {"bound": "hbm", "kernel": "flux_kernel<double,0,1,1,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
+    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,512,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
             "achieved": cells_local * WORDS_FLUX_KERNEL * 8 / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": load_traffic(cells_local),
             "algorithmic_bytes_per_cell": WORDS_FLUX_KERNEL * 8, "kernel_ms": flux_ms, "stress_kernel_ms": stress_ms,
             "step_achieved_29_words": cells_local * WORDS_STEP * 8 / (ms * 1e-3) / 1e9,
             "note": "the converged Float64 solve is FP64-pipe bound, not HBM bound (see DESIGN.md §5 and profiles/)",
@@ -372,6 +382,27 @@ def main():
                                               "achieved_GBs": cells_global * words * 8 / (tio * 1e-3) / 1e9,
                                               "roofline_frac": cells_global * words * 8 / (tio * 1e-3) / 1e9 / peak}
         ei.close(); del di, hi, T0
+
+    if world > 1:
+        # mode B: ring = 0, the flux kernel pushes the seam column of ρτx into the east neighbour over NVLink
+        from climaocean.jl_b200 import slabs
+        gs, hs = make_host_case(NX, NY, 64, rank, world)
+        hs0 = cj.SurfaceFluxData.synthetic(gs, ring=0)
+        ds = hs0.to_device_columns(device, NZ)
+        cfg_s = make_cfg(ds.grid, NZ, 64, local)
+        cfg_s.grid.ring = 0
+        cfg_s.grid.periodic_x = 0
+        es_ = cj.Engine(cfg_s)
+        slabs.attach_seam(es_, dist, rank, world)
+        ms_s, _, fs_, ss_, _ = time_device_steps(es_, ds, args.steps, args.warmup, dist, device)
+        extras["seam_push_mode"] = {"value": cells_global / (ms_s * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": ms_s,
+                                    "flux_kernel_ms": fs_, "stress_kernel_ms_incl_seam_wait": ss_,
+                                    "seam_bytes_per_step_per_rank": NY * 8,
+                                    "note": "NVLink peer store from inside the flux kernel + stream write/wait-value; no NCCL call per step"}
+        barrier(dist)
+        es_.seam_detach()
+        es_.close()
+        del ds, hs0
 
     cpu = None
     if rank == 0 and world == 1:

@@ -717,7 +717,10 @@ template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
   const FluxP<FT>& F = dev_params<FT>(c).ao;
   return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc;
 }
-constexpr int COFLUX_TILE = 512;
+#ifndef COFLUX_TILE_CELLS
+#define COFLUX_TILE_CELLS 256
+#endif
+constexpr int COFLUX_TILE = COFLUX_TILE_CELLS;   // cells per CTA of the tile kernel (multiple of 128)
 // compile-time specialisation of the hot loop for the OMIP parameter sets (0 = generic)
 template <typename FT> static int tile_spec(const coflux_ctx* c) {
   const DevParams<FT>& P = dev_params<FT>(c);
@@ -854,7 +857,7 @@ static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* 
   a.tx = view2d(f->x_momentum, 0, es); a.ty = view2d(f->y_momentum, 0, es);
   a.dt = (FT)dt;
   a.P = dev_params<FT>(c);
-  ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 128), 128, 0, st>>>(a);
+  ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, COFLUX_IO_BLOCK), COFLUX_IO_BLOCK, 0, st>>>(a);
   return check_launch(c, 1);
 }
 extern "C" int coflux_sea_ice_ocean_fluxes(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* ice, double dt,

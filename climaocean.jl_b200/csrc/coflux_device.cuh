@@ -168,7 +168,7 @@ template <typename FT> __device__ __forceinline__ FT psi_conv_cbrt(FT y) {  // c
 template <typename FT> __device__ __forceinline__ FT psi_businger_momentum(FT x) {  // Kansas limb, x = (1 − γ ζ)^{1/4}
   return FT(2) * M<FT>::log((FT(1) + x) / FT(2)) + M<FT>::log((FT(1) + x * x) / FT(2)) - FT(2) * M<FT>::atan(x) + M<FT>::pi() / FT(2);
 }
-template <typename FT> __device__ FT psi_momentum(int kind, FT z) {
+template <typename FT> __device__ __noinline__ FT psi_momentum(int kind, FT z) {
   if (kind == COFLUX_STABILITY_EDSON) {
     if (z >= FT(0)) {
       FT dz = M<FT>::min(FT(50), FT(0.35) * z);
@@ -195,7 +195,7 @@ template <typename FT> __device__ FT psi_momentum(int kind, FT z) {
            FT(2) * rt3 * (M<FT>::atan((FT(2) * x - B) / (rt3 * B)) - M<FT>::atan((FT(2) - B) / (rt3 * B))));
   return p1 + p2;
 }
-template <typename FT> __device__ FT psi_scalar(int kind, FT z) {
+template <typename FT> __device__ __noinline__ FT psi_scalar(int kind, FT z) {
   if (kind == COFLUX_STABILITY_EDSON) {
     if (z >= FT(0)) {
       FT dz = M<FT>::min(FT(50), FT(0.35) * z);

@@ -27,11 +27,15 @@
 //   * the Edson ψ_u/ψ_θ pair at the same ζ shares √(1−15ζ), ζ²/(1+ζ²), exp(−0.35ζ); x^1.5 = x·√x;
 //   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ (virtually always after the transient) by the Taylor series of the same
 //     function (tools/gen_psi_taylor.py; |error| < 3e-18) instead of 5–7 transcendental calls;
+//   * the unstable Edson ψ_u, ψ_θ on −ζ ∈ [2⁻⁹, 2⁷) from a 32 KB table of degree-7 piecewise polynomials
+//     (16 per binade, tools/gen_psi_table.py; error ≤ 3e-16·max(1,|ψ|), i.e. rounding level) instead of
+//     4 log + 3 atan + 2 cbrt + 2 sqrt + 5 divisions; outside that range the exact formulas are used;
 //   * a limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the resolution:
 //     8 % of the cells never "converge") is detected exactly (Brent) and the state the reference
 //     reaches at maxiter is produced after < period extra passes — bit-identical to iterating on.
 #pragma once
 #include "coflux_kernels.cuh"
+#include "coflux_psi_table.h"
 
 namespace coflux {
 
@@ -102,7 +106,7 @@ template <typename FT> __device__ __forceinline__ FT psi_series_s_stab(FT x) {
 #define COFLUX_PSI_SMALL 0.001953125 /* 2^-9 */
 
 // Edson ψ_u(z), ψ_θ(z) at the same argument
-template <typename FT> __device__ __forceinline__ void psi_edson_pair(FT z, FT& pm, FT& ps) {
+template <typename FT> __device__ __noinline__ void psi_edson_pair(FT z, FT& pm, FT& ps) {
   if (z >= FT(0)) {
     const FT dz = M<FT>::min(FT(50), FT(0.35) * z);
     const FT e = M<FT>::exp(-dz);
@@ -122,11 +126,74 @@ template <typename FT> __device__ __forceinline__ void psi_edson_pair(FT z, FT& 
     ps = (FT(1) - f) * pks + f * pcs;
   }
 }
+// ---------------------------------------------------------------------------------------------
+// Table evaluation of the unstable Edson functions (coflux_psi_table.h).  z = −ζ ∈ [2^KMIN, 2^KMAX).
+// The interval index comes straight from the floating-point bits (exponent + top 4 mantissa bits),
+// the local coordinate t ∈ [−1,1) from the remaining mantissa bits — all exact operations.
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct PsiTable;
+template <> struct PsiTable<double> {
+  static __device__ __forceinline__ const double* row(double z, double& t) {
+    const long long bits = __double_as_longlong(z);
+    const int k = (int)((bits >> 52) & 0x7ff) - 1023;
+    const int j = (int)((bits >> 48) & 0xf);
+    const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
+    t = 2.0 * one_plus_u - 3.0;
+    return &COFLUX_PSI_TABLE_F64[(k - COFLUX_PSI_KMIN) * COFLUX_PSI_NS + j][0][0];
+  }
+  static __device__ __forceinline__ bool in_range(double z) { return z >= 0.001953125 && z < 128.0; }
+};
+template <> struct PsiTable<float> {
+  static __device__ __forceinline__ const float* row(float z, float& t) {
+    const int bits = __float_as_int(z);
+    const int k = ((bits >> 23) & 0xff) - 127;
+    const int j = (bits >> 19) & 0xf;
+    const float one_plus_u = __int_as_float(((bits & 0x0007ffff) << 4) | 0x3f800000);
+    t = 2.0f * one_plus_u - 3.0f;
+    return &COFLUX_PSI_TABLE_F32[(k - COFLUX_PSI_KMIN) * COFLUX_PSI_NS + j][0][0];
+  }
+  static __device__ __forceinline__ bool in_range(float z) { return z >= 0.001953125f && z < 128.0f; }
+};
+static_assert(COFLUX_PSI_NS == 16 && COFLUX_PSI_DEG == 7 && COFLUX_PSI_KMIN == -9 && COFLUX_PSI_KMAX == 7, "table layout changed");
+template <typename FT> __device__ __forceinline__ FT poly8(const FT* c, FT t) {
+  FT acc = __ldg(c + 7);
+#pragma unroll
+  for (int k = 6; k >= 0; --k) acc = fma_<FT>(acc, t, __ldg(c + k));
+  return acc;
+}
+// ψ_u(ζ) and ψ_θ(ζ), Edson et al. (2013): series near 0, table on the bulk of the unstable range,
+// exact formulas elsewhere (stable side, and −ζ ≥ 128 which only occurs in the start-up transient)
+template <typename FT> __device__ __forceinline__ void psi_edson_pair_fast(FT z, FT& pm, FT& ps) {
+  if (z < FT(0)) {
+    const FT mz = -z;
+    if (__builtin_expect(PsiTable<FT>::in_range(mz), 1)) {
+      FT t;
+      const FT* c = PsiTable<FT>::row(mz, t);
+      pm = poly8<FT>(c, t); ps = poly8<FT>(c + 8, t);
+      return;
+    }
+    if (mz <= FT(COFLUX_PSI_SMALL)) { pm = psi_series_m_unst<FT>(z); ps = psi_series_s_unst<FT>(z); return; }
+  }
+  psi_edson_pair<FT>(z, pm, ps);
+}
+template <typename FT> __device__ __forceinline__ FT psi_edson_u_fast(FT x) {
+  if (M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_m_stab<FT>(x) : psi_series_m_unst<FT>(x);
+  if (x < FT(0) && PsiTable<FT>::in_range(-x)) { FT t; const FT* c = PsiTable<FT>::row(-x, t); return poly8<FT>(c, t); }
+  return psi_momentum((int)COFLUX_STABILITY_EDSON, x);
+}
+template <typename FT> __device__ __forceinline__ FT psi_edson_t_fast(FT x) {
+  if (M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_s_stab<FT>(x) : psi_series_s_unst<FT>(x);
+  if (x < FT(0) && PsiTable<FT>::in_range(-x)) { FT t; const FT* c = PsiTable<FT>::row(-x, t); return poly8<FT>(c + 8, t); }
+  return psi_scalar((int)COFLUX_STABILITY_EDSON, x);
+}
+
 template <typename FT, int SPEC> __device__ __forceinline__ FT psi_small_momentum(bool edson, int stab, FT x) {
+  if (SPEC) return psi_edson_u_fast<FT>(x);
   if (edson && M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_m_stab<FT>(x) : psi_series_m_unst<FT>(x);
   return psi_momentum(SPEC ? (int)COFLUX_STABILITY_EDSON : stab, x);
 }
 template <typename FT, int SPEC> __device__ __forceinline__ FT psi_small_scalar(bool edson, int stab, FT x) {
+  if (SPEC) return psi_edson_t_fast<FT>(x);
   if (edson && M<FT>::abs(x) <= FT(COFLUX_PSI_SMALL)) return (x >= FT(0)) ? psi_series_s_stab<FT>(x) : psi_series_s_unst<FT>(x);
   return psi_scalar(SPEC ? (int)COFLUX_STABILITY_EDSON : stab, x);
 }
@@ -187,7 +254,8 @@ __device__ __forceinline__ void iterate_fast(const DevParams<FT>& P, const FluxP
   const FT invL = (bstar == FT(0)) ? FT(0) : kappa * bstar / (u0 * u0);
   const FT zeta = h * invL;
   FT psi_hm, psi_hs;
-  if (edson) psi_edson_pair<FT>(zeta, psi_hm, psi_hs);
+  if (SPEC) psi_edson_pair_fast<FT>(zeta, psi_hm, psi_hs);
+  else if (edson) psi_edson_pair<FT>(zeta, psi_hm, psi_hs);
   else { psi_hm = psi_momentum(F.stability, zeta); psi_hs = psi_scalar(F.stability, zeta); }
   FT prof_u = (K.lnh - M<FT>::log(lu)) - psi_hm;
   if (logform) prof_u += psi_small_momentum<FT, SPEC>(edson, F.stability, lu * invL);
@@ -219,14 +287,19 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
   return !((drift < F.tol) || (it >= F.maxit));
 }
 
-// Occupancy knobs.  COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every cell in shared memory between
-// phase A and phase C (5 CTAs/SM fit); 0 recomputes the atmosphere state in phase C from the exchange
-// state (one extra pow+exp per cell, bit-identical) and frees room for a 6th CTA per SM.
+// Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`; profiles/README.md):
+//   TILE 512 / 5 CTAs per SM (96 regs) 9.2 ms, TILE 384 / 6 CTAs (80 regs) 9.0 ms, TILE 256 / 8 CTAs
+//   (64 regs, 88 B of spills) 8.7 ms — the loop is latency bound (dependent FP64 chains), so the
+//   extra resident warps win over the spills.  COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every
+//   cell in shared memory between phase A and phase C; 0 recomputes the atmosphere state in phase C.
 #ifndef COFLUX_TILE_CARRY
 #define COFLUX_TILE_CARRY 1
 #endif
 #ifndef COFLUX_TILE_MIN_BLOCKS
-#define COFLUX_TILE_MIN_BLOCKS 5
+#define COFLUX_TILE_MIN_BLOCKS 8
+#endif
+#ifndef COFLUX_TILE_PRE
+#define COFLUX_TILE_PRE 2      /* similarity passes done in phase A before a cell is queued */
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
@@ -313,10 +386,15 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
 #endif
       us = ts = qs = F.init;
       bool go = fixed ? (F.maxit > 0) : true;
-      if (go) {
+      // the first COFLUX_TILE_PRE passes run here, in lock step: they are the start-up transient
+      // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6, |ζ| ≫ 128 and takes the exact ψ formulas),
+      // so that the refill loop of phase B only meets settled iterates on the short code path
+#pragma unroll 1
+      for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
+        const FT u0 = us, t0 = ts, q0 = qs;
         iterate_fast<FT, SPEC>(P, F, K, U2, S.dtheta, S.dq, gTv, a1, a2, S.nu_m, us, ts, qs);
-        it = 1;
-        go = keep_going<FT>(F, it, us, ts, qs, F.init, F.init, F.init);
+        ++it;
+        go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
       }
       if (go) {
         sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.Tv[cidx] = S.T_v; sm.qv[cidx] = S.q_vap;
