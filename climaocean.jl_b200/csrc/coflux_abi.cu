@@ -461,6 +461,9 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
     K.lnhA_t = K.fast_t ? std::log(P.h / F.tr.A) : FT(0);
     K.lnhl_t = std::log(P.h / ((F.tr.kind == COFLUX_ROUGHNESS_FIXED) ? F.tr.fixed : F.tr.lmax));
     K.lrclip_t = K.fast_t ? std::log(F.tr.A / F.tr.lmax) / F.tr.b : FT(0);
+    K.alpha_g = F.mr.alpha / F.mr.g; K.inv_g = FT(1) / F.mr.g;
+    K.inv_Rv = FT(1) / P.th.R_v; K.inv_Rd = FT(1) / P.th.R_d; K.inv_Ttr = FT(1) / P.th.T_tr;
+    K.inv_ramp = FT(1) / (P.th.T_fr - P.th.T_in);
   }
   const coflux_ice_ocean_params& io = c.ice_ocean;
   P.io.heat_flux = io.heat_flux; P.io.friction = io.friction_velocity; P.io.um_star = (FT)io.characteristic_melting_speed;
@@ -733,7 +736,7 @@ template <typename FT> static int tile_spec(const coflux_ctx* c) {
 }
 template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_tile_spec(const FluxArgs<FT>& a, cudaStream_t st) {
   auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, COFLUX_TILE, SPEC>;
-  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, SPEC != 1>);
+  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
   static bool configured = false;     // per instantiation
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -113,6 +113,8 @@ template <typename FT> struct FastConsts {
   FT lnhA_q, lnhl_q, lrclip_q;     // ln(h/A), ln(h/ℓmax or fixed), ln(A/ℓmax)/b  (water vapour)
   FT lnhA_t, lnhl_t, lrclip_t;     // same for temperature
   int edson, gust_skip, fast_q, fast_t;
+  // reciprocals / products hoisted for the lean Float64 pass (coflux_solve_tile.cuh::iterate_lean)
+  FT alpha_g, inv_g, inv_Rv, inv_Rd, inv_Ttr, inv_ramp;
 };
 template <typename FT> struct DevParams {
   ThermoC<FT> th;

@@ -27,7 +27,7 @@
 //   * the Edson ψ_u/ψ_θ pair at the same ζ shares √(1−15ζ), ζ²/(1+ζ²), exp(−0.35ζ); x^1.5 = x·√x;
 //   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ (virtually always after the transient) by the Taylor series of the same
 //     function (tools/gen_psi_taylor.py; |error| < 3e-18) instead of 5–7 transcendental calls;
-//   * the unstable Edson ψ_u, ψ_θ on −ζ ∈ [2⁻⁹, 2⁷) from a 32 KB table of degree-7 piecewise polynomials
+//   * the unstable Edson ψ_u, ψ_θ on −ζ ∈ [2⁻⁹, 2¹³) from a 44 KB table of degree-7 piecewise polynomials
 //     (16 per binade, tools/gen_psi_table.py; error ≤ 3e-16·max(1,|ψ|), i.e. rounding level) instead of
 //     4 log + 3 atan + 2 cbrt + 2 sqrt + 5 divisions; outside that range the exact formulas are used;
 //   * a limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the resolution:
@@ -36,6 +36,8 @@
 #pragma once
 #include "coflux_kernels.cuh"
 #include "coflux_psi_table.h"
+#include "coflux_fastmath.cuh"
+#include <type_traits>
 
 namespace coflux {
 
@@ -141,7 +143,7 @@ template <> struct PsiTable<double> {
     t = 2.0 * one_plus_u - 3.0;
     return &COFLUX_PSI_TABLE_F64[(k - COFLUX_PSI_KMIN) * COFLUX_PSI_NS + j][0][0];
   }
-  static __device__ __forceinline__ bool in_range(double z) { return z >= 0.001953125 && z < 128.0; }
+  static __device__ __forceinline__ bool in_range(double z) { return z >= 0.001953125 && z < (double)(1 << COFLUX_PSI_KMAX); }
 };
 template <> struct PsiTable<float> {
   static __device__ __forceinline__ const float* row(float z, float& t) {
@@ -152,9 +154,9 @@ template <> struct PsiTable<float> {
     t = 2.0f * one_plus_u - 3.0f;
     return &COFLUX_PSI_TABLE_F32[(k - COFLUX_PSI_KMIN) * COFLUX_PSI_NS + j][0][0];
   }
-  static __device__ __forceinline__ bool in_range(float z) { return z >= 0.001953125f && z < 128.0f; }
+  static __device__ __forceinline__ bool in_range(float z) { return z >= 0.001953125f && z < (float)(1 << COFLUX_PSI_KMAX); }
 };
-static_assert(COFLUX_PSI_NS == 16 && COFLUX_PSI_DEG == 7 && COFLUX_PSI_KMIN == -9 && COFLUX_PSI_KMAX == 7, "table layout changed");
+static_assert(COFLUX_PSI_NS == 16 && COFLUX_PSI_DEG == 7 && COFLUX_PSI_KMIN <= -9 && COFLUX_PSI_KMAX >= 7 && COFLUX_PSI_KMAX < 31, "table layout changed");
 template <typename FT> __device__ __forceinline__ FT poly8(const FT* c, FT t) {
   FT acc = __ldg(c + 7);
 #pragma unroll
@@ -162,7 +164,7 @@ template <typename FT> __device__ __forceinline__ FT poly8(const FT* c, FT t) {
   return acc;
 }
 // ψ_u(ζ) and ψ_θ(ζ), Edson et al. (2013): series near 0, table on the bulk of the unstable range,
-// exact formulas elsewhere (stable side, and −ζ ≥ 128 which only occurs in the start-up transient)
+// exact formulas elsewhere (stable side, and −ζ ≥ 2^KMAX which only occurs in the start-up transient of calm cells)
 template <typename FT> __device__ __forceinline__ void psi_edson_pair_fast(FT z, FT& pm, FT& ps) {
   if (z < FT(0)) {
     const FT mz = -z;
@@ -287,6 +289,225 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
   return !((drift < F.tol) || (it >= F.maxit));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lean Float64 pass (SPEC 1 / SPEC 2 only).  Same reference iteration, organised so that the loop is
+// straight-line code on registers:
+//   * every elementary function is the branch-free FMA sequence of coflux_fastmath.cuh (SFU seed + Newton,
+//     table log/exp); the three divisions by u★ share one reciprocal;
+//   * the sign of b★ selects ONE of two blocks (unstable: gustiness cube root, ψ pair from the table, 5-term
+//     series for ψ(ℓ/L); stable: closed forms with the lean exp/√, 3-term series) — the queue is sorted by
+//     that sign, so warps do not diverge;
+//   * anything outside the domain of the short path (u★ ≤ 1e-30, a calm cell, −ζ outside [2⁻²⁰, 2¹³),
+//     an out-of-range buoyancy-flux argument) sets one flag, and the caller redoes the whole pass
+//     with the exact code behind a single by-value call (lean_cold_pass) — rare after the start-up transient;
+//   * all literals come from constant memory (LeanLit), not 64-bit immediates.
+// ≈ 165 FP64 instructions per pass instead of ≈ 540.  Every step differs from iterate_fast by rounding-level
+// amounts only; tests/test_gpu_parity.py holds the kernel to the same 1e-12 bar, and COFLUX_LEAN=0 builds
+// the previous loop for A/B runs.
+// ---------------------------------------------------------------------------------------------
+#ifndef COFLUX_LEAN
+#define COFLUX_LEAN 1
+#endif
+struct LeanTabs { const double* lg; const double* ex; };
+struct LeanCell { double U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
+struct D3 { double u, t, q; };
+
+struct LeanLit {
+  double tiny_u, w_lo, w_hi, z_lo, z_hi, x_tiny;
+  double mu5, mu4, mu3, mu2, mu1;        // ψ_u(x), x → 0⁻
+  double su5, su4, su3, su2, su1;        // ψ_θ(x), x → 0⁻
+  double ms3, ms2, ms1;                  // ψ_u(x), x → 0⁺
+  double ss3, ss2, ss1, ss0;             // ψ_θ(x), x → 0⁺
+  double c035, c50, m075, c5_035, m07, m075c, two3, m23, c1428, m8525;
+};
+__constant__ LeanLit LL = {
+  1e-30, 1e-30, 1e30, 9.5367431640625e-07 /* 2^-20 */, 8192.0, 0.0001220703125 /* 2^-13 */,
+  -12220.416809168435, -1198.931685655382, -131.46927083333333, -17.578125, -3.75,
+  -39314.5732184928, -3548.0861371527776, -355.4458333333333, -42.1875, -7.5,
+  -0.1225, 0.91875, -5.2,
+  -0.09034314814814814, 0.6497666666666667, -4.998666666666667, -0.005,
+  0.35, 50.0, -0.75, 5.0 / 0.35, -0.7, -0.75 * 5.0 / 0.35, 2.0 / 3.0, -(2.0 / 3.0), 14.28, -8.525};
+
+// the unstable ψ pair from the table; z = −ζ ∈ [2⁻²⁰, 2¹³)
+__device__ __forceinline__ void psi_table_pair(double z, double& pm, double& ps) {
+  const long long bits = __double_as_longlong(z);
+  const int hi = (int)(bits >> 32);
+  const int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);        // (exponent − KMIN)·16 + top 4 mantissa bits
+  const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
+  const double t = fm::fma_(2.0, one_plus_u, -3.0);
+  const double2* c = reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][0][0]);
+  const double2 m0 = __ldg(c), m1 = __ldg(c + 1), m2 = __ldg(c + 2), m3 = __ldg(c + 3);
+  const double2 s0 = __ldg(c + 4), s1 = __ldg(c + 5), s2 = __ldg(c + 6), s3 = __ldg(c + 7);
+  double a = fm::fma_(m3.y, t, m3.x), b = fm::fma_(s3.y, t, s3.x);
+  a = fm::fma_(a, t, m2.y); b = fm::fma_(b, t, s2.y);
+  a = fm::fma_(a, t, m2.x); b = fm::fma_(b, t, s2.x);
+  a = fm::fma_(a, t, m1.y); b = fm::fma_(b, t, s1.y);
+  a = fm::fma_(a, t, m1.x); b = fm::fma_(b, t, s1.x);
+  a = fm::fma_(a, t, m0.y); b = fm::fma_(b, t, s0.y);
+  pm = fm::fma_(a, t, m0.x); ps = fm::fma_(b, t, s0.x);
+}
+
+// one function of the pair (which = 0: ψ_u, 1: ψ_θ); z = −x ∈ [2⁻²⁰, 2¹³)
+__device__ __forceinline__ double psi_table_one(double z, int which) {
+  const long long bits = __double_as_longlong(z);
+  const int hi = (int)(bits >> 32);
+  const int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
+  const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
+  const double t = fm::fma_(2.0, one_plus_u, -3.0);
+  const double2* c = reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][which][0]);
+  const double2 m0 = __ldg(c), m1 = __ldg(c + 1), m2 = __ldg(c + 2), m3 = __ldg(c + 3);
+  double a = fm::fma_(m3.y, t, m3.x);
+  a = fm::fma_(a, t, m2.y); a = fm::fma_(a, t, m2.x);
+  a = fm::fma_(a, t, m1.y); a = fm::fma_(a, t, m1.x);
+  a = fm::fma_(a, t, m0.y);
+  return fm::fma_(a, t, m0.x);
+}
+// stable closed forms (Edson et al. 2013), any z ≥ 0
+__device__ __forceinline__ double psi_stable_m(double z, double e /* exp(−min(50, 0.35 z)) */) {
+  return fm::fma_(LL.m075 * (z - LL.c5_035), e, fm::fma_(LL.m07, z, LL.m075c));
+}
+__device__ __forceinline__ double psi_stable_s(double z, double e) {
+  const double w = fm::fma_(LL.two3, z, 1.0);
+  return fm::fma_(LL.m23 * (z - LL.c1428), e, fm::fma_(-w, fm::sqrt(w), LL.m8525));
+}
+
+// One pass.  Returns false when the pass left the short path (the scales are then unchanged and the
+// caller must run lean_cold_pass).
+template <int SPEC>
+__device__ __forceinline__ bool iterate_lean(const DevParams<double>& P, const FluxP<double>& F, const FastConsts<double>& K,
+                                             const LeanTabs& tb, const LeanCell& c, double& us, double& ts, double& qs) {
+  const double u0 = us, t0 = ts, q0 = qs;
+  const double bstar = fm::fma_(c.cb1, t0, c.cb2 * q0);
+  const bool unstable = bstar < 0.0;
+  bool ok = (u0 > LL.tiny_u) && (c.Ustab > 0.0);
+  const double r = fm::rcp(u0);
+  const double invL = (F.kappa * bstar) * (r * r);
+  const double zeta = P.h * invL;
+  double U = c.Ustab;                                        // √(Δu² + U_G,min²): no gustiness when Jᵇ ≤ 0
+  if (unstable) {
+    const double w = (-u0 * bstar) * P.hbl;                  // Jᵇ·h_bl > 0
+    ok = ok && (w > LL.w_lo) && (w < LL.w_hi) && (-zeta >= LL.z_lo) && (-zeta < LL.z_hi);
+    const double UG = fmax(F.beta * fm::cbrt(w), F.ugmin);
+    U = fm::sqrt(fm::fma_(UG, UG, c.U2));
+  }
+  double alpha_g = K.alpha_g;
+  if (SPEC == 2) alpha_g = fmax(fm::fma_(F.mr.a1, fmin(U, F.mr.umax), F.mr.a2), F.mr.amin) * K.inv_g;
+  const double lu = fmin(fm::fma_(alpha_g * u0, u0, c.bnu * r), F.mr.lmax);
+  const double ll = fm::log(lu, tb.lg);
+  const double lr = fm::log((lu * u0) * c.inv_nu, tb.lg);    // ln R★
+  double lnq = K.lnhl_q, lq = F.qr.lmax;
+  if (lr > K.lrclip_q) {                                     // A·R★^(−b) < ℓ_max
+    lnq = fm::fma_(F.qr.b, lr, K.lnhA_q);
+    if (SPEC == 1) lq = F.qr.A * fm::exp(-F.qr.b * lr, tb.ex);
+  }
+  const double xm = lu * invL, xs = lq * invL;               // ℓ/L★ (same sign as ζ)
+  if (SPEC == 1 && unstable) ok = ok && (-xm < LL.z_hi) && (-xs < LL.z_hi);
+  if (!__builtin_expect(ok, 1)) return false;
+  double psi_hm, psi_hs, sm_ = 0.0, ss_ = 0.0;
+  if (unstable) {
+    psi_table_pair(-zeta, psi_hm, psi_hs);
+    if (SPEC == 1) {                                         // ψ(ℓ/L★): short series near 0, the same table beyond
+      if (-xm <= LL.x_tiny) {
+        double a = fm::fma_(LL.mu5, xm, LL.mu4);
+        a = fm::fma_(a, xm, LL.mu3); a = fm::fma_(a, xm, LL.mu2); a = fm::fma_(a, xm, LL.mu1);
+        sm_ = a * xm;
+      } else {
+        sm_ = psi_table_one(-xm, 0);
+      }
+      if (-xs <= LL.x_tiny) {
+        double b = fm::fma_(LL.su5, xs, LL.su4);
+        b = fm::fma_(b, xs, LL.su3); b = fm::fma_(b, xs, LL.su2); b = fm::fma_(b, xs, LL.su1);
+        ss_ = b * xs;
+      } else {
+        ss_ = psi_table_one(-xs, 1);
+      }
+    }
+  } else {
+    const double e = fm::exp(-fmin(LL.c50, LL.c035 * zeta), tb.ex);
+    psi_hm = psi_stable_m(zeta, e);
+    psi_hs = psi_stable_s(zeta, e);
+    if (SPEC == 1) {
+      if (xm <= LL.x_tiny) sm_ = xm * fm::fma_(fm::fma_(LL.ms3, xm, LL.ms2), xm, LL.ms1);
+      else sm_ = psi_stable_m(xm, fm::exp(-fmin(LL.c50, LL.c035 * xm), tb.ex));
+      if (xs <= LL.x_tiny) ss_ = fm::fma_(fm::fma_(fm::fma_(LL.ss3, xs, LL.ss2), xs, LL.ss1), xs, LL.ss0);
+      else ss_ = psi_stable_s(xs, fm::exp(-fmin(LL.c50, LL.c035 * xs), tb.ex));
+    }
+  }
+  const double prof_u = ((K.lnh - ll) - psi_hm) + sm_;
+  const double prof_q = (lnq - psi_hs) + ss_;
+  if (!(prof_u > 0.0)) { us = ts = qs = 0.0; return true; }
+  const double chi_u = F.kappa * fm::rcp(prof_u);
+  const double chi_q = (prof_q > 0.0) ? F.kappa * fm::rcp(prof_q) : 0.0;
+  us = chi_u * U; ts = chi_q * c.dth; qs = chi_q * c.dq;
+  return true;
+}
+// the exact pass behind one by-value call, so that the lean loop stays small and its state stays in registers
+template <int SPEC>
+__device__ __noinline__ D3 lean_cold_pass(const DevParams<double>* P, double U2, double dth, double dq, double cb1, double cb2, double nu,
+                                          double us, double ts, double qs) {
+  iterate_fast<double, SPEC>(*P, P->ao, P->K, U2, dth, dq, 1.0, cb1, cb2, nu, us, ts, qs);
+  return D3{us, ts, qs};
+}
+
+// Lean thermodynamics (A1, A2) for phase A: the saturation pressure p_tr·(T/T_tr)^(Δcp/R_v)·exp(…) becomes ONE
+// exponential of (Δcp/R_v)·ln(T/T_tr) + (ℒ₀ − Δcp·T₀)/R_v·(1/T_tr − 1/T); ln(T/T_tr) and 1/T are shared by the
+// liquid and the mixed-phase evaluation at the same temperature.
+struct LeanT { double rT, L, D; };     // 1/T, ln(T/T_tr), 1/T_tr − 1/T
+__device__ __forceinline__ LeanT lean_T(const FastConsts<double>& K, const LeanTabs& tb, double T) {
+  LeanT t;
+  t.rT = fm::rcp(T);
+  t.L = fm::log(T * K.inv_Ttr, tb.lg);
+  t.D = K.inv_Ttr - t.rT;
+  return t;
+}
+__device__ __forceinline__ double psat_lean(const ThermoC<double>& c, const FastConsts<double>& K, const LeanTabs& tb, const LeanT& t,
+                                            double LH_0, double dcp) {
+  return c.p_tr * fm::exp(fm::fma_(dcp * K.inv_Rv, t.L, ((LH_0 - dcp * c.T_0) * K.inv_Rv) * t.D), tb.ex);
+}
+// ps_liquid: the liquid-phase saturation pressure at T if the caller already has it (reused when λ = 1), else < 0
+__device__ __forceinline__ Thermo<double> phase_equil_lean(const ThermoC<double>& c, const FastConsts<double>& K, const LeanTabs& tb,
+                                                           const LeanT& t, double p, double T, double q, double ps_liquid) {
+  double lam = 1.0;
+  if (!(T > c.T_fr)) lam = (T <= c.T_in) ? 0.0 : (T - c.T_in) * K.inv_ramp;
+  double ps;
+  if (lam == 1.0 && ps_liquid >= 0.0) {
+    ps = ps_liquid;
+  } else {
+    const double LH_0 = lam * c.LH_v0 + (1.0 - lam) * c.LH_s0;
+    const double dcp = lam * (c.cp_v - c.cp_l) + (1.0 - lam) * (c.cp_v - c.cp_i);
+    ps = psat_lean(c, K, tb, t, LH_0, dcp);
+  }
+  const double denom = p - ps;
+  const double q_vs = (denom > 0.0) ? c.Rd_over_Rv * (1.0 - q) * ps * fm::rcp(denom) : CUDART_INF;
+  const double q_c = fmax(q - q_vs, 0.0);
+  const double q_liq = lam * q_c, q_ice = (1.0 - lam) * q_c;
+  const double R_m = c.R_d * (1.0 + (c.eps - 1.0) * q - c.eps * q_c);
+  Thermo<double> s;
+  s.rho = p * fm::rcp(R_m * T);
+  s.cp_m = c.cp_d + (c.cp_v - c.cp_d) * q + (c.cp_l - c.cp_v) * q_liq + (c.cp_i - c.cp_v) * q_ice;
+  s.q_vap = q - q_liq - q_ice;
+  s.T_v = T * R_m * K.inv_Rd;
+  return s;
+}
+// ocean surface state (bulk interface temperature): q_s, Δq, Δθ, T_v and q_v of the saturated surface air
+__device__ __forceinline__ SurfaceState<double> surface_state_lean(const DevParams<double>& P, const FluxP<double>& F, const LeanTabs& tb,
+                                                                   const Thermo<double>& atm, double pa, double theta_a, double x, double Ts) {
+  const ThermoC<double>& c = P.th;
+  const FastConsts<double>& K = P.K;
+  SurfaceState<double> s;
+  const LeanT t = lean_T(K, tb, Ts);
+  const double ps = psat_lean(c, K, tb, t, c.LH_v0, c.cp_v - c.cp_l);
+  const double qstar = ps * fm::rcp(atm.rho * c.R_v * Ts);
+  s.qs = qstar * x;
+  s.dq = atm.q_vap - s.qs;
+  s.dtheta = theta_a - Ts;
+  const Thermo<double> surf = phase_equil_lean(c, K, tb, t, pa, Ts, s.qs, ps);
+  s.T_v = surf.T_v;
+  s.q_vap = surf.q_vap;
+  s.nu_m = air_viscosity(F.mr.visc, Ts);
+  s.nu_t = s.nu_m; s.nu_q = s.nu_m;
+  return s;
+}
 // Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`; profiles/README.md):
 //   TILE 512 / 5 CTAs per SM (96 regs) 9.2 ms, TILE 384 / 6 CTAs (80 regs) 9.0 ms, TILE 256 / 8 CTAs
 //   (64 regs, 88 B of spills) 8.7 ms — the loop is latency bound (dependent FP64 chains), so the
@@ -296,37 +517,55 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 #define COFLUX_TILE_CARRY 1
 #endif
 #ifndef COFLUX_TILE_MIN_BLOCKS
-#define COFLUX_TILE_MIN_BLOCKS 8
+#define COFLUX_TILE_MIN_BLOCKS 6
 #endif
 #ifndef COFLUX_TILE_PRE
 #define COFLUX_TILE_PRE 2      /* similarity passes done in phase A before a cell is queued */
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
-template <typename FT, int TILE, bool VARNU> struct TileSmem {
+template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
   FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
 #if COFLUX_TILE_CARRY
   FT rho[TILE], cp[TILE];                                 // carried to phase C
 #endif
+  // lean Float64 loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus √(Δu²+U_G,min²), 1/ν, the
+  // COFLUX_LOG_TABLE / COFLUX_EXP_TABLE copies and the per-thread Brent snapshot
+  FT Us[LEAN ? TILE : 1];
+  FT inu[(LEAN && VARNU) ? TILE : 1];
+  alignas(16) double lgt[LEAN ? 256 : 2];
+  double ext[LEAN ? 64 : 2];
+  long long snap[LEAN ? 3 : 1][LEAN ? 128 : 1];
+  int snap_it[LEAN ? 128 : 1], window[LEAN ? 128 : 1], stop_at[LEAN ? 128 : 1];
   int it[TILE];
   unsigned short queue[TILE];
   int n_front, n_back, head;
+};
+template <typename FT, int SPEC> struct TileTraits {
+  static constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
+  static constexpr bool LEAN = (COFLUX_LEAN != 0) && std::is_same<FT, double>::value && (SPEC != 0);
 };
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
 __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
-  TileSmem<FT, TILE, VARNU>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU>*>(smem_raw);
+  constexpr bool VARNU = TileTraits<FT, SPEC>::VARNU;
+  constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;
+  TileSmem<FT, TILE, VARNU, LEAN>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN>*>(smem_raw);
   const DevParams<FT>& P = a.P;
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
   const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
+  if (LEAN) {
+    for (int k = tid; k < 256; k += 128) sm.lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
+    if (tid < 64) sm.ext[tid] = COFLUX_EXP_TABLE[tid];
+  }
   __syncthreads();
+  const LeanTabs tb{sm.lgt, sm.ext};
   const FastConsts<FT>& K = P.K;
   const FT delta = c.eps - FT(1);
   const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
@@ -373,34 +612,67 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
       const FT vo = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
       const FT Ts = ldg<FT>(a.oT, i, j) + P.T_offset;
       const FT So = ldg<FT>(a.oS, i, j);
-      const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = ua - uo; dv = va - vo; } else { du = ua; dv = va; }
-      const FT s = So / FT(1000);
-      const FT x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s);
-      const FT theta_a = Ta + P.g * P.h / atm.cp_m;
-      const SurfaceState<FT> S = surface_state<FT, 0>(P, F, atm, pa, theta_a, x, Ts);
-      const FT U2 = du * du + dv * dv, gTv = P.g / S.T_v, a1 = FT(1) + delta * S.q_vap, a2 = delta * S.T_v;
-#if COFLUX_TILE_CARRY
-      sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
-#endif
+      const FT U2 = du * du + dv * dv;
       us = ts = qs = F.init;
       bool go = fixed ? (F.maxit > 0) : true;
+      FT dtheta, dq, Tv, qv, nu_m;
       // the first COFLUX_TILE_PRE passes run here, in lock step: they are the start-up transient
-      // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6, |ζ| ≫ 128 and takes the exact ψ formulas),
-      // so that the refill loop of phase B only meets settled iterates on the short code path
+      // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6 and |ζ| up to thousands), so that the refill
+      // loop of phase B only meets settled iterates on the short code path
+      if constexpr (LEAN) {
+        const LeanT tA = lean_T(K, tb, Ta);
+        const Thermo<double> atm = phase_equil_lean(c, K, tb, tA, pa, Ta, qa, -1.0);
+        const double s = So * 1e-3;
+        const double x = (1.0 - s) * fm::rcp(1.0 - s + P.wmf_alpha * s);
+        const double theta_a = Ta + (P.g * P.h) * fm::rcp(atm.cp_m);
+        const SurfaceState<double> S = surface_state_lean(P, F, tb, atm, pa, theta_a, x, Ts);
+        dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
+#if COFLUX_TILE_CARRY
+        sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
+#endif
+        LeanCell lc;
+        lc.U2 = U2; lc.dth = dtheta; lc.dq = dq;
+        { const double v = fm::fma_(F.ugmin, F.ugmin, U2); lc.Ustab = (v > 0.0) ? fm::sqrt(v) : 0.0; }
+        { const double gTv = P.g * fm::rcp(Tv); lc.cb1 = gTv * (1.0 + delta * qv); lc.cb2 = gTv * (delta * Tv); }
+        lc.bnu = F.mr.beta_s * nu_m; lc.inv_nu = fm::rcp(nu_m);
 #pragma unroll 1
-      for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
-        const FT u0 = us, t0 = ts, q0 = qs;
-        iterate_fast<FT, SPEC>(P, F, K, U2, S.dtheta, S.dq, gTv, a1, a2, S.nu_m, us, ts, qs);
-        ++it;
-        go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
+        for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
+          const double u0 = us, t0 = ts, q0 = qs;
+          if (!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs)) {
+            const D3 r = lean_cold_pass<SPEC>(&P, U2, dtheta, dq, lc.cb1, lc.cb2, nu_m, u0, t0, q0);
+            us = r.u; ts = r.t; qs = r.q;
+          }
+          ++it;
+          go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
+        }
+        if (go) { sm.Us[cidx] = lc.Ustab; if (VARNU) sm.inu[cidx] = lc.inv_nu; }
+        Tv = lc.cb1; qv = lc.cb2;      // what the lean loop of phase B wants in sm.Tv / sm.qv
+      } else {
+        const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
+        const FT s = So / FT(1000);
+        const FT x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s);
+        const FT theta_a = Ta + P.g * P.h / atm.cp_m;
+        const SurfaceState<FT> S = surface_state<FT, 0>(P, F, atm, pa, theta_a, x, Ts);
+        dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
+#if COFLUX_TILE_CARRY
+        sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
+#endif
+        const FT gTv = P.g / Tv, a1 = FT(1) + delta * qv, a2 = delta * Tv;
+#pragma unroll 1
+        for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
+          const FT u0 = us, t0 = ts, q0 = qs;
+          iterate_fast<FT, SPEC>(P, F, K, U2, dtheta, dq, gTv, a1, a2, nu_m, us, ts, qs);
+          ++it;
+          go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
+        }
       }
       if (go) {
-        sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.Tv[cidx] = S.T_v; sm.qv[cidx] = S.q_vap;
-        if (VARNU) sm.nu[cidx] = S.nu_m;
+        sm.U2[cidx] = U2; sm.dth[cidx] = dtheta; sm.dq[cidx] = dq; sm.Tv[cidx] = Tv; sm.qv[cidx] = qv;
+        if (VARNU) sm.nu[cidx] = nu_m;
         // stability class of every later pass: sign of the buoyancy scale ∝ Δθ·a1 + a2·Δq (χ_θ = χ_q > 0)
-        const bool unstable = (S.dtheta * a1 + a2 * S.dq) < FT(0);
+        const bool unstable = LEAN ? ((dtheta * Tv + qv * dq) < FT(0)) : ((dtheta * (FT(1) + delta * qv) + (delta * Tv) * dq) < FT(0));
         if (unstable) sm.queue[atomicAdd(&sm.n_front, 1)] = (unsigned short)cidx;
         else sm.queue[TILE - 1 - atomicAdd(&sm.n_back, 1)] = (unsigned short)cidx;
       }
@@ -412,13 +684,77 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
   const int n_front = sm.n_front, n_total = sm.n_front + sm.n_back;
 
   // ------------------------------------------------------------------ phase B: lane refill
-  {
+  // Brent cycle detection: (su, st, sq) is a snapshot of the iterate taken at pass `snap_it`; it is
+  // refreshed after 1, 2, 4, 8 … passes.  When the iterate returns EXACTLY to the snapshot the orbit
+  // is periodic with period λ = it − snap_it; the reference keeps iterating until maxiter, i.e. it
+  // ends (maxiter − it) mod λ passes further along the same orbit — run just those and stop.
+  if constexpr (LEAN) {
+    constexpr int BRENT_FROM = 24;               // cycle detection starts here (Float64 converges in < 30 passes)
+    int slot = -1, it = 0;
+    LeanCell lc{};
+    double nu = F.mr.visc.nu, us = 0, ts = 0, qs = 0;
+    if (!VARNU) { lc.bnu = F.mr.beta_s * nu; lc.inv_nu = fm::rcp(nu); }
+    auto pop = [&]() {
+      const int pos = atomicAdd(&sm.head, 1);
+      slot = -1;
+      if (pos < n_total) {
+        slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
+        lc.U2 = sm.U2[slot]; lc.Ustab = sm.Us[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot];
+        lc.cb1 = sm.Tv[slot]; lc.cb2 = sm.qv[slot];
+        if (VARNU) { nu = sm.nu[slot]; lc.inv_nu = sm.inu[slot]; lc.bnu = F.mr.beta_s * nu; }
+        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
+      }
+    };
+    // rare tail of a cell's iteration: Brent bookkeeping lives in shared memory, not in registers
+    auto brent = [&](bool go) -> bool {
+      const long long bu = __double_as_longlong(us), bt = __double_as_longlong(ts), bq = __double_as_longlong(qs);
+      if (it == BRENT_FROM) {
+        sm.snap[0][tid] = bu; sm.snap[1][tid] = bt; sm.snap[2][tid] = bq;
+        sm.snap_it[tid] = it; sm.window[tid] = 1; sm.stop_at[tid] = -1;
+        return go;
+      }
+      const int stop_at = sm.stop_at[tid];
+      if (stop_at >= 0) {                         // finishing a detected cycle
+        if (it < stop_at) return true;
+        it = F.maxit;
+        return false;
+      }
+      if (!go) return false;
+      const int snap_it = sm.snap_it[tid];
+      if (bu == sm.snap[0][tid] && bt == sm.snap[1][tid] && bq == sm.snap[2][tid]) {
+        const int lambda = it - snap_it;
+        const int stop = it + (F.maxit - it) % lambda;
+        sm.stop_at[tid] = stop;
+        if (it < stop) return true;
+        it = F.maxit;
+        return false;
+      }
+      if (it - snap_it == sm.window[tid]) {
+        sm.snap[0][tid] = bu; sm.snap[1][tid] = bt; sm.snap[2][tid] = bq;
+        sm.snap_it[tid] = it; sm.window[tid] *= 2;
+      }
+      return true;
+    };
+    pop();
+    while (__any_sync(0xffffffffu, slot >= 0)) {
+      if (slot >= 0) {
+        const double u0 = us, t0 = ts, q0 = qs;
+        if (!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs)) {
+          const D3 r = lean_cold_pass<SPEC>(&P, lc.U2, lc.dth, lc.dq, lc.cb1, lc.cb2, nu, u0, t0, q0);
+          us = r.u; ts = r.t; qs = r.q;
+        }
+        ++it;
+        bool go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
+        if (__builtin_expect(it >= BRENT_FROM && !fixed, 0)) go = brent(go);
+        if (!go) {
+          sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
+          pop();
+        }
+      }
+    }
+  } else {
     int slot = -1, it = 0;
     FT U2 = 0, dth = 0, dq = 0, gTv = 0, a1 = 0, a2 = 0, nu = 0, us = 0, ts = 0, qs = 0;
-    // Brent cycle detection: (su, st, sq) is a snapshot of the iterate taken at pass `snap_it`; it is
-    // refreshed after 1, 2, 4, 8 … passes.  When the iterate returns EXACTLY to the snapshot the orbit
-    // is periodic with period λ = it − snap_it; the reference keeps iterating until maxiter, i.e. it
-    // ends (maxiter − it) mod λ passes further along the same orbit — run just those and stop.
     FT su = 0, st = 0, sq = 0;
     int snap_it = 0, window = 1, stop_at = 0;
     auto pop = [&]() {
@@ -494,9 +830,17 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
       const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
       const FT rho = atm.rho, cp = atm.cp_m;
 #endif
-      const FT dU = M<FT>::sqrt(du * du + dv * dv);
-      const FT taux = (dU == FT(0)) ? dU : -us * us * du / dU;
-      const FT tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
+      FT taux, tauy;
+      if constexpr (LEAN) {
+        const double d2 = du * du + dv * dv;
+        const double k = (d2 > 1e-280) ? (-us * us) * fm::rcp(fm::sqrt(d2)) : 0.0;   // −u★²/‖Δu‖ (0 when calm)
+        taux = (d2 > 1e-280) ? k * du : ((d2 == 0.0) ? 0.0 : -us * us * du / ::sqrt(d2));
+        tauy = (d2 > 1e-280) ? k * dv : ((d2 == 0.0) ? 0.0 : -us * us * dv / ::sqrt(d2));
+      } else {
+        const FT dU = M<FT>::sqrt(du * du + dv * dv);
+        taux = (dU == FT(0)) ? dU : -us * us * du / dU;
+        tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
+      }
       const FT LH = c.LH_v0 + (c.cp_v - c.cp_l) * (Ta - c.T_0);
       Qv = -rho * us * qs * LH;
       Qc = -rho * cp * us * ts;
