@@ -464,6 +464,7 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
     K.alpha_g = F.mr.alpha / F.mr.g; K.inv_g = FT(1) / F.mr.g;
     K.inv_Rv = FT(1) / P.th.R_v; K.inv_Rd = FT(1) / P.th.R_d; K.inv_Ttr = FT(1) / P.th.T_tr;
     K.inv_ramp = FT(1) / (P.th.T_fr - P.th.T_in);
+    K.bnu = F.mr.beta_s * F.mr.visc.nu; K.inv_nu = FT(1) / F.mr.visc.nu;
   }
   const coflux_ice_ocean_params& io = c.ice_ocean;
   P.io.heat_flux = io.heat_flux; P.io.friction = io.friction_velocity; P.io.um_star = (FT)io.characteristic_melting_speed;
@@ -718,10 +719,10 @@ static bool force_v1() {
 }
 template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
   const FluxP<FT>& F = dev_params<FT>(c).ao;
-  return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc;
+  return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1;
 }
 #ifndef COFLUX_TILE_CELLS
-#define COFLUX_TILE_CELLS 256
+#define COFLUX_TILE_CELLS 384
 #endif
 constexpr int COFLUX_TILE = COFLUX_TILE_CELLS;   // cells per CTA of the tile kernel (multiple of 128)
 // compile-time specialisation of the hot loop for the OMIP parameter sets (0 = generic)
@@ -740,6 +741,10 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   static bool configured = false;     // per instantiation
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // shared-memory carve-out: exactly what COFLUX_TILE_MIN_BLOCKS resident CTAs need (+1 KB each of system use); the rest
+    // of the 256 KB stays L1, which holds the psi table rows and the gathered atmosphere tiles
+    const int carve = (int)((COFLUX_TILE_MIN_BLOCKS * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
     configured = true;
   }
   kern<<<grid_for(a.ncell - a.cell0, COFLUX_TILE), 128, smem, st>>>(a);

@@ -114,7 +114,7 @@ template <typename FT> struct FastConsts {
   FT lnhA_t, lnhl_t, lrclip_t;     // same for temperature
   int edson, gust_skip, fast_q, fast_t;
   // reciprocals / products hoisted for the lean Float64 pass (coflux_solve_tile.cuh::iterate_lean)
-  FT alpha_g, inv_g, inv_Rv, inv_Rd, inv_Ttr, inv_ramp;
+  FT alpha_g, inv_g, inv_Rv, inv_Rd, inv_Ttr, inv_ramp, bnu, inv_nu;   // bnu, inv_nu: constant-viscosity case
 };
 template <typename FT> struct DevParams {
   ThermoC<FT> th;

@@ -143,10 +143,11 @@ COFLUX_FM double log(double x, const double* tab) {
   const double rj = tab[2 * j], lj = tab[2 * j + 1];
 #endif
   const double r = fma_(m, rj, -1.0);                 // |r| ≤ 2⁻⁸
-  double q = fma_(r, KC.l6, KC.l5);
-  q = fma_(q, r, KC.l4);
+  // −1/6 and 1/5 rounded to 21 bits (32-bit immediates; they multiply r⁶, r⁵ ≤ 2⁻⁴⁰, so 2⁻²² relative is plenty)
+  double q = fma_(r, -0.16666662693023682, 0.20000004768371582);
+  q = fma_(q, r, -0.25);
   q = fma_(q, r, KC.l3);
-  q = fma_(q, r, KC.l2);
+  q = fma_(q, r, -0.5);
   const double p = fma_(q, r * r, r);                 // log1p(r), truncation r⁷/7 < 2e-18
   return fma_((double)e, KC.ln2, lj) + p;
 }
@@ -159,9 +160,9 @@ COFLUX_FM double exp(double x, const double* tab) {
   const double nf = t - KC.magic;
   double r = fma_(nf, KC.ln2_64_hi, x);               // −double(ln2/64): the fma rounds the exact x − n·hi once
   r = fma_(nf, KC.ln2_64_lo, r);                      // −(ln2/64 − double(ln2/64))
-  double q = fma_(r, KC.e5, KC.e4);
+  double q = fma_(r, 0.00833333283662796, KC.e4);     // 1/120 rounded to 21 bits (multiplies r⁵ < 2⁻³⁷)
   q = fma_(q, r, KC.e3);
-  q = fma_(q, r, KC.e2);
+  q = fma_(q, r, 0.5);
   q = fma_(q, r, 1.0);
   const double p = q * r;                             // e^r − 1, truncation r⁶/720 < 4e-17
   const double T = from_bits(bits_of(tab[n & 63]) + ((int64_t)(n >> 6) << 52));

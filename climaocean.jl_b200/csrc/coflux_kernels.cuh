@@ -37,6 +37,27 @@ struct DCol {      // 3-D view for column sweeps
 template <typename FT> __device__ __forceinline__ FT ldg(const DArr& a, int i, int j) {
   return __ldg(reinterpret_cast<const FT*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj));
 }
+// streaming load: read-only, not allocated in L1 (keeps L1 for the ψ table and the gathered atmosphere tiles)
+#ifndef COFLUX_STREAM_LOADS
+#define COFLUX_STREAM_LOADS 0
+#endif
+template <typename FT> __device__ __forceinline__ FT ldgs(const DArr& a, int i, int j);
+template <> __device__ __forceinline__ double ldgs<double>(const DArr& a, int i, int j) {
+  const double* p = reinterpret_cast<const double*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj);
+#if COFLUX_STREAM_LOADS
+  double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+#else
+  return __ldg(p);
+#endif
+}
+template <> __device__ __forceinline__ float ldgs<float>(const DArr& a, int i, int j) {
+  const float* p = reinterpret_cast<const float*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj);
+#if COFLUX_STREAM_LOADS
+  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#else
+  return __ldg(p);
+#endif
+}
 template <typename FT> __device__ __forceinline__ void stg(const DArr& a, int i, int j, FT v) {
   if (a.p) reinterpret_cast<FT*>(a.p)[(int64_t)i * a.si + (int64_t)j * a.sj] = v;
 }

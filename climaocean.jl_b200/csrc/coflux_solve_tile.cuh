@@ -308,131 +308,134 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 #ifndef COFLUX_LEAN
 #define COFLUX_LEAN 1
 #endif
+#ifndef COFLUX_PSI_PREFETCH
+#define COFLUX_PSI_PREFETCH 0
+#endif
 struct LeanTabs { const double* lg; const double* ex; };
 struct LeanCell { double U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
 struct D3 { double u, t, q; };
 
+// Literals of the hot loop.  Those with ≤ 21 significant bits are written in place: an FP64 instruction takes
+// them as a 32-bit immediate (the high word).  High-order series coefficients only need a few correct bits
+// (they multiply |x|^k ≤ 2^(−13k)), so they are rounded to that form; the rest sit in constant memory.
 struct LeanLit {
-  double tiny_u, w_lo, w_hi, z_lo, z_hi, x_tiny;
-  double mu5, mu4, mu3, mu2, mu1;        // ψ_u(x), x → 0⁻
-  double su5, su4, su3, su2, su1;        // ψ_θ(x), x → 0⁻
-  double ms3, ms2, ms1;                  // ψ_u(x), x → 0⁺
-  double ss3, ss2, ss1, ss0;             // ψ_θ(x), x → 0⁺
-  double c035, c50, m075, c5_035, m07, m075c, two3, m23, c1428, m8525;
+  double su3, ms2, ms1, ss2, ss1, ss0;
+  double c035, c5_035, m07, m075c, two3, m23, c1428, m8525;
 };
 __constant__ LeanLit LL = {
-  1e-30, 1e-30, 1e30, 9.5367431640625e-07 /* 2^-20 */, 8192.0, 0.0001220703125 /* 2^-13 */,
-  -12220.416809168435, -1198.931685655382, -131.46927083333333, -17.578125, -3.75,
-  -39314.5732184928, -3548.0861371527776, -355.4458333333333, -42.1875, -7.5,
-  -0.1225, 0.91875, -5.2,
-  -0.09034314814814814, 0.6497666666666667, -4.998666666666667, -0.005,
-  0.35, 50.0, -0.75, 5.0 / 0.35, -0.7, -0.75 * 5.0 / 0.35, 2.0 / 3.0, -(2.0 / 3.0), 14.28, -8.525};
+  -355.4458333333333, 0.91875, -5.2, 0.6497666666666667, -4.998666666666667, -0.005,
+  0.35, 5.0 / 0.35, -0.7, -0.75 * 5.0 / 0.35, 2.0 / 3.0, -(2.0 / 3.0), 14.28, -8.525};
+#define COFLUX_NROWS ((COFLUX_PSI_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
 
-// the unstable ψ pair from the table; z = −ζ ∈ [2⁻²⁰, 2¹³)
-__device__ __forceinline__ void psi_table_pair(double z, double& pm, double& ps) {
+// Row of the ψ table for z (clamped into the table, so that the loads are safe for ANY z: the caller may then
+// issue them before it knows whether z is in range, and the scheduler can hoist them above the cube root) and
+// the local coordinate t ∈ [−1, 1).
+__device__ __forceinline__ const double2* psi_table_row(double z, double& t) {
   const long long bits = __double_as_longlong(z);
   const int hi = (int)(bits >> 32);
-  const int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);        // (exponent − KMIN)·16 + top 4 mantissa bits
+  int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);              // (exponent − KMIN)·16 + top 4 mantissa bits
+  row = max(0, min(row, COFLUX_NROWS - 1));
   const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
-  const double t = fm::fma_(2.0, one_plus_u, -3.0);
-  const double2* c = reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][0][0]);
-  const double2 m0 = __ldg(c), m1 = __ldg(c + 1), m2 = __ldg(c + 2), m3 = __ldg(c + 3);
-  const double2 s0 = __ldg(c + 4), s1 = __ldg(c + 5), s2 = __ldg(c + 6), s3 = __ldg(c + 7);
-  double a = fm::fma_(m3.y, t, m3.x), b = fm::fma_(s3.y, t, s3.x);
-  a = fm::fma_(a, t, m2.y); b = fm::fma_(b, t, s2.y);
-  a = fm::fma_(a, t, m2.x); b = fm::fma_(b, t, s2.x);
-  a = fm::fma_(a, t, m1.y); b = fm::fma_(b, t, s1.y);
-  a = fm::fma_(a, t, m1.x); b = fm::fma_(b, t, s1.x);
-  a = fm::fma_(a, t, m0.y); b = fm::fma_(b, t, s0.y);
-  pm = fm::fma_(a, t, m0.x); ps = fm::fma_(b, t, s0.x);
+  t = fm::fma_(2.0, one_plus_u, -3.0);
+  return reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][0][0]);
 }
-
-// one function of the pair (which = 0: ψ_u, 1: ψ_θ); z = −x ∈ [2⁻²⁰, 2¹³)
-__device__ __forceinline__ double psi_table_one(double z, int which) {
-  const long long bits = __double_as_longlong(z);
-  const int hi = (int)(bits >> 32);
-  const int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
-  const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
-  const double t = fm::fma_(2.0, one_plus_u, -3.0);
-  const double2* c = reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][which][0]);
-  const double2 m0 = __ldg(c), m1 = __ldg(c + 1), m2 = __ldg(c + 2), m3 = __ldg(c + 3);
-  double a = fm::fma_(m3.y, t, m3.x);
-  a = fm::fma_(a, t, m2.y); a = fm::fma_(a, t, m2.x);
-  a = fm::fma_(a, t, m1.y); a = fm::fma_(a, t, m1.x);
-  a = fm::fma_(a, t, m0.y);
-  return fm::fma_(a, t, m0.x);
+__device__ __forceinline__ double poly8v(double2 c0, double2 c1, double2 c2, double2 c3, double t) {
+  double a = fm::fma_(c3.y, t, c3.x);
+  a = fm::fma_(a, t, c2.y); a = fm::fma_(a, t, c2.x);
+  a = fm::fma_(a, t, c1.y); a = fm::fma_(a, t, c1.x);
+  a = fm::fma_(a, t, c0.y);
+  return fm::fma_(a, t, c0.x);
 }
-// stable closed forms (Edson et al. 2013), any z ≥ 0
-__device__ __forceinline__ double psi_stable_m(double z, double e /* exp(−min(50, 0.35 z)) */) {
-  return fm::fma_(LL.m075 * (z - LL.c5_035), e, fm::fma_(LL.m07, z, LL.m075c));
+// stable closed forms (Edson et al. 2013), any z ≥ 0;  e = exp(−min(50, 0.35 z))
+__device__ __forceinline__ double psi_stable_m(double z, double e) {
+  return fm::fma_(-0.75 * (z - LL.c5_035), e, fm::fma_(LL.m07, z, LL.m075c));
 }
 __device__ __forceinline__ double psi_stable_s(double z, double e) {
   const double w = fm::fma_(LL.two3, z, 1.0);
   return fm::fma_(LL.m23 * (z - LL.c1428), e, fm::fma_(-w, fm::sqrt(w), LL.m8525));
 }
 
+// min / max by compare-select (3 instructions; fmin/fmax cost 5 with their NaN handling — the second operand
+// is a finite parameter everywhere below, so a NaN first operand still yields the parameter)
+__device__ __forceinline__ double dmin_(double a, double b) { return (a < b) ? a : b; }
+__device__ __forceinline__ double dmax_(double a, double b) { return (a > b) ? a : b; }
+
 // One pass.  Returns false when the pass left the short path (the scales are then unchanged and the
 // caller must run lean_cold_pass).
 template <int SPEC>
 __device__ __forceinline__ bool iterate_lean(const DevParams<double>& P, const FluxP<double>& F, const FastConsts<double>& K,
                                              const LeanTabs& tb, const LeanCell& c, double& us, double& ts, double& qs) {
+  constexpr double TINY = 0.0001220703125;                   // 2⁻¹³: |ℓ/L★| below which the short series are exact to rounding
+  constexpr double Z_LO = 9.5367431640625e-07, Z_HI = 8192.0;   // table domain of −ζ: [2⁻²⁰, 2¹³)
+  constexpr double SMALL = 7.888609052210118e-31, BIG = 1.2676506002282294e30;   // 2⁻¹⁰⁰, 2¹⁰⁰
   const double u0 = us, t0 = ts, q0 = qs;
   const double bstar = fm::fma_(c.cb1, t0, c.cb2 * q0);
   const bool unstable = bstar < 0.0;
-  bool ok = (u0 > LL.tiny_u) && (c.Ustab > 0.0);
+  bool ok = (u0 > SMALL) && (c.Ustab > 0.0);
   const double r = fm::rcp(u0);
   const double invL = (F.kappa * bstar) * (r * r);
   const double zeta = P.h * invL;
+  // SPEC 1 (constant Charnock): the roughness lengths do not depend on this pass's wind speed — evaluate them
+  // first, so that ONE block per stability class holds everything that depends on the sign of ζ
+  double lu = 0, ll = 0, lnq = K.lnhl_q, lq = F.qr.lmax, xm = 0, xs = 0;
+  auto roughness = [&](double alpha_g) {
+    lu = dmin_(fm::fma_(alpha_g * u0, u0, c.bnu * r), F.mr.lmax);
+    ll = fm::log(lu, tb.lg);
+    const double lr = fm::log((lu * u0) * c.inv_nu, tb.lg);  // ln R★
+    if (lr > K.lrclip_q) {                                   // A·R★^(−b) < ℓ_max
+      lnq = fm::fma_(F.qr.b, lr, K.lnhA_q);
+      if (SPEC == 1) lq = F.qr.A * fm::exp(-F.qr.b * lr, tb.ex);
+    }
+    xm = lu * invL; xs = lq * invL;                          // ℓ/L★ (same sign as ζ)
+  };
+  if (SPEC == 1) roughness(K.alpha_g);
   double U = c.Ustab;                                        // √(Δu² + U_G,min²): no gustiness when Jᵇ ≤ 0
-  if (unstable) {
-    const double w = (-u0 * bstar) * P.hbl;                  // Jᵇ·h_bl > 0
-    ok = ok && (w > LL.w_lo) && (w < LL.w_hi) && (-zeta >= LL.z_lo) && (-zeta < LL.z_hi);
-    const double UG = fmax(F.beta * fm::cbrt(w), F.ugmin);
-    U = fm::sqrt(fm::fma_(UG, UG, c.U2));
-  }
-  double alpha_g = K.alpha_g;
-  if (SPEC == 2) alpha_g = fmax(fm::fma_(F.mr.a1, fmin(U, F.mr.umax), F.mr.a2), F.mr.amin) * K.inv_g;
-  const double lu = fmin(fm::fma_(alpha_g * u0, u0, c.bnu * r), F.mr.lmax);
-  const double ll = fm::log(lu, tb.lg);
-  const double lr = fm::log((lu * u0) * c.inv_nu, tb.lg);    // ln R★
-  double lnq = K.lnhl_q, lq = F.qr.lmax;
-  if (lr > K.lrclip_q) {                                     // A·R★^(−b) < ℓ_max
-    lnq = fm::fma_(F.qr.b, lr, K.lnhA_q);
-    if (SPEC == 1) lq = F.qr.A * fm::exp(-F.qr.b * lr, tb.ex);
-  }
-  const double xm = lu * invL, xs = lq * invL;               // ℓ/L★ (same sign as ζ)
-  if (SPEC == 1 && unstable) ok = ok && (-xm < LL.z_hi) && (-xs < LL.z_hi);
-  if (!__builtin_expect(ok, 1)) return false;
   double psi_hm, psi_hs, sm_ = 0.0, ss_ = 0.0;
   if (unstable) {
-    psi_table_pair(-zeta, psi_hm, psi_hs);
+    double t;
+    const double2* row = psi_table_row(-zeta, t);            // loads first: the cube root below hides their latency
+    const double2 m0 = __ldg(row), m1 = __ldg(row + 1), m2 = __ldg(row + 2), m3 = __ldg(row + 3);
+    const double2 s0 = __ldg(row + 4), s1 = __ldg(row + 5), s2 = __ldg(row + 6), s3 = __ldg(row + 7);
+    const double w = (-u0 * bstar) * P.hbl;                  // Jᵇ·h_bl > 0
+    ok = ok && (w > SMALL) && (w < BIG) && (-zeta >= Z_LO) && (-zeta < Z_HI);
+    const double UG = dmax_(F.beta * fm::cbrt(w), F.ugmin);
+    U = fm::sqrt(fm::fma_(UG, UG, c.U2));
     if (SPEC == 1) {                                         // ψ(ℓ/L★): short series near 0, the same table beyond
-      if (-xm <= LL.x_tiny) {
-        double a = fm::fma_(LL.mu5, xm, LL.mu4);
-        a = fm::fma_(a, xm, LL.mu3); a = fm::fma_(a, xm, LL.mu2); a = fm::fma_(a, xm, LL.mu1);
+      ok = ok && (-xm < Z_HI) && (-xs < Z_HI);
+      if (-xm <= TINY) {
+        double a = fm::fma_(-12220.4140625, xm, -1198.931640625);
+        a = fm::fma_(a, xm, -131.46923828125); a = fm::fma_(a, xm, -17.578125); a = fm::fma_(a, xm, -3.75);
         sm_ = a * xm;
       } else {
-        sm_ = psi_table_one(-xm, 0);
+        double tt;
+        const double2* rr = psi_table_row(-xm, tt);
+        sm_ = poly8v(__ldg(rr), __ldg(rr + 1), __ldg(rr + 2), __ldg(rr + 3), tt);
       }
-      if (-xs <= LL.x_tiny) {
-        double b = fm::fma_(LL.su5, xs, LL.su4);
-        b = fm::fma_(b, xs, LL.su3); b = fm::fma_(b, xs, LL.su2); b = fm::fma_(b, xs, LL.su1);
+      if (-xs <= TINY) {
+        double b = fm::fma_(-39314.5625, xs, -3548.0859375);
+        b = fm::fma_(b, xs, LL.su3); b = fm::fma_(b, xs, -42.1875); b = fm::fma_(b, xs, -7.5);
         ss_ = b * xs;
       } else {
-        ss_ = psi_table_one(-xs, 1);
+        double tt;
+        const double2* rr = psi_table_row(-xs, tt);
+        ss_ = poly8v(__ldg(rr + 4), __ldg(rr + 5), __ldg(rr + 6), __ldg(rr + 7), tt);
       }
     }
+    psi_hm = poly8v(m0, m1, m2, m3, t);
+    psi_hs = poly8v(s0, s1, s2, s3, t);
   } else {
-    const double e = fm::exp(-fmin(LL.c50, LL.c035 * zeta), tb.ex);
+    const double e = fm::exp(-dmin_(LL.c035 * zeta, 50.0), tb.ex);
     psi_hm = psi_stable_m(zeta, e);
     psi_hs = psi_stable_s(zeta, e);
     if (SPEC == 1) {
-      if (xm <= LL.x_tiny) sm_ = xm * fm::fma_(fm::fma_(LL.ms3, xm, LL.ms2), xm, LL.ms1);
-      else sm_ = psi_stable_m(xm, fm::exp(-fmin(LL.c50, LL.c035 * xm), tb.ex));
-      if (xs <= LL.x_tiny) ss_ = fm::fma_(fm::fma_(fm::fma_(LL.ss3, xs, LL.ss2), xs, LL.ss1), xs, LL.ss0);
-      else ss_ = psi_stable_s(xs, fm::exp(-fmin(LL.c50, LL.c035 * xs), tb.ex));
+      if (xm <= TINY) sm_ = xm * fm::fma_(fm::fma_(-0.12249755859375, xm, LL.ms2), xm, LL.ms1);
+      else sm_ = psi_stable_m(xm, fm::exp(-dmin_(LL.c035 * xm, 50.0), tb.ex));
+      if (xs <= TINY) ss_ = fm::fma_(fm::fma_(fm::fma_(-0.09034299850463867, xs, LL.ss2), xs, LL.ss1), xs, LL.ss0);
+      else ss_ = psi_stable_s(xs, fm::exp(-dmin_(LL.c035 * xs, 50.0), tb.ex));
     }
   }
+  if (SPEC == 2) roughness(dmax_(fm::fma_(F.mr.a1, dmin_(U, F.mr.umax), F.mr.a2), F.mr.amin) * K.inv_g);
+  if (!__builtin_expect(ok, 1)) return false;
   const double prof_u = ((K.lnh - ll) - psi_hm) + sm_;
   const double prof_q = (lnq - psi_hs) + ss_;
   if (!(prof_u > 0.0)) { us = ts = qs = 0.0; return true; }
@@ -531,14 +534,12 @@ template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
 #if COFLUX_TILE_CARRY
   FT rho[TILE], cp[TILE];                                 // carried to phase C
 #endif
-  // lean Float64 loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus √(Δu²+U_G,min²), 1/ν, the
-  // COFLUX_LOG_TABLE / COFLUX_EXP_TABLE copies and the per-thread Brent snapshot
-  FT Us[LEAN ? TILE : 1];
+  // lean Float64 loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus 1/ν and the COFLUX_LOG_TABLE /
+  // COFLUX_EXP_TABLE copies.  (The Brent snapshot of a cell in flight lives in that cell's own us/ts/qs/it
+  // slots, which nobody reads until the cell is written back.)
   FT inu[(LEAN && VARNU) ? TILE : 1];
   alignas(16) double lgt[LEAN ? 256 : 2];
   double ext[LEAN ? 64 : 2];
-  long long snap[LEAN ? 3 : 1][LEAN ? 128 : 1];
-  int snap_it[LEAN ? 128 : 1], window[LEAN ? 128 : 1], stop_at[LEAN ? 128 : 1];
   int it[TILE];
   unsigned short queue[TILE];
   int n_front, n_back, head;
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
     const int i = ii - a.ring, j = jj - a.ring;
     FT ua, va, Ta, pa, qa;
     if (INTERP) {
-      const FT fi = ldg<FT>(a.fi, i, j), fj = ldg<FT>(a.fj, i, j);
+      const FT fi = ldgs<FT>(a.fi, i, j), fj = ldgs<FT>(a.fj, i, j);
       const int i0 = (int)M<FT>::trunc(fi), j0 = (int)M<FT>::trunc(fj);
       const int i1 = i0 + ((fi > FT(0)) - (fi < FT(0))), j1 = j0 + ((fj > FT(0)) - (fj < FT(0)));
       const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
@@ -595,23 +596,23 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
       if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
       if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
       if (a.cs.p && a.sn.p) {
-        const FT cs = ldg<FT>(a.cs, i, j), sn = ldg<FT>(a.sn, i, j);
+        const FT cs = ldgs<FT>(a.cs, i, j), sn = ldgs<FT>(a.sn, i, j);
         const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
         ua = ur; va = vr;
       }
       stg<FT>(a.xu, i, j, ua); stg<FT>(a.xv, i, j, va); stg<FT>(a.xT, i, j, Ta); stg<FT>(a.xp, i, j, pa);
       stg<FT>(a.xq, i, j, qa); stg<FT>(a.xQs, i, j, Qs); stg<FT>(a.xQl, i, j, Ql); stg<FT>(a.xMp, i, j, Mp);
     } else {
-      ua = ldg<FT>(a.xu, i, j); va = ldg<FT>(a.xv, i, j); Ta = ldg<FT>(a.xT, i, j); pa = ldg<FT>(a.xp, i, j);
-      qa = ldg<FT>(a.xq, i, j);
+      ua = ldgs<FT>(a.xu, i, j); va = ldgs<FT>(a.xv, i, j); Ta = ldgs<FT>(a.xT, i, j); pa = ldgs<FT>(a.xp, i, j);
+      qa = ldgs<FT>(a.xq, i, j);
     }
     FT us = FT(0), ts = FT(0), qs = FT(0);
     int it = 0;
     if (is_active(a.mask, i, j)) {
-      const FT uo = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
-      const FT vo = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
-      const FT Ts = ldg<FT>(a.oT, i, j) + P.T_offset;
-      const FT So = ldg<FT>(a.oS, i, j);
+      const FT uo = (ldgs<FT>(a.ou, i, j) + ldgs<FT>(a.ou, i + 1, j)) * FT(0.5);
+      const FT vo = (ldgs<FT>(a.ov, i, j) + ldgs<FT>(a.ov, i, j + 1)) * FT(0.5);
+      const FT Ts = ldgs<FT>(a.oT, i, j) + P.T_offset;
+      const FT So = ldgs<FT>(a.oS, i, j);
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = ua - uo; dv = va - vo; } else { du = ua; dv = va; }
       const FT U2 = du * du + dv * dv;
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
           ++it;
           go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
         }
-        if (go) { sm.Us[cidx] = lc.Ustab; if (VARNU) sm.inu[cidx] = lc.inv_nu; }
+        if (VARNU && go) sm.inu[cidx] = lc.inv_nu;
         Tv = lc.cb1; qv = lc.cb2;      // what the lean loop of phase B wants in sm.Tv / sm.qv
       } else {
         const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
@@ -693,45 +694,46 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
     int slot = -1, it = 0;
     LeanCell lc{};
     double nu = F.mr.visc.nu, us = 0, ts = 0, qs = 0;
-    if (!VARNU) { lc.bnu = F.mr.beta_s * nu; lc.inv_nu = fm::rcp(nu); }
+    if (!VARNU) { lc.bnu = K.bnu; lc.inv_nu = K.inv_nu; }
     auto pop = [&]() {
       const int pos = atomicAdd(&sm.head, 1);
       slot = -1;
       if (pos < n_total) {
         slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
-        lc.U2 = sm.U2[slot]; lc.Ustab = sm.Us[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot];
-        lc.cb1 = sm.Tv[slot]; lc.cb2 = sm.qv[slot];
+        lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.Tv[slot]; lc.cb2 = sm.qv[slot];
+        { const double v = fm::fma_(F.ugmin, F.ugmin, lc.U2); lc.Ustab = (v > 0.0) ? fm::sqrt(v) : 0.0; }
         if (VARNU) { nu = sm.nu[slot]; lc.inv_nu = sm.inu[slot]; lc.bnu = F.mr.beta_s * nu; }
         us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
       }
     };
-    // rare tail of a cell's iteration: Brent bookkeeping lives in shared memory, not in registers
+    // rare tail of a cell's iteration: the Brent bookkeeping lives in the cell's own shared-memory slots
+    // (us/ts/qs: snapshot; it: snap_it | window << 8 | (stop_at + 1) << 16), not in registers
     auto brent = [&](bool go) -> bool {
-      const long long bu = __double_as_longlong(us), bt = __double_as_longlong(ts), bq = __double_as_longlong(qs);
       if (it == BRENT_FROM) {
-        sm.snap[0][tid] = bu; sm.snap[1][tid] = bt; sm.snap[2][tid] = bq;
-        sm.snap_it[tid] = it; sm.window[tid] = 1; sm.stop_at[tid] = -1;
+        sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs;
+        sm.it[slot] = it | (1 << 8);
         return go;
       }
-      const int stop_at = sm.stop_at[tid];
+      const int packed = sm.it[slot];
+      const int snap_it = packed & 0xff, window = (packed >> 8) & 0xff, stop_at = (packed >> 16) - 1;
       if (stop_at >= 0) {                         // finishing a detected cycle
         if (it < stop_at) return true;
         it = F.maxit;
         return false;
       }
       if (!go) return false;
-      const int snap_it = sm.snap_it[tid];
-      if (bu == sm.snap[0][tid] && bt == sm.snap[1][tid] && bq == sm.snap[2][tid]) {
+      if (__double_as_longlong(us) == __double_as_longlong(sm.us[slot]) && __double_as_longlong(ts) == __double_as_longlong(sm.ts[slot]) &&
+          __double_as_longlong(qs) == __double_as_longlong(sm.qs[slot])) {
         const int lambda = it - snap_it;
         const int stop = it + (F.maxit - it) % lambda;
-        sm.stop_at[tid] = stop;
+        sm.it[slot] = packed | ((stop + 1) << 16);
         if (it < stop) return true;
         it = F.maxit;
         return false;
       }
-      if (it - snap_it == sm.window[tid]) {
-        sm.snap[0][tid] = bu; sm.snap[1][tid] = bt; sm.snap[2][tid] = bq;
-        sm.snap_it[tid] = it; sm.window[tid] *= 2;
+      if (it - snap_it == window) {
+        sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs;
+        sm.it[slot] = it | ((window * 2) << 8);
       }
       return true;
     };
@@ -739,13 +741,13 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
     while (__any_sync(0xffffffffu, slot >= 0)) {
       if (slot >= 0) {
         const double u0 = us, t0 = ts, q0 = qs;
-        if (!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs)) {
+        if (__builtin_expect(!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs), 0)) {
           const D3 r = lean_cold_pass<SPEC>(&P, lc.U2, lc.dth, lc.dq, lc.cb1, lc.cb2, nu, u0, t0, q0);
           us = r.u; ts = r.t; qs = r.q;
         }
         ++it;
         bool go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
-        if (__builtin_expect(it >= BRENT_FROM && !fixed, 0)) go = brent(go);
+        if (__builtin_expect(it >= BRENT_FROM && !fixed && F.maxit < 250, 0)) go = brent(go);   // (8-bit fields)
         if (!go) {
           sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
           pop();

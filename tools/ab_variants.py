@@ -11,12 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "lean0_t256_b8": ["COFLUX_LEAN=0", "COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=8"],
-    "lean1_t256_b8": ["COFLUX_LEAN=1", "COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=8"],
-    "lean1_t256_b6": ["COFLUX_LEAN=1", "COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=6"],
-    "lean1_t384_b5": ["COFLUX_LEAN=1", "COFLUX_TILE_CELLS=384", "COFLUX_TILE_MIN_BLOCKS=5"],
-    "lean1_t512_b4": ["COFLUX_LEAN=1", "COFLUX_TILE_CELLS=512", "COFLUX_TILE_MIN_BLOCKS=4"],
-    "lean1_t256_b4": ["COFLUX_LEAN=1", "COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=4"],
+    "b8_t256": ["COFLUX_TILE_MIN_BLOCKS=8"],
+    "b7_t256": ["COFLUX_TILE_MIN_BLOCKS=7"],
+    "b6_t256": ["COFLUX_TILE_MIN_BLOCKS=6"],
+    "b6_t384": ["COFLUX_TILE_MIN_BLOCKS=6", "COFLUX_TILE_CELLS=384"],
+    "b5_t384": ["COFLUX_TILE_MIN_BLOCKS=5", "COFLUX_TILE_CELLS=384"],
+    "b5_t512": ["COFLUX_TILE_MIN_BLOCKS=5", "COFLUX_TILE_CELLS=512"],
 }
 
 
@@ -26,11 +26,13 @@ def build():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     os.makedirs(VDIR, exist_ok=True)
+    for f in os.listdir(VDIR):
+        os.remove(os.path.join(VDIR, f))
     procs = []
     for name, defs in VARIANTS.items():
         out = os.path.join(VDIR, name + ".so")
-        cmd = [b.NVCC] + b.NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-o", out, b.SRC]
-        procs.append((name, subprocess.Popen(cmd)))
+        cmd = [b.NVCC] + b.NVCC_FLAGS + [f"-D{d}" for d in defs] + ["-Xptxas", "-v", "-o", out, b.SRC]
+        procs.append((name, subprocess.Popen(cmd, stderr=open(os.path.join(VDIR, name + '.log'), 'w'))))
     for name, p in procs:
         print(name, "rc", p.wait())
 
