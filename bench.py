@@ -314,12 +314,12 @@ def main():
     cells_local = grid.Nx * grid.Ny
     value = cells_global / (ms * 1e-3) / 1e6
     its = dev.iterations.numpy()[0, 7:-7, 7:-7]
-    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,512,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
+    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,384,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
             "achieved": cells_local * WORDS_FLUX_KERNEL * 8 / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "peak_source": peak_src, "traffic": load_traffic(cells_local),
             "algorithmic_bytes_per_cell": WORDS_FLUX_KERNEL * 8, "kernel_ms": flux_ms, "stress_kernel_ms": stress_ms,
             "step_achieved_29_words": cells_local * WORDS_STEP * 8 / (ms * 1e-3) / 1e9,
-            "note": "the converged Float64 solve is FP64-pipe bound, not HBM bound (see DESIGN.md §5 and profiles/)",
+            "note": "the converged Float64 solve is bound by dependent FP64 latency / issue, not by HBM (DESIGN.md §4, profiles/README.md)",
             "iterations_mean": float(its.mean()), "iterations_max": int(its.max())}
     roof["frac"] = roof["achieved"] / peak
     roof["step_frac_29_words"] = roof["step_achieved_29_words"] / peak

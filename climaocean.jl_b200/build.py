@@ -30,6 +30,16 @@ def build_cuda(force=False, verbose=False, out=OUT, defines=()):
     return out
 
 
+def build_tools(force=False):
+    """lib/fm_check: device-side accuracy check of csrc/coflux_fastmath.cuh (run by tests/test_fastmath.py on the GPU box)."""
+    src = os.path.join(ROOT, "tools", "fm_check.cu")
+    out = os.path.join(HERE, "lib", "fm_check")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _stale(out, [src, os.path.join(HERE, "csrc", "coflux_fastmath.cuh"), os.path.join(HERE, "csrc", "coflux_math_tables.h")]):
+        subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-o", out, src], check=True)
+    return out
+
+
 def build_oracle(force=False):
     odir = os.path.join(ROOT, "oracle")
     out = os.path.join(odir, "libcoflux_oracle.so")
@@ -41,4 +51,5 @@ def build_oracle(force=False):
 
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_tools(force="--force" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))

@@ -462,8 +462,6 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
     K.lnhl_t = std::log(P.h / ((F.tr.kind == COFLUX_ROUGHNESS_FIXED) ? F.tr.fixed : F.tr.lmax));
     K.lrclip_t = K.fast_t ? std::log(F.tr.A / F.tr.lmax) / F.tr.b : FT(0);
     K.alpha_g = F.mr.alpha / F.mr.g; K.inv_g = FT(1) / F.mr.g;
-    K.inv_Rv = FT(1) / P.th.R_v; K.inv_Rd = FT(1) / P.th.R_d; K.inv_Ttr = FT(1) / P.th.T_tr;
-    K.inv_ramp = FT(1) / (P.th.T_fr - P.th.T_in);
     K.bnu = F.mr.beta_s * F.mr.visc.nu; K.inv_nu = FT(1) / F.mr.visc.nu;
   }
   const coflux_ice_ocean_params& io = c.ice_ocean;
@@ -743,7 +741,8 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // shared-memory carve-out: exactly what COFLUX_TILE_MIN_BLOCKS resident CTAs need (+1 KB each of system use); the rest
     // of the 256 KB stays L1, which holds the psi table rows and the gathered atmosphere tiles
-    const int carve = (int)((COFLUX_TILE_MIN_BLOCKS * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    const int min_blocks = (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCKS : COFLUX_TILE_MIN_BLOCKS_F32;
+    const int carve = (int)((min_blocks * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
     configured = true;
   }

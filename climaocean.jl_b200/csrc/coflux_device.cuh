@@ -59,6 +59,7 @@ template <> struct M<double> {
   static __device__ COFLUX_INL_CBRT double cbrt(double x) { return ::cbrt(x); }
   static __device__ COFLUX_INL_ATAN double atan(double x) { return ::atan(x); }
   static __device__ COFLUX_INL_POW double pow(double x, double y) { return ::pow(x, y); }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
   static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
   static __device__ __forceinline__ double trunc(double x) { return ::trunc(x); }
@@ -74,6 +75,7 @@ template <> struct M<float> {
   static __device__ COFLUX_INL_CBRT float cbrt(float x) { return ::cbrtf(x); }
   static __device__ COFLUX_INL_ATAN float atan(float x) { return ::atanf(x); }
   static __device__ COFLUX_INL_POW float pow(float x, float y) { return ::powf(x, y); }
+  static __device__ __forceinline__ float div(float a, float b) { return a / b; }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float floor(float x) { return ::floorf(x); }
   static __device__ __forceinline__ float trunc(float x) { return ::truncf(x); }
@@ -114,7 +116,7 @@ template <typename FT> struct FastConsts {
   FT lnhA_t, lnhl_t, lrclip_t;     // same for temperature
   int edson, gust_skip, fast_q, fast_t;
   // reciprocals / products hoisted for the lean Float64 pass (coflux_solve_tile.cuh::iterate_lean)
-  FT alpha_g, inv_g, inv_Rv, inv_Rd, inv_Ttr, inv_ramp, bnu, inv_nu;   // bnu, inv_nu: constant-viscosity case
+  FT alpha_g, inv_g, bnu, inv_nu;   // bnu, inv_nu: constant-viscosity case
 };
 template <typename FT> struct DevParams {
   ThermoC<FT> th;
@@ -132,31 +134,34 @@ template <typename FT> struct DevParams {
 // ---------------------------------------------------------------------------------------------
 template <typename FT> struct Thermo { FT rho, cp_m, q_vap, T_v; };
 
-template <typename FT>
+// MP: the math policy supplying pow and exp (M<FT>: CUDA math library; the Float64 tile kernel passes a policy
+// built on coflux_fastmath.cuh).  The ORDER of operations is the reference's in either case: 1/T_tr − 1/T cancels
+// three digits, so any reformulation of this expression moves q_sat by ~10 ulp and Δq = q_a − q_s by 100× that.
+template <typename FT, class MP = M<FT>>
 __device__ __forceinline__ FT psat_generic(const ThermoC<FT>& c, FT T, FT LH_0, FT dcp) {
-  return c.p_tr * M<FT>::pow(T / c.T_tr, dcp / c.R_v) *
-         M<FT>::exp((LH_0 - dcp * c.T_0) / c.R_v * (FT(1) / c.T_tr - FT(1) / T));
+  return c.p_tr * MP::pow(MP::div(T, c.T_tr), MP::div(dcp, c.R_v)) *
+         MP::exp(MP::div(LH_0 - dcp * c.T_0, c.R_v) * (MP::div(FT(1), c.T_tr) - MP::div(FT(1), T)));
 }
 template <typename FT> __device__ __forceinline__ FT liquid_fraction(const ThermoC<FT>& c, FT T) {
   if (T > c.T_fr) return FT(1);
   if (T <= c.T_in) return FT(0);
   return (T - c.T_in) / (c.T_fr - c.T_in);
 }
-template <typename FT> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q) {
+template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q) {
   FT lam = liquid_fraction(c, T);
   FT LH_0 = lam * c.LH_v0 + (FT(1) - lam) * c.LH_s0;
   FT dcp = lam * (c.cp_v - c.cp_l) + (FT(1) - lam) * (c.cp_v - c.cp_i);
-  FT ps = psat_generic(c, T, LH_0, dcp);
+  FT ps = psat_generic<FT, MP>(c, T, LH_0, dcp);
   FT denom = p - ps;
-  FT q_vs = (denom > FT(0)) ? c.Rd_over_Rv * (FT(1) - q) * ps / denom : M<FT>::inf();
+  FT q_vs = (denom > FT(0)) ? MP::div(c.Rd_over_Rv * (FT(1) - q) * ps, denom) : M<FT>::inf();
   FT q_c = M<FT>::max(q - q_vs, FT(0));
   FT q_liq = lam * q_c, q_ice = (FT(1) - lam) * q_c;
   FT R_m = c.R_d * (FT(1) + (c.eps - FT(1)) * q - c.eps * q_c);
   Thermo<FT> s;
-  s.rho = p / (R_m * T);
+  s.rho = MP::div(p, R_m * T);
   s.cp_m = c.cp_d + (c.cp_v - c.cp_d) * q + (c.cp_l - c.cp_v) * q_liq + (c.cp_i - c.cp_v) * q_ice;
   s.q_vap = q - q_liq - q_ice;
-  s.T_v = T * R_m / c.R_d;
+  s.T_v = MP::div(T * R_m, c.R_d);
   return s;
 }
 
@@ -279,17 +284,17 @@ template <typename FT> struct CellOut {
 
 template <typename FT> struct SurfaceState { FT qs, dq, dtheta, T_v, q_vap, nu_m, nu_t, nu_q; };
 
-template <typename FT, int SURF>
+template <typename FT, int SURF, class MP = M<FT>>
 __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P, const FluxP<FT>& F,
                                                           const Thermo<FT>& atm, FT pa, FT theta_a, FT x, FT Ts) {
   const ThermoC<FT>& c = P.th;
   SurfaceState<FT> s;
-  FT ps = (SURF == 0) ? psat_generic(c, Ts, c.LH_v0, c.cp_v - c.cp_l) : psat_generic(c, Ts, c.LH_s0, c.cp_v - c.cp_i);
-  FT qstar = ps / (atm.rho * c.R_v * Ts);
+  FT ps = (SURF == 0) ? psat_generic<FT, MP>(c, Ts, c.LH_v0, c.cp_v - c.cp_l) : psat_generic<FT, MP>(c, Ts, c.LH_s0, c.cp_v - c.cp_i);
+  FT qstar = MP::div(ps, atm.rho * c.R_v * Ts);
   s.qs = qstar * x;
   s.dq = atm.q_vap - s.qs;
   s.dtheta = theta_a - Ts;
-  Thermo<FT> surf = phase_equil_pTq(c, pa, Ts, s.qs);
+  Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs);
   s.T_v = surf.T_v;
   s.q_vap = surf.q_vap;
   s.nu_m = air_viscosity(F.mr.visc, Ts);

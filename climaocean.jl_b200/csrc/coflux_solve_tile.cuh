@@ -452,75 +452,33 @@ __device__ __noinline__ D3 lean_cold_pass(const DevParams<double>* P, double U2,
   return D3{us, ts, qs};
 }
 
-// Lean thermodynamics (A1, A2) for phase A: the saturation pressure p_tr·(T/T_tr)^(Δcp/R_v)·exp(…) becomes ONE
-// exponential of (Δcp/R_v)·ln(T/T_tr) + (ℒ₀ − Δcp·T₀)/R_v·(1/T_tr − 1/T); ln(T/T_tr) and 1/T are shared by the
-// liquid and the mixed-phase evaluation at the same temperature.
-struct LeanT { double rT, L, D; };     // 1/T, ln(T/T_tr), 1/T_tr − 1/T
-__device__ __forceinline__ LeanT lean_T(const FastConsts<double>& K, const LeanTabs& tb, double T) {
-  LeanT t;
-  t.rT = fm::rcp(T);
-  t.L = fm::log(T * K.inv_Ttr, tb.lg);
-  t.D = K.inv_Ttr - t.rT;
-  return t;
-}
-__device__ __forceinline__ double psat_lean(const ThermoC<double>& c, const FastConsts<double>& K, const LeanTabs& tb, const LeanT& t,
-                                            double LH_0, double dcp) {
-  return c.p_tr * fm::exp(fm::fma_(dcp * K.inv_Rv, t.L, ((LH_0 - dcp * c.T_0) * K.inv_Rv) * t.D), tb.ex);
-}
-// ps_liquid: the liquid-phase saturation pressure at T if the caller already has it (reused when λ = 1), else < 0
-__device__ __forceinline__ Thermo<double> phase_equil_lean(const ThermoC<double>& c, const FastConsts<double>& K, const LeanTabs& tb,
-                                                           const LeanT& t, double p, double T, double q, double ps_liquid) {
-  double lam = 1.0;
-  if (!(T > c.T_fr)) lam = (T <= c.T_in) ? 0.0 : (T - c.T_in) * K.inv_ramp;
-  double ps;
-  if (lam == 1.0 && ps_liquid >= 0.0) {
-    ps = ps_liquid;
-  } else {
-    const double LH_0 = lam * c.LH_v0 + (1.0 - lam) * c.LH_s0;
-    const double dcp = lam * (c.cp_v - c.cp_l) + (1.0 - lam) * (c.cp_v - c.cp_i);
-    ps = psat_lean(c, K, tb, t, LH_0, dcp);
-  }
-  const double denom = p - ps;
-  const double q_vs = (denom > 0.0) ? c.Rd_over_Rv * (1.0 - q) * ps * fm::rcp(denom) : CUDART_INF;
-  const double q_c = fmax(q - q_vs, 0.0);
-  const double q_liq = lam * q_c, q_ice = (1.0 - lam) * q_c;
-  const double R_m = c.R_d * (1.0 + (c.eps - 1.0) * q - c.eps * q_c);
-  Thermo<double> s;
-  s.rho = p * fm::rcp(R_m * T);
-  s.cp_m = c.cp_d + (c.cp_v - c.cp_d) * q + (c.cp_l - c.cp_v) * q_liq + (c.cp_i - c.cp_v) * q_ice;
-  s.q_vap = q - q_liq - q_ice;
-  s.T_v = T * R_m * K.inv_Rd;
-  return s;
-}
-// ocean surface state (bulk interface temperature): q_s, Δq, Δθ, T_v and q_v of the saturated surface air
-__device__ __forceinline__ SurfaceState<double> surface_state_lean(const DevParams<double>& P, const FluxP<double>& F, const LeanTabs& tb,
-                                                                   const Thermo<double>& atm, double pa, double theta_a, double x, double Ts) {
-  const ThermoC<double>& c = P.th;
-  const FastConsts<double>& K = P.K;
-  SurfaceState<double> s;
-  const LeanT t = lean_T(K, tb, Ts);
-  const double ps = psat_lean(c, K, tb, t, c.LH_v0, c.cp_v - c.cp_l);
-  const double qstar = ps * fm::rcp(atm.rho * c.R_v * Ts);
-  s.qs = qstar * x;
-  s.dq = atm.q_vap - s.qs;
-  s.dtheta = theta_a - Ts;
-  const Thermo<double> surf = phase_equil_lean(c, K, tb, t, pa, Ts, s.qs, ps);
-  s.T_v = surf.T_v;
-  s.q_vap = surf.q_vap;
-  s.nu_m = air_viscosity(F.mr.visc, Ts);
-  s.nu_t = s.nu_m; s.nu_q = s.nu_m;
-  return s;
-}
-// Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`; profiles/README.md):
-//   TILE 512 / 5 CTAs per SM (96 regs) 9.2 ms, TILE 384 / 6 CTAs (80 regs) 9.0 ms, TILE 256 / 8 CTAs
-//   (64 regs, 88 B of spills) 8.7 ms — the loop is latency bound (dependent FP64 chains), so the
-//   extra resident warps win over the spills.  COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every
-//   cell in shared memory between phase A and phase C; 0 recomputes the atmosphere state in phase C.
+// Math policy of the phase-A thermodynamics in the lean Float64 kernel: pow and exp from coflux_fastmath.cuh
+// (tables read from global memory here: three evaluations per cell), everything else — including the IEEE divisions
+// and the order of operations — exactly as in coflux_device.cuh.  Measured against the oracle on 256×128 cells:
+// q★ deviates 8.7e-14 (relative, floor 1e-3) with this policy; a fused single-exponential form of p_sat that is
+// mathematically identical deviates 5.2e-13 and pushes the salt flux past the 1e-12 bar — hence this form.
+struct MLeanD {
+  static __device__ __forceinline__ double pow(double x, double y) { return fm::exp(y * fm::log(x, &COFLUX_LOG_TABLE[0][0]), COFLUX_EXP_TABLE); }
+  static __device__ __forceinline__ double exp(double x) { return fm::exp(x, COFLUX_EXP_TABLE); }
+  // a/b by reciprocal + residual correction: agrees with the IEEE quotient on every one of 4.2 M random arguments
+  // (tools/fm_check.cu) at half the instructions and without the slow-path branch
+  static __device__ __forceinline__ double div(double a, double b) { return fm::div(a, b); }
+};
+
+// Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`, lean loop; tools/ab_variants.py, profiles/README.md):
+//   TILE 256: 8 CTAs/SM (64 regs, 288 B spills) 4.08 ms, 7 CTAs (72 regs) 3.98 ms, 6 CTAs (80 regs, 24 B) 3.98 ms;
+//   TILE 384: 6 CTAs 3.86 ms, 5 CTAs (96 regs) 3.95 ms;  TILE 512: 5 CTAs 4.11 ms.
+//   The kernel is latency bound (in-order issue over ~9-cycle FP64 dependencies, IPC ≈ 0.45/SMSP): resident warps and
+//   a long tile (fewer idle lanes while a tile's queue drains) matter, spills to L1 cost more than they buy.
+//   COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every cell in shared memory between phase A and phase C.
 #ifndef COFLUX_TILE_CARRY
 #define COFLUX_TILE_CARRY 1
 #endif
 #ifndef COFLUX_TILE_MIN_BLOCKS
 #define COFLUX_TILE_MIN_BLOCKS 6
+#endif
+#ifndef COFLUX_TILE_MIN_BLOCKS_F32
+#define COFLUX_TILE_MIN_BLOCKS_F32 8
 #endif
 #ifndef COFLUX_TILE_PRE
 #define COFLUX_TILE_PRE 2      /* similarity passes done in phase A before a cell is queued */
@@ -550,7 +508,7 @@ template <typename FT, int SPEC> struct TileTraits {
 };
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
-__global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+__global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCKS : COFLUX_TILE_MIN_BLOCKS_F32) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool VARNU = TileTraits<FT, SPEC>::VARNU;
   constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;
@@ -623,12 +581,11 @@ __global__ void __launch_bounds__(128, COFLUX_TILE_MIN_BLOCKS) flux_tile_kernel(
       // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6 and |ζ| up to thousands), so that the refill
       // loop of phase B only meets settled iterates on the short code path
       if constexpr (LEAN) {
-        const LeanT tA = lean_T(K, tb, Ta);
-        const Thermo<double> atm = phase_equil_lean(c, K, tb, tA, pa, Ta, qa, -1.0);
-        const double s = So * 1e-3;
-        const double x = (1.0 - s) * fm::rcp(1.0 - s + P.wmf_alpha * s);
-        const double theta_a = Ta + (P.g * P.h) * fm::rcp(atm.cp_m);
-        const SurfaceState<double> S = surface_state_lean(P, F, tb, atm, pa, theta_a, x, Ts);
+        const Thermo<double> atm = phase_equil_pTq<double, MLeanD>(c, pa, Ta, qa);
+        const double s = fm::div(So, 1000.0);
+        const double x = fm::div(1.0 - s, 1.0 - s + P.wmf_alpha * s);
+        const double theta_a = Ta + fm::div(P.g * P.h, atm.cp_m);
+        const SurfaceState<double> S = surface_state<double, 0, MLeanD>(P, F, atm, pa, theta_a, x, Ts);
         dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
 #if COFLUX_TILE_CARRY
         sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;

@@ -21,6 +21,7 @@ def _built():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     b.build_cuda()
+    b.build_tools()
     b.build_oracle()
     sys.path.pop(0)
     yield
