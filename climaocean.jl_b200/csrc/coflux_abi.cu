@@ -58,16 +58,16 @@ extern "C" int coflux_sizeof(const char* name) {
 // context
 // ---------------------------------------------------------------------------------------------
 struct HostStage {   // device staging planes + pipeline resources for coflux_update_state_host
-  static const int MAX_CHUNKS = 8;
+  static const int MAX_CHUNKS = 16;
   int halo = -1;
   size_t plane_bytes = 0;
   char* in[4] = {nullptr, nullptr, nullptr, nullptr};     // ocean u v T S
   char* xch[8] = {};                                     // exchange state
   char* ao[6] = {};                                      // Qv Qc Fv ρτx ρτy Ts
   char* net[8] = {};                                     // τx τy JT JS Qu Qal Qts J0
-  cudaStream_t stream = nullptr;                         // compute
+  cudaStream_t stream = nullptr, stream2 = nullptr;      // compute (chunks alternate, so that consecutive chunk kernels overlap)
   cudaStream_t copy_in = nullptr, copy_out = nullptr;    // H2D / D2H
-  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_f[MAX_CHUNKS] = {};
 };
 // Multi-GPU seam (mode B): this context's buffer, IPC-mapped by both neighbours.
 //   [0]   uint32 data_flag[2]  — written by the WEST neighbour: step id whose ρτx column (parity) is complete
@@ -508,10 +508,12 @@ static void free_stage(HostStage& s) {
   for (char*& p : s.ao) { if (p) cudaFree(p); p = nullptr; }
   for (char*& p : s.net) { if (p) cudaFree(p); p = nullptr; }
   if (s.stream) cudaStreamDestroy(s.stream);
+  if (s.stream2) cudaStreamDestroy(s.stream2);
   if (s.copy_in) cudaStreamDestroy(s.copy_in);
   if (s.copy_out) cudaStreamDestroy(s.copy_out);
   for (cudaEvent_t& ev : s.ev_in) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
   for (cudaEvent_t& ev : s.ev_k) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  for (cudaEvent_t& ev : s.ev_f) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
   s = HostStage();
 }
 
@@ -735,7 +737,7 @@ template <typename FT> static int tile_spec(const coflux_ctx* c) {
 }
 template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_tile_spec(const FluxArgs<FT>& a, cudaStream_t st) {
   auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, COFLUX_TILE, SPEC>;
-  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
+  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN, TileTraits<FT, SPEC>::TABS>);
   static bool configured = false;     // per instantiation
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1059,10 +1061,12 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
     for (char* p : s.net) CUDA_TRY(cudaMemset(p, 0, plane));
     for (char* p : s.ao) CUDA_TRY(cudaMemset(p, 0, plane));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s.copy_out, cudaStreamNonBlocking));
     for (cudaEvent_t& ev : s.ev_in) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (cudaEvent_t& ev : s.ev_k) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (cudaEvent_t& ev : s.ev_f) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CUDA_TRY(cudaDeviceSynchronize());
   }
   coflux_ocean_surface ocean;
@@ -1097,6 +1101,10 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
   // first parent row of H2D chunk c+1, so it waits for that chunk.  The stress rows that became
   // computable (they need ρτy of the previous row) follow, then their D2H.
   const int ring = g.ring, nyr = a.nyr;
+  // 16 equal row chunks, kernels of consecutive chunks on two alternating streams: a chunk kernel is only 1 300 CTAs
+  // (1.4 waves), so back-to-back launches on ONE stream leave the SMs idle in every tail and the kernels — not PCIe —
+  // bound the pipeline (measured: 8 chunks on one stream 7.8 ms per step at 1/12° Float64, while PCIe moves the 252 MB
+  // each way in 5.8 ms, tools/pcie_probe.py).  With two streams the next chunk's CTAs fill the tail of the previous one.
   int nch = HostStage::MAX_CHUNKS;
   if (g.Ny < 8 * nch) nch = 1;
   int f[HostStage::MAX_CHUNKS + 1], r[HostStage::MAX_CHUNKS + 1], sj[HostStage::MAX_CHUNKS + 1];
@@ -1117,12 +1125,15 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
     CUDA_TRY(cudaEventRecord(s.ev_in[k], s.copy_in));
   }
   for (int k = 0; k < nch; ++k) {
-    CUDA_TRY(cudaStreamWaitEvent(s.stream, s.ev_in[(k + 1 < nch) ? k + 1 : k], 0));
-    rc = launch_flux_rows<FT>(c, a, f[k], f[k + 1], s.stream);
+    cudaStream_t st = (k & 1) ? s.stream2 : s.stream;
+    CUDA_TRY(cudaStreamWaitEvent(st, s.ev_in[(k + 1 < nch) ? k + 1 : k], 0));
+    rc = launch_flux_rows<FT>(c, a, f[k], f[k + 1], st);
     if (rc) return rc;
-    rc = launch_stress_rows<FT>(c, sa, sj[k], sj[k + 1], s.stream);
+    CUDA_TRY(cudaEventRecord(s.ev_f[k], st));
+    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, s.ev_f[k - 1], 0));   // the first stress row of the chunk reads ρτy of the row before
+    rc = launch_stress_rows<FT>(c, sa, sj[k], sj[k + 1], st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(s.ev_k[k], s.stream));
+    CUDA_TRY(cudaEventRecord(s.ev_k[k], st));
     CUDA_TRY(cudaStreamWaitEvent(s.copy_out, s.ev_k[k], 0));
     // D2H: the interior rows just completed; the first / last chunk also carry the (untouched) halo rows
     const int p0 = (k == 0) ? 0 : sj[k] + H, p1 = (k == nch - 1) ? nj : sj[k + 1] + H;
@@ -1137,6 +1148,7 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
   }
   CUDA_TRY(cudaStreamSynchronize(s.copy_out));
   CUDA_TRY(cudaStreamSynchronize(s.stream));
+  CUDA_TRY(cudaStreamSynchronize(s.stream2));
   if (h2d_bytes) *h2d_bytes = h2d;
   if (d2h_bytes) *d2h_bytes = d2h;
   return COFLUX_OK;

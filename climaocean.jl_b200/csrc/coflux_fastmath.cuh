@@ -169,5 +169,21 @@ COFLUX_FM double exp(double x, const double* tab) {
   return fma_(T, p, T);
 }
 
+// ---- Float32 overloads: the CUDA single-precision functions (already SFU-based and short), so that the same pass
+// template serves both precisions -----------------------------------------------------------------------
+COFLUX_FM float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
+COFLUX_FM float rcp(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+COFLUX_FM float div(float a, float b) { return a / b; }
+COFLUX_FM float sqrt(float x) { return ::sqrtf(x); }
+COFLUX_FM float cbrt(float x) { return ::cbrtf(x); }
+COFLUX_FM float log(float x, const double*) { return ::logf(x); }
+COFLUX_FM float exp(float x, const double*) { return ::expf(x); }
+
 }  // namespace fm
 }  // namespace coflux

@@ -308,80 +308,110 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 #ifndef COFLUX_LEAN
 #define COFLUX_LEAN 1
 #endif
+#ifndef COFLUX_LEAN_F32
+#define COFLUX_LEAN_F32 1
+#endif
 #ifndef COFLUX_PSI_PREFETCH
 #define COFLUX_PSI_PREFETCH 0
 #endif
-struct LeanTabs { const double* lg; const double* ex; };
-struct LeanCell { double U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
-struct D3 { double u, t, q; };
+struct LeanTabs { const double* lg; const double* ex; };     // shared-memory log / exp tables (Float64 only)
+template <typename FT> struct LeanCell { FT U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
+template <typename FT> struct D3 { FT u, t, q; };
 
-// Literals of the hot loop.  Those with ≤ 21 significant bits are written in place: an FP64 instruction takes
-// them as a 32-bit immediate (the high word).  High-order series coefficients only need a few correct bits
+// Literals of the hot loop.  In Float64 those with ≤ 21 significant bits are written in place: an FP64 instruction
+// takes them as a 32-bit immediate (the high word).  High-order series coefficients only need a few correct bits
 // (they multiply |x|^k ≤ 2^(−13k)), so they are rounded to that form; the rest sit in constant memory.
-struct LeanLit {
-  double su3, ms2, ms1, ss2, ss1, ss0;
-  double c035, c5_035, m07, m075c, two3, m23, c1428, m8525;
+template <typename FT> struct LeanLit {
+  FT su3, ms2, ms1, ss2, ss1, ss0;
+  FT c035, c5_035, m07, m075c, two3, m23, c1428, m8525;
 };
-__constant__ LeanLit LL = {
-  -355.4458333333333, 0.91875, -5.2, 0.6497666666666667, -4.998666666666667, -0.005,
-  0.35, 5.0 / 0.35, -0.7, -0.75 * 5.0 / 0.35, 2.0 / 3.0, -(2.0 / 3.0), 14.28, -8.525};
+#define COFLUX_LEAN_LITERALS(T) { T(-355.4458333333333), T(0.91875), T(-5.2), T(0.6497666666666667), T(-4.998666666666667), T(-0.005), \
+  T(0.35), T(5.0 / 0.35), T(-0.7), T(-0.75 * 5.0 / 0.35), T(2.0 / 3.0), T(-(2.0 / 3.0)), T(14.28), T(-8.525) }
+__constant__ LeanLit<double> LL64 = COFLUX_LEAN_LITERALS(double);
+__constant__ LeanLit<float> LL32 = COFLUX_LEAN_LITERALS(float);
+template <typename FT> __device__ __forceinline__ const LeanLit<FT>& lean_lit();
+template <> __device__ __forceinline__ const LeanLit<double>& lean_lit<double>() { return LL64; }
+template <> __device__ __forceinline__ const LeanLit<float>& lean_lit<float>() { return LL32; }
 #define COFLUX_NROWS ((COFLUX_PSI_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
 
 // Row of the ψ table for z (clamped into the table, so that the loads are safe for ANY z: the caller may then
 // issue them before it knows whether z is in range, and the scheduler can hoist them above the cube root) and
-// the local coordinate t ∈ [−1, 1).
-__device__ __forceinline__ const double2* psi_table_row(double z, double& t) {
+// the local coordinate t ∈ [−1, 1).  A row holds the 8 coefficients of ψ_u followed by the 8 of ψ_θ.
+__device__ __forceinline__ const double* psi_table_row(double z, double& t) {
   const long long bits = __double_as_longlong(z);
   const int hi = (int)(bits >> 32);
   int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);              // (exponent − KMIN)·16 + top 4 mantissa bits
   row = max(0, min(row, COFLUX_NROWS - 1));
   const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
   t = fm::fma_(2.0, one_plus_u, -3.0);
-  return reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[row][0][0]);
+  return &COFLUX_PSI_TABLE_F64[row][0][0];
 }
-__device__ __forceinline__ double poly8v(double2 c0, double2 c1, double2 c2, double2 c3, double t) {
-  double a = fm::fma_(c3.y, t, c3.x);
-  a = fm::fma_(a, t, c2.y); a = fm::fma_(a, t, c2.x);
-  a = fm::fma_(a, t, c1.y); a = fm::fma_(a, t, c1.x);
-  a = fm::fma_(a, t, c0.y);
-  return fm::fma_(a, t, c0.x);
+__device__ __forceinline__ const float* psi_table_row(float z, float& t) {
+  const int bits = __float_as_int(z);
+  int row = (bits >> 19) - ((127 + COFLUX_PSI_KMIN) << 4);
+  row = max(0, min(row, COFLUX_NROWS - 1));
+  const float one_plus_u = __int_as_float(((bits & 0x0007ffff) << 4) | 0x3f800000);
+  t = fm::fma_(2.0f, one_plus_u, -3.0f);
+  return &COFLUX_PSI_TABLE_F32[row][0][0];
+}
+template <typename FT> struct Coef8 { FT c[8]; };
+__device__ __forceinline__ Coef8<double> ld_coef8(const double* p) {       // 4 × LDG.128
+  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  return Coef8<double>{{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y}};
+}
+__device__ __forceinline__ Coef8<float> ld_coef8(const float* p) {         // 2 × LDG.128
+  const float4* q = reinterpret_cast<const float4*>(p);
+  const float4 a = __ldg(q), b = __ldg(q + 1);
+  return Coef8<float>{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+template <typename FT> __device__ __forceinline__ FT poly8v(const Coef8<FT>& k, FT t) {
+  FT a = fm::fma_(k.c[7], t, k.c[6]);
+  a = fm::fma_(a, t, k.c[5]); a = fm::fma_(a, t, k.c[4]);
+  a = fm::fma_(a, t, k.c[3]); a = fm::fma_(a, t, k.c[2]);
+  a = fm::fma_(a, t, k.c[1]);
+  return fm::fma_(a, t, k.c[0]);
 }
 // stable closed forms (Edson et al. 2013), any z ≥ 0;  e = exp(−min(50, 0.35 z))
-__device__ __forceinline__ double psi_stable_m(double z, double e) {
-  return fm::fma_(-0.75 * (z - LL.c5_035), e, fm::fma_(LL.m07, z, LL.m075c));
+template <typename FT> __device__ __forceinline__ FT psi_stable_m(FT z, FT e) {
+  const LeanLit<FT>& LL = lean_lit<FT>();
+  return fm::fma_(FT(-0.75) * (z - LL.c5_035), e, fm::fma_(LL.m07, z, LL.m075c));
 }
-__device__ __forceinline__ double psi_stable_s(double z, double e) {
-  const double w = fm::fma_(LL.two3, z, 1.0);
+template <typename FT> __device__ __forceinline__ FT psi_stable_s(FT z, FT e) {
+  const LeanLit<FT>& LL = lean_lit<FT>();
+  const FT w = fm::fma_(LL.two3, z, FT(1));
   return fm::fma_(LL.m23 * (z - LL.c1428), e, fm::fma_(-w, fm::sqrt(w), LL.m8525));
 }
 
 // min / max by compare-select (3 instructions; fmin/fmax cost 5 with their NaN handling — the second operand
 // is a finite parameter everywhere below, so a NaN first operand still yields the parameter)
-__device__ __forceinline__ double dmin_(double a, double b) { return (a < b) ? a : b; }
-__device__ __forceinline__ double dmax_(double a, double b) { return (a > b) ? a : b; }
+template <typename FT> __device__ __forceinline__ FT dmin_(FT a, FT b) { return (a < b) ? a : b; }
+template <typename FT> __device__ __forceinline__ FT dmax_(FT a, FT b) { return (a > b) ? a : b; }
 
 // One pass.  Returns false when the pass left the short path (the scales are then unchanged and the
-// caller must run lean_cold_pass).
-template <int SPEC>
-__device__ __forceinline__ bool iterate_lean(const DevParams<double>& P, const FluxP<double>& F, const FastConsts<double>& K,
-                                             const LeanTabs& tb, const LeanCell& c, double& us, double& ts, double& qs) {
-  constexpr double TINY = 0.0001220703125;                   // 2⁻¹³: |ℓ/L★| below which the short series are exact to rounding
-  constexpr double Z_LO = 9.5367431640625e-07, Z_HI = 8192.0;   // table domain of −ζ: [2⁻²⁰, 2¹³)
-  constexpr double SMALL = 7.888609052210118e-31, BIG = 1.2676506002282294e30;   // 2⁻¹⁰⁰, 2¹⁰⁰
-  const double u0 = us, t0 = ts, q0 = qs;
-  const double bstar = fm::fma_(c.cb1, t0, c.cb2 * q0);
-  const bool unstable = bstar < 0.0;
-  bool ok = (u0 > SMALL) && (c.Ustab > 0.0);
-  const double r = fm::rcp(u0);
-  const double invL = (F.kappa * bstar) * (r * r);
-  const double zeta = P.h * invL;
+// caller must run lean_cold_pass).  Float32 runs the same pass with the CUDA single-precision functions
+// (fm:: overloads), the Float32 ψ table and the same series.
+template <typename FT, int SPEC>
+__device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP<FT>& F, const FastConsts<FT>& K,
+                                             const LeanTabs& tb, const LeanCell<FT>& c, FT& us, FT& ts, FT& qs) {
+  const LeanLit<FT>& LL = lean_lit<FT>();
+  constexpr FT TINY = FT(0.0001220703125);                   // 2⁻¹³: |ℓ/L★| below which the short series are exact to rounding
+  constexpr FT Z_LO = FT(9.5367431640625e-07), Z_HI = FT(8192.0);   // table domain of −ζ: [2⁻²⁰, 2¹³)
+  constexpr FT SMALL = FT(7.888609052210118e-31), BIG = FT(1.2676506002282294e30);   // 2⁻¹⁰⁰, 2¹⁰⁰
+  const FT u0 = us, t0 = ts, q0 = qs;
+  const FT bstar = fm::fma_(c.cb1, t0, c.cb2 * q0);
+  const bool unstable = bstar < FT(0);
+  bool ok = (u0 > SMALL) && (c.Ustab > FT(0));
+  const FT r = fm::rcp(u0);
+  const FT invL = (F.kappa * bstar) * (r * r);
+  const FT zeta = P.h * invL;
   // SPEC 1 (constant Charnock): the roughness lengths do not depend on this pass's wind speed — evaluate them
   // first, so that ONE block per stability class holds everything that depends on the sign of ζ
-  double lu = 0, ll = 0, lnq = K.lnhl_q, lq = F.qr.lmax, xm = 0, xs = 0;
-  auto roughness = [&](double alpha_g) {
-    lu = dmin_(fm::fma_(alpha_g * u0, u0, c.bnu * r), F.mr.lmax);
+  FT lu = 0, ll = 0, lnq = K.lnhl_q, lq = F.qr.lmax, xm = 0, xs = 0;
+  auto roughness = [&](FT alpha_g) {
+    lu = dmin_<FT>(fm::fma_(alpha_g * u0, u0, c.bnu * r), F.mr.lmax);
     ll = fm::log(lu, tb.lg);
-    const double lr = fm::log((lu * u0) * c.inv_nu, tb.lg);  // ln R★
+    const FT lr = fm::log((lu * u0) * c.inv_nu, tb.lg);      // ln R★
     if (lr > K.lrclip_q) {                                   // A·R★^(−b) < ℓ_max
       lnq = fm::fma_(F.qr.b, lr, K.lnhA_q);
       if (SPEC == 1) lq = F.qr.A * fm::exp(-F.qr.b * lr, tb.ex);
@@ -389,68 +419,69 @@ __device__ __forceinline__ bool iterate_lean(const DevParams<double>& P, const F
     xm = lu * invL; xs = lq * invL;                          // ℓ/L★ (same sign as ζ)
   };
   if (SPEC == 1) roughness(K.alpha_g);
-  double U = c.Ustab;                                        // √(Δu² + U_G,min²): no gustiness when Jᵇ ≤ 0
-  double psi_hm, psi_hs, sm_ = 0.0, ss_ = 0.0;
+  FT U = c.Ustab;                                            // √(Δu² + U_G,min²): no gustiness when Jᵇ ≤ 0
+  FT psi_hm, psi_hs, sm_ = FT(0), ss_ = FT(0);
   if (unstable) {
-    double t;
-    const double2* row = psi_table_row(-zeta, t);            // loads first: the cube root below hides their latency
-    const double2 m0 = __ldg(row), m1 = __ldg(row + 1), m2 = __ldg(row + 2), m3 = __ldg(row + 3);
-    const double2 s0 = __ldg(row + 4), s1 = __ldg(row + 5), s2 = __ldg(row + 6), s3 = __ldg(row + 7);
-    const double w = (-u0 * bstar) * P.hbl;                  // Jᵇ·h_bl > 0
+    FT t;
+    const FT* row = psi_table_row(-zeta, t);                 // loads first: the cube root below hides their latency
+    const Coef8<FT> km = ld_coef8(row), ks = ld_coef8(row + 8);
+    const FT w = (-u0 * bstar) * P.hbl;                      // Jᵇ·h_bl > 0
     ok = ok && (w > SMALL) && (w < BIG) && (-zeta >= Z_LO) && (-zeta < Z_HI);
-    const double UG = dmax_(F.beta * fm::cbrt(w), F.ugmin);
+    const FT UG = dmax_<FT>(F.beta * fm::cbrt(w), F.ugmin);
     U = fm::sqrt(fm::fma_(UG, UG, c.U2));
     if (SPEC == 1) {                                         // ψ(ℓ/L★): short series near 0, the same table beyond
       ok = ok && (-xm < Z_HI) && (-xs < Z_HI);
       if (-xm <= TINY) {
-        double a = fm::fma_(-12220.4140625, xm, -1198.931640625);
-        a = fm::fma_(a, xm, -131.46923828125); a = fm::fma_(a, xm, -17.578125); a = fm::fma_(a, xm, -3.75);
+        FT a = fm::fma_(FT(-12220.4140625), xm, FT(-1198.931640625));
+        a = fm::fma_(a, xm, FT(-131.46923828125)); a = fm::fma_(a, xm, FT(-17.578125)); a = fm::fma_(a, xm, FT(-3.75));
         sm_ = a * xm;
       } else {
-        double tt;
-        const double2* rr = psi_table_row(-xm, tt);
-        sm_ = poly8v(__ldg(rr), __ldg(rr + 1), __ldg(rr + 2), __ldg(rr + 3), tt);
+        FT tt;
+        const FT* rr = psi_table_row(-xm, tt);
+        sm_ = poly8v<FT>(ld_coef8(rr), tt);
       }
       if (-xs <= TINY) {
-        double b = fm::fma_(-39314.5625, xs, -3548.0859375);
-        b = fm::fma_(b, xs, LL.su3); b = fm::fma_(b, xs, -42.1875); b = fm::fma_(b, xs, -7.5);
+        FT b = fm::fma_(FT(-39314.5625), xs, FT(-3548.0859375));
+        b = fm::fma_(b, xs, LL.su3); b = fm::fma_(b, xs, FT(-42.1875)); b = fm::fma_(b, xs, FT(-7.5));
         ss_ = b * xs;
       } else {
-        double tt;
-        const double2* rr = psi_table_row(-xs, tt);
-        ss_ = poly8v(__ldg(rr + 4), __ldg(rr + 5), __ldg(rr + 6), __ldg(rr + 7), tt);
+        FT tt;
+        const FT* rr = psi_table_row(-xs, tt);
+        ss_ = poly8v<FT>(ld_coef8(rr + 8), tt);
       }
     }
-    psi_hm = poly8v(m0, m1, m2, m3, t);
-    psi_hs = poly8v(s0, s1, s2, s3, t);
+    psi_hm = poly8v<FT>(km, t);
+    psi_hs = poly8v<FT>(ks, t);
   } else {
-    const double e = fm::exp(-dmin_(LL.c035 * zeta, 50.0), tb.ex);
-    psi_hm = psi_stable_m(zeta, e);
-    psi_hs = psi_stable_s(zeta, e);
+    const FT e = fm::exp(-dmin_<FT>(LL.c035 * zeta, FT(50)), tb.ex);
+    psi_hm = psi_stable_m<FT>(zeta, e);
+    psi_hs = psi_stable_s<FT>(zeta, e);
     if (SPEC == 1) {
-      if (xm <= TINY) sm_ = xm * fm::fma_(fm::fma_(-0.12249755859375, xm, LL.ms2), xm, LL.ms1);
-      else sm_ = psi_stable_m(xm, fm::exp(-dmin_(LL.c035 * xm, 50.0), tb.ex));
-      if (xs <= TINY) ss_ = fm::fma_(fm::fma_(fm::fma_(-0.09034299850463867, xs, LL.ss2), xs, LL.ss1), xs, LL.ss0);
-      else ss_ = psi_stable_s(xs, fm::exp(-dmin_(LL.c035 * xs, 50.0), tb.ex));
+      if (xm <= TINY) sm_ = xm * fm::fma_(fm::fma_(FT(-0.12249755859375), xm, LL.ms2), xm, LL.ms1);
+      else sm_ = psi_stable_m<FT>(xm, fm::exp(-dmin_<FT>(LL.c035 * xm, FT(50)), tb.ex));
+      if (xs <= TINY) ss_ = fm::fma_(fm::fma_(fm::fma_(FT(-0.09034299850463867), xs, LL.ss2), xs, LL.ss1), xs, LL.ss0);
+      else ss_ = psi_stable_s<FT>(xs, fm::exp(-dmin_<FT>(LL.c035 * xs, FT(50)), tb.ex));
     }
   }
-  if (SPEC == 2) roughness(dmax_(fm::fma_(F.mr.a1, dmin_(U, F.mr.umax), F.mr.a2), F.mr.amin) * K.inv_g);
+  if (SPEC == 2) roughness(dmax_<FT>(fm::fma_(F.mr.a1, dmin_<FT>(U, F.mr.umax), F.mr.a2), F.mr.amin) * K.inv_g);
   if (!__builtin_expect(ok, 1)) return false;
-  const double prof_u = ((K.lnh - ll) - psi_hm) + sm_;
-  const double prof_q = (lnq - psi_hs) + ss_;
-  if (!(prof_u > 0.0)) { us = ts = qs = 0.0; return true; }
-  const double chi_u = F.kappa * fm::rcp(prof_u);
-  const double chi_q = (prof_q > 0.0) ? F.kappa * fm::rcp(prof_q) : 0.0;
+  const FT prof_u = ((K.lnh - ll) - psi_hm) + sm_;
+  const FT prof_q = (lnq - psi_hs) + ss_;
+  if (!(prof_u > FT(0))) { us = ts = qs = FT(0); return true; }
+  const FT chi_u = F.kappa * fm::rcp(prof_u);
+  const FT chi_q = (prof_q > FT(0)) ? F.kappa * fm::rcp(prof_q) : FT(0);
   us = chi_u * U; ts = chi_q * c.dth; qs = chi_q * c.dq;
   return true;
 }
 // the exact pass behind one by-value call, so that the lean loop stays small and its state stays in registers
-template <int SPEC>
-__device__ __noinline__ D3 lean_cold_pass(const DevParams<double>* P, double U2, double dth, double dq, double cb1, double cb2, double nu,
-                                          double us, double ts, double qs) {
-  iterate_fast<double, SPEC>(*P, P->ao, P->K, U2, dth, dq, 1.0, cb1, cb2, nu, us, ts, qs);
-  return D3{us, ts, qs};
+template <typename FT, int SPEC>
+__device__ __noinline__ D3<FT> lean_cold_pass(const DevParams<FT>* P, FT U2, FT dth, FT dq, FT cb1, FT cb2, FT nu, FT us, FT ts, FT qs) {
+  iterate_fast<FT, SPEC>(*P, P->ao, P->K, U2, dth, dq, FT(1), cb1, cb2, nu, us, ts, qs);
+  return D3<FT>{us, ts, qs};
 }
+template <typename FT> __device__ __forceinline__ bool same_bits(FT a, FT b);
+template <> __device__ __forceinline__ bool same_bits<double>(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
+template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
 
 // Math policy of the phase-A thermodynamics in the lean Float64 kernel: pow and exp from coflux_fastmath.cuh
 // (tables read from global memory here: three evaluations per cell), everything else — including the IEEE divisions
@@ -485,7 +516,7 @@ struct MLeanD {
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
-template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
+template <typename FT, int TILE, bool VARNU, bool LEAN, bool TABS> struct TileSmem {
   FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
@@ -496,15 +527,16 @@ template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
   // COFLUX_EXP_TABLE copies.  (The Brent snapshot of a cell in flight lives in that cell's own us/ts/qs/it
   // slots, which nobody reads until the cell is written back.)
   FT inu[(LEAN && VARNU) ? TILE : 1];
-  alignas(16) double lgt[LEAN ? 256 : 2];
-  double ext[LEAN ? 64 : 2];
+  alignas(16) double lgt[TABS ? 256 : 2];
+  double ext[TABS ? 64 : 2];
   int it[TILE];
   unsigned short queue[TILE];
   int n_front, n_back, head;
 };
 template <typename FT, int SPEC> struct TileTraits {
   static constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
-  static constexpr bool LEAN = (COFLUX_LEAN != 0) && std::is_same<FT, double>::value && (SPEC != 0);
+  static constexpr bool LEAN = (COFLUX_LEAN != 0) && (SPEC != 0) && (std::is_same<FT, double>::value || (COFLUX_LEAN_F32 != 0));
+  static constexpr bool TABS = LEAN && std::is_same<FT, double>::value;   // log / exp tables in shared memory
 };
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
@@ -512,14 +544,16 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool VARNU = TileTraits<FT, SPEC>::VARNU;
   constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;
-  TileSmem<FT, TILE, VARNU, LEAN>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN>*>(smem_raw);
+  constexpr bool TABS = TileTraits<FT, SPEC>::TABS;
+  using MP = std::conditional_t<TABS, MLeanD, M<FT>>;      // math policy of the phase-A thermodynamics
+  TileSmem<FT, TILE, VARNU, LEAN, TABS>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN, TABS>*>(smem_raw);
   const DevParams<FT>& P = a.P;
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
   const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
-  if (LEAN) {
+  if (TABS) {
     for (int k = tid; k < 256; k += 128) sm.lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
     if (tid < 64) sm.ext[tid] = COFLUX_EXP_TABLE[tid];
   }
@@ -581,29 +615,29 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
       // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6 and |ζ| up to thousands), so that the refill
       // loop of phase B only meets settled iterates on the short code path
       if constexpr (LEAN) {
-        const Thermo<double> atm = phase_equil_pTq<double, MLeanD>(c, pa, Ta, qa);
-        const double s = fm::div(So, 1000.0);
-        const double x = fm::div(1.0 - s, 1.0 - s + P.wmf_alpha * s);
-        const double theta_a = Ta + fm::div(P.g * P.h, atm.cp_m);
-        const SurfaceState<double> S = surface_state<double, 0, MLeanD>(P, F, atm, pa, theta_a, x, Ts);
+        const Thermo<FT> atm = phase_equil_pTq<FT, MP>(c, pa, Ta, qa);
+        const FT s = MP::div(So, FT(1000));
+        const FT x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s);
+        const FT theta_a = Ta + MP::div(P.g * P.h, atm.cp_m);
+        const SurfaceState<FT> S = surface_state<FT, 0, MP>(P, F, atm, pa, theta_a, x, Ts);
         dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
 #if COFLUX_TILE_CARRY
         sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
 #endif
-        LeanCell lc;
+        LeanCell<FT> lc;
         lc.U2 = U2; lc.dth = dtheta; lc.dq = dq;
-        { const double v = fm::fma_(F.ugmin, F.ugmin, U2); lc.Ustab = (v > 0.0) ? fm::sqrt(v) : 0.0; }
-        { const double gTv = P.g * fm::rcp(Tv); lc.cb1 = gTv * (1.0 + delta * qv); lc.cb2 = gTv * (delta * Tv); }
+        { const FT v = fm::fma_(F.ugmin, F.ugmin, U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
+        { const FT gTv = P.g * fm::rcp(Tv); lc.cb1 = gTv * (FT(1) + delta * qv); lc.cb2 = gTv * (delta * Tv); }
         lc.bnu = F.mr.beta_s * nu_m; lc.inv_nu = fm::rcp(nu_m);
 #pragma unroll 1
         for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
-          const double u0 = us, t0 = ts, q0 = qs;
-          if (!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs)) {
-            const D3 r = lean_cold_pass<SPEC>(&P, U2, dtheta, dq, lc.cb1, lc.cb2, nu_m, u0, t0, q0);
+          const FT u0 = us, t0 = ts, q0 = qs;
+          if (!iterate_lean<FT, SPEC>(P, F, K, tb, lc, us, ts, qs)) {
+            const D3<FT> r = lean_cold_pass<FT, SPEC>(&P, U2, dtheta, dq, lc.cb1, lc.cb2, nu_m, u0, t0, q0);
             us = r.u; ts = r.t; qs = r.q;
           }
           ++it;
-          go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
+          go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
         }
         if (VARNU && go) sm.inu[cidx] = lc.inv_nu;
         Tv = lc.cb1; qv = lc.cb2;      // what the lean loop of phase B wants in sm.Tv / sm.qv
@@ -647,10 +681,11 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
   // is periodic with period λ = it − snap_it; the reference keeps iterating until maxiter, i.e. it
   // ends (maxiter − it) mod λ passes further along the same orbit — run just those and stop.
   if constexpr (LEAN) {
-    constexpr int BRENT_FROM = 24;               // cycle detection starts here (Float64 converges in < 30 passes)
+    constexpr int BRENT_FROM = (sizeof(FT) == 8) ? 24 : 6;   // cycle detection starts here (Float64 converges in < 30 passes;
+                                                             // in Float32 8 % of the cells only ever reach a limit cycle)
     int slot = -1, it = 0;
-    LeanCell lc{};
-    double nu = F.mr.visc.nu, us = 0, ts = 0, qs = 0;
+    LeanCell<FT> lc{};
+    FT nu = F.mr.visc.nu, us = 0, ts = 0, qs = 0;
     if (!VARNU) { lc.bnu = K.bnu; lc.inv_nu = K.inv_nu; }
     auto pop = [&]() {
       const int pos = atomicAdd(&sm.head, 1);
@@ -658,7 +693,7 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
       if (pos < n_total) {
         slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
         lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.Tv[slot]; lc.cb2 = sm.qv[slot];
-        { const double v = fm::fma_(F.ugmin, F.ugmin, lc.U2); lc.Ustab = (v > 0.0) ? fm::sqrt(v) : 0.0; }
+        { const FT v = fm::fma_(F.ugmin, F.ugmin, lc.U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
         if (VARNU) { nu = sm.nu[slot]; lc.inv_nu = sm.inu[slot]; lc.bnu = F.mr.beta_s * nu; }
         us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
       }
@@ -679,8 +714,7 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
         return false;
       }
       if (!go) return false;
-      if (__double_as_longlong(us) == __double_as_longlong(sm.us[slot]) && __double_as_longlong(ts) == __double_as_longlong(sm.ts[slot]) &&
-          __double_as_longlong(qs) == __double_as_longlong(sm.qs[slot])) {
+      if (same_bits<FT>(us, sm.us[slot]) && same_bits<FT>(ts, sm.ts[slot]) && same_bits<FT>(qs, sm.qs[slot])) {
         const int lambda = it - snap_it;
         const int stop = it + (F.maxit - it) % lambda;
         sm.it[slot] = packed | ((stop + 1) << 16);
@@ -697,13 +731,13 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
     pop();
     while (__any_sync(0xffffffffu, slot >= 0)) {
       if (slot >= 0) {
-        const double u0 = us, t0 = ts, q0 = qs;
-        if (__builtin_expect(!iterate_lean<SPEC>(P, F, K, tb, lc, us, ts, qs), 0)) {
-          const D3 r = lean_cold_pass<SPEC>(&P, lc.U2, lc.dth, lc.dq, lc.cb1, lc.cb2, nu, u0, t0, q0);
+        const FT u0 = us, t0 = ts, q0 = qs;
+        if (__builtin_expect(!iterate_lean<FT, SPEC>(P, F, K, tb, lc, us, ts, qs), 0)) {
+          const D3<FT> r = lean_cold_pass<FT, SPEC>(&P, lc.U2, lc.dth, lc.dq, lc.cb1, lc.cb2, nu, u0, t0, q0);
           us = r.u; ts = r.t; qs = r.q;
         }
         ++it;
-        bool go = keep_going<double>(F, it, us, ts, qs, u0, t0, q0);
+        bool go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
         if (__builtin_expect(it >= BRENT_FROM && !fixed && F.maxit < 250, 0)) go = brent(go);   // (8-bit fields)
         if (!go) {
           sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
@@ -791,10 +825,10 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
 #endif
       FT taux, tauy;
       if constexpr (LEAN) {
-        const double d2 = du * du + dv * dv;
-        const double k = (d2 > 1e-280) ? (-us * us) * fm::rcp(fm::sqrt(d2)) : 0.0;   // −u★²/‖Δu‖ (0 when calm)
-        taux = (d2 > 1e-280) ? k * du : ((d2 == 0.0) ? 0.0 : -us * us * du / ::sqrt(d2));
-        tauy = (d2 > 1e-280) ? k * dv : ((d2 == 0.0) ? 0.0 : -us * us * dv / ::sqrt(d2));
+        const FT d2 = du * du + dv * dv;
+        const FT k = (d2 > FT(1e-30)) ? (-us * us) * fm::rcp(fm::sqrt(d2)) : FT(0);   // −u★²/‖Δu‖ (0 when calm)
+        taux = (d2 > FT(1e-30)) ? k * du : ((d2 == FT(0)) ? FT(0) : -us * us * du / M<FT>::sqrt(d2));
+        tauy = (d2 > FT(1e-30)) ? k * dv : ((d2 == FT(0)) ? FT(0) : -us * us * dv / M<FT>::sqrt(d2));
       } else {
         const FT dU = M<FT>::sqrt(du * du + dv * dv);
         taux = (dU == FT(0)) ? dU : -us * us * du / dU;
