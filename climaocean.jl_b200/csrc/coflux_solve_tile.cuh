@@ -516,19 +516,16 @@ struct MLeanD {
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
-template <typename FT, int TILE, bool VARNU, bool LEAN, bool TABS> struct TileSmem {
+template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
   FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
 #if COFLUX_TILE_CARRY
   FT rho[TILE], cp[TILE];                                 // carried to phase C
 #endif
-  // lean Float64 loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus 1/ν and the COFLUX_LOG_TABLE /
-  // COFLUX_EXP_TABLE copies.  (The Brent snapshot of a cell in flight lives in that cell's own us/ts/qs/it
-  // slots, which nobody reads until the cell is written back.)
+  // lean loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus 1/ν.  (The Brent snapshot of a cell in
+  // flight lives in that cell's own us/ts/qs/it slots, which nobody reads until the cell is written back.)
   FT inu[(LEAN && VARNU) ? TILE : 1];
-  alignas(16) double lgt[TABS ? 256 : 2];
-  double ext[TABS ? 64 : 2];
   int it[TILE];
   unsigned short queue[TILE];
   int n_front, n_back, head;
@@ -546,7 +543,11 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
   constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;
   constexpr bool TABS = TileTraits<FT, SPEC>::TABS;
   using MP = std::conditional_t<TABS, MLeanD, M<FT>>;      // math policy of the phase-A thermodynamics
-  TileSmem<FT, TILE, VARNU, LEAN, TABS>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN, TABS>*>(smem_raw);
+  TileSmem<FT, TILE, VARNU, LEAN>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN>*>(smem_raw);
+  // log / exp tables of the lean Float64 functions: STATIC shared arrays, so that their addresses are compile-time
+  // shared-window offsets (through the dynamic block every lookup paid a generic→shared address conversion)
+  __shared__ __align__(16) double s_lgt[TABS ? 256 : 2];
+  __shared__ double s_ext[TABS ? 64 : 2];
   const DevParams<FT>& P = a.P;
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
@@ -554,11 +555,11 @@ __global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCK
   const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
   if (TABS) {
-    for (int k = tid; k < 256; k += 128) sm.lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
-    if (tid < 64) sm.ext[tid] = COFLUX_EXP_TABLE[tid];
+    for (int k = tid; k < 256; k += 128) s_lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
+    if (tid < 64) s_ext[tid] = COFLUX_EXP_TABLE[tid];
   }
   __syncthreads();
-  const LeanTabs tb{sm.lgt, sm.ext};
+  const LeanTabs tb{s_lgt, s_ext};
   const FastConsts<FT>& K = P.K;
   const FT delta = c.eps - FT(1);
   const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
