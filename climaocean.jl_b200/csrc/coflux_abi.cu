@@ -736,19 +736,20 @@ template <typename FT> static int tile_spec(const coflux_ctx* c) {
   return 0;
 }
 template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_tile_spec(const FluxArgs<FT>& a, cudaStream_t st) {
-  auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, COFLUX_TILE, SPEC>;
-  const size_t smem = sizeof(TileSmem<FT, COFLUX_TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
+  constexpr int TILE = TileTraits<FT, SPEC>::TILE;
+  auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, TILE, SPEC>;
+  const size_t smem = sizeof(TileSmem<FT, TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
   static bool configured = false;     // per instantiation
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // shared-memory carve-out: exactly what COFLUX_TILE_MIN_BLOCKS resident CTAs need (+1 KB each of system use); the rest
     // of the 256 KB stays L1, which holds the psi table rows and the gathered atmosphere tiles
-    const int min_blocks = (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCKS : COFLUX_TILE_MIN_BLOCKS_F32;
+    const int min_blocks = TileTraits<FT, SPEC>::MIN_BLOCKS;
     const int carve = (int)((min_blocks * (smem + 1024 + 2560) * 100 + 228 * 1024 - 1) / (228 * 1024));   // + static log/exp tables
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
     configured = true;
   }
-  kern<<<grid_for(a.ncell - a.cell0, COFLUX_TILE), 128, smem, st>>>(a);
+  kern<<<grid_for(a.ncell - a.cell0, TILE), 128, smem, st>>>(a);
   return COFLUX_OK;
 }
 template <typename FT, bool INTERP, bool ASSEMBLE> static int launch_tile(const coflux_ctx* c, const FluxArgs<FT>& a, cudaStream_t st) {

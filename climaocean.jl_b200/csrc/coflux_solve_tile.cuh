@@ -508,11 +508,14 @@ struct MLeanD {
 #ifndef COFLUX_TILE_MIN_BLOCKS
 #define COFLUX_TILE_MIN_BLOCKS 6
 #endif
+#ifndef COFLUX_TILE_CELLS
+#define COFLUX_TILE_CELLS 384
+#endif
 #ifndef COFLUX_TILE_MIN_BLOCKS_F32
 #define COFLUX_TILE_MIN_BLOCKS_F32 8
 #endif
 #ifndef COFLUX_TILE_PRE
-#define COFLUX_TILE_PRE 2      /* similarity passes done in phase A before a cell is queued */
+#define COFLUX_TILE_PRE 0      /* similarity passes done in lock step in phase A before a cell is queued (A/B on B200, 1/12° F64 default / corrected / F32: 2 → 3.99 / 3.77 / 2.67 ms, 1 → 3.95 / 3.70 / 2.53, 0 → 3.90 / 3.56 / 2.50) */
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
@@ -534,10 +537,15 @@ template <typename FT, int SPEC> struct TileTraits {
   static constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
   static constexpr bool LEAN = (COFLUX_LEAN != 0) && (SPEC != 0) && (std::is_same<FT, double>::value || (COFLUX_LEAN_F32 != 0));
   static constexpr bool TABS = LEAN && std::is_same<FT, double>::value;   // log / exp tables in shared memory
+  // resident CTAs per SM / cells per CTA, A/B-measured per precision and parameter set (profiles/README.md):
+  // Float64 `:default` and generic 6 × 384 (80 registers); Float64 `:corrected` 7 × 256 (72 registers: its pass carries
+  // no ψ(ℓ/L) terms); Float32 8 × 384 (64 registers)
+  static constexpr int MIN_BLOCKS = (sizeof(FT) == 8) ? ((SPEC == 2) ? COFLUX_TILE_MIN_BLOCKS + 1 : COFLUX_TILE_MIN_BLOCKS) : COFLUX_TILE_MIN_BLOCKS_F32;
+  static constexpr int TILE = (sizeof(FT) == 8 && SPEC == 2) ? 256 : COFLUX_TILE_CELLS;
 };
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
-__global__ void __launch_bounds__(128, (sizeof(FT) == 8) ? COFLUX_TILE_MIN_BLOCKS : COFLUX_TILE_MIN_BLOCKS_F32) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+__global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool VARNU = TileTraits<FT, SPEC>::VARNU;
   constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;

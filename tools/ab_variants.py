@@ -11,12 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "b8_t256": ["COFLUX_TILE_MIN_BLOCKS=8"],
-    "b7_t256": ["COFLUX_TILE_MIN_BLOCKS=7"],
-    "b6_t256": ["COFLUX_TILE_MIN_BLOCKS=6"],
-    "b6_t384": ["COFLUX_TILE_MIN_BLOCKS=6", "COFLUX_TILE_CELLS=384"],
-    "b5_t384": ["COFLUX_TILE_MIN_BLOCKS=5", "COFLUX_TILE_CELLS=384"],
-    "b5_t512": ["COFLUX_TILE_MIN_BLOCKS=5", "COFLUX_TILE_CELLS=512"],
+    "b6_t384": [],
+    "b7_t256": ["COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=7"],
+    "b7_t320": ["COFLUX_TILE_CELLS=320", "COFLUX_TILE_MIN_BLOCKS=7"],
+    "b8_t256": ["COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=8"],
+    "b5_t448": ["COFLUX_TILE_CELLS=448", "COFLUX_TILE_MIN_BLOCKS=5"],
 }
 
 
