@@ -164,6 +164,10 @@ class HostStep(C.Structure):
                                           "net_S", "latent_heat", "sensible_heat")] + [("halo", i32), ("reserved", i32)]
 
 
+class SalinityNormalization(C.Structure):
+    _fields_ = [("flux", Array), ("additional", Array), ("area", Array), ("mask", Array)]
+
+
 STRUCTS = {"array": Array, "air_viscosity": AirViscosity, "momentum_roughness": MomentumRoughness,
            "scalar_roughness": ScalarRoughness, "flux_params": FluxParams, "thermodynamics": Thermodynamics,
            "atmosphere_properties": AtmosphereProperties, "ocean_properties": OceanProperties,
@@ -171,7 +175,8 @@ STRUCTS = {"array": Array, "air_viscosity": AirViscosity, "momentum_roughness": 
            "config": Config, "atmos_series": AtmosSeries, "exchange_state": ExchangeState,
            "ocean_surface": OceanSurface, "interface_fluxes": InterfaceFluxes, "sea_ice_state": SeaIceState,
            "ocean_columns": OceanColumns, "ice_ocean_fluxes": IceOceanFluxes, "net_ocean_fluxes": NetOceanFluxes,
-           "update_inputs": UpdateInputs, "update_outputs": UpdateOutputs, "host_step": HostStep}
+           "update_inputs": UpdateInputs, "update_outputs": UpdateOutputs, "host_step": HostStep,
+           "salinity_normalization": SalinityNormalization}
 
 # every symbol include/coflux.h declares
 EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "coflux_sizeof", "coflux_default_config",
@@ -179,7 +184,7 @@ EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "cofl
            "coflux_interpolate_atmosphere", "coflux_atmosphere_ocean_fluxes", "coflux_atmosphere_sea_ice_fluxes",
            "coflux_sea_ice_ocean_fluxes", "coflux_assemble_net_ocean_fluxes", "coflux_update_state",
            "coflux_update_state_host", "coflux_launch_count", "coflux_profile_enable", "coflux_profile_read", "coflux_seam_export", "coflux_seam_attach",
-           "coflux_seam_detach")
+           "coflux_seam_detach", "coflux_salinity_flux_sums", "coflux_subtract_mean_flux", "coflux_normalize_salinity_flux")
 
 
 class CofluxError(RuntimeError):
@@ -228,6 +233,9 @@ def load_library(path=None):
     lib.coflux_seam_export.argtypes = [vp, vp]
     lib.coflux_seam_attach.argtypes = [vp, vp, vp, i32, i32]
     lib.coflux_seam_detach.argtypes = [vp]
+    lib.coflux_salinity_flux_sums.argtypes = [vp, P(SalinityNormalization), vp, vp]
+    lib.coflux_subtract_mean_flux.argtypes = [vp, P(SalinityNormalization), vp, vp]
+    lib.coflux_normalize_salinity_flux.argtypes = [vp, P(SalinityNormalization), vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("coflux_abi_version", "coflux_sizeof"):

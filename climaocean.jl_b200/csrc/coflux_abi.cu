@@ -6,6 +6,7 @@
 // entry, and the multi-GPU seam.  There is no CPU compute path in this file: every entry point
 // either launches CUDA kernels or fails with a status code.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -49,7 +50,7 @@ extern "C" int coflux_sizeof(const char* name) {
   SZ(array); SZ(air_viscosity); SZ(momentum_roughness); SZ(scalar_roughness); SZ(flux_params); SZ(thermodynamics);
   SZ(atmosphere_properties); SZ(ocean_properties); SZ(radiation_properties); SZ(ice_ocean_params); SZ(grid_desc);
   SZ(config); SZ(atmos_series); SZ(exchange_state); SZ(ocean_surface); SZ(interface_fluxes); SZ(sea_ice_state);
-  SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step);
+  SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step); SZ(salinity_normalization);
 #undef SZ
   return -1;
 }
@@ -96,7 +97,9 @@ struct Profile {
   double flux_ms = 0, stress_ms = 0;
   long long calls = 0;
 };
+static const int SALT_BLOCKS = 148 * 4;   // CTAs of the salinity-flux reduction (fixed: the summation order must not depend on the grid size)
 struct coflux_ctx {
+  double* salt_ws = nullptr;             // [2 * SALT_BLOCKS] CTA partials + [2] totals of the salinity-flux reduction
   coflux_config cfg;
   Profile prof;
   int device;
@@ -524,6 +527,7 @@ extern "C" int coflux_destroy(coflux_ctx* c) {
   coflux_seam_detach(c);
   if (c->seam.local) cudaFree(c->seam.local);
   free_stage(c->stage);
+  if (c->salt_ws) cudaFree(c->salt_ws);
   for (auto& row : c->prof.ev)
     for (cudaEvent_t& e : row) if (e) cudaEventDestroy(e);
   delete c;
@@ -1163,6 +1167,76 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
   CUDA_TRY(cudaSetDevice(c->device));
   return c->cfg.dtype == COFLUX_F64 ? do_update_host<double>(c, atm, step, time, h2d_bytes, d2h_bytes)
                                     : do_update_host<float>(c, atm, step, time, h2d_bytes, d2h_bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NormalizeSalinity (omip_simulation.jl:187-220)
+// ---------------------------------------------------------------------------------------------
+static int salt_workspace(coflux_ctx* c) {
+  if (c->salt_ws) return COFLUX_OK;
+  CUDA_TRY(cudaMalloc(&c->salt_ws, sizeof(double) * (2 * SALT_BLOCKS + 2)));
+  return COFLUX_OK;
+}
+template <typename FT>
+static int do_salt_sums(coflux_ctx* c, const coflux_salinity_normalization* n, double* sums, cudaStream_t st) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  SaltSumArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.Nx = g.Nx; a.Ny = g.Ny;
+  a.flux = view2d(n->flux, 0, sizeof(FT)); a.add = view2d(n->additional, 0, sizeof(FT)); a.area = view2d(n->area, 0, sizeof(FT));
+  a.mask = view2d(n->mask, 0, 1);
+  a.partial = c->salt_ws;
+  salt_sums_kernel<FT><<<SALT_BLOCKS, 256, 0, st>>>(a);
+  salt_sums_final_kernel<<<1, 32, 0, st>>>(c->salt_ws, SALT_BLOCKS, sums);
+  return check_launch(c, 2);
+}
+template <typename FT>
+static int do_subtract_mean(coflux_ctx* c, const coflux_salinity_normalization* n, const double* sums, cudaStream_t st) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  SubMeanArgs<FT> a;
+  a.p = static_cast<char*>(n->flux.ptr) + (int64_t)n->flux.off_k * n->flux.stride_k * (int64_t)sizeof(FT);
+  a.si = n->flux.stride_i; a.sj = n->flux.stride_j;
+  a.ni = g.Nx + 2 * n->flux.off_i; a.nj = g.Ny + 2 * n->flux.off_j;
+  a.sums = sums;
+  const long long cells = (long long)a.ni * a.nj;
+  const unsigned grid = (unsigned)std::min<long long>((cells + 255) / 256, 148LL * 8);
+  subtract_mean_kernel<FT><<<grid, 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+static int check_norm(coflux_ctx* c, const coflux_salinity_normalization* n) {
+  REQUIRE(c && n, "NULL argument");
+  REQUIRE(n->flux.ptr && n->area.ptr, "salinity normalization needs the flux field and the cell areas");
+  REQUIRE(n->flux.off_i >= 0 && n->flux.off_j >= 0, "negative halo offsets");
+  return COFLUX_OK;
+}
+extern "C" int coflux_salinity_flux_sums(coflux_ctx* c, const coflux_salinity_normalization* n, double* device_sums, void* stream) {
+  int rc = check_norm(c, n);
+  if (rc) return rc;
+  REQUIRE(device_sums, "device_sums is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  rc = salt_workspace(c);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_salt_sums<double>(c, n, device_sums, st) : do_salt_sums<float>(c, n, device_sums, st);
+}
+extern "C" int coflux_subtract_mean_flux(coflux_ctx* c, const coflux_salinity_normalization* n, const double* device_sums, void* stream) {
+  int rc = check_norm(c, n);
+  if (rc) return rc;
+  REQUIRE(device_sums, "device_sums is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_subtract_mean<double>(c, n, device_sums, st) : do_subtract_mean<float>(c, n, device_sums, st);
+}
+extern "C" int coflux_normalize_salinity_flux(coflux_ctx* c, const coflux_salinity_normalization* n, void* stream) {
+  int rc = check_norm(c, n);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  rc = salt_workspace(c);
+  if (rc) return rc;
+  double* sums = c->salt_ws + 2 * SALT_BLOCKS;
+  rc = coflux_salinity_flux_sums(c, n, sums, stream);
+  if (rc) return rc;
+  return coflux_subtract_mean_flux(c, n, sums, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

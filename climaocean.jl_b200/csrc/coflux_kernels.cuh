@@ -415,4 +415,63 @@ template <typename FT> __global__ void __launch_bounds__(COFLUX_IO_BLOCK) ice_oc
   stg<FT>(a.ihm, i, j, h);
 }
 
+// ---------------------------------------------------------------------------------------------
+// NormalizeSalinity (omip_simulation.jl:187-220): area-weighted mean of the combined surface salinity flux,
+// removed from the whole parent of the bulk-flux field.  HBM-bound streaming: 1–2 words read per cell for the
+// sums, 1 read + 1 write per parent element for the subtraction.  The reduction is a fixed-order tree (thread →
+// warp shuffle → CTA → one thread over the CTA partials), accumulated in Float64 for either precision.
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct SaltSumArgs {
+  int Nx, Ny;
+  DArr flux, add, area, mask;
+  double* partial;      // [2 * gridDim.x]
+};
+template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(const __grid_constant__ SaltSumArgs<FT> a) {
+  const long long n = (long long)a.Nx * a.Ny;
+  double num = 0.0, den = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+    if (!is_active(a.mask, i, j)) continue;
+    double f = (double)ldg<FT>(a.flux, i, j);
+    if (a.add.p) f += (double)ldg<FT>(a.add, i, j);
+    const double A = (double)ldg<FT>(a.area, i, j);
+    num = fma(f, A, num);
+    den += A;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
+  __shared__ double sn[8], sd[8];
+  if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tn = 0.0, td = 0.0;
+    for (int w = 0; w < 8; ++w) { tn += sn[w]; td += sd[w]; }
+    a.partial[2 * blockIdx.x] = tn; a.partial[2 * blockIdx.x + 1] = td;
+  }
+}
+__global__ void __launch_bounds__(32) salt_sums_final_kernel(const double* partial, int nblocks, double* sums) {
+  // one warp, fixed order: lane l adds partials l, l+32, …; then a shuffle tree
+  double num = 0.0, den = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 32) { num += partial[2 * b]; den += partial[2 * b + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
+  if (threadIdx.x == 0) { sums[0] = num; sums[1] = den; }
+}
+template <typename FT> struct SubMeanArgs {
+  char* p;              // first element of the parent
+  int64_t si, sj;
+  int ni, nj;           // parent extents (interior + 2 halos)
+  const double* sums;
+};
+template <typename FT> __global__ void __launch_bounds__(256) subtract_mean_kernel(const __grid_constant__ SubMeanArgs<FT> a) {
+  const double den = a.sums[1];
+  const FT mean = (den != 0.0) ? (FT)(a.sums[0] / den) : FT(0);
+  const long long n = (long long)a.ni * a.nj;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / a.ni), i = (int)(idx - (long long)j * a.ni);
+    FT* q = reinterpret_cast<FT*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj);
+    *q -= mean;
+  }
+}
+
 }  // namespace coflux

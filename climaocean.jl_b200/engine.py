@@ -89,6 +89,16 @@ class Engine:
         _abi.check(self.lib.coflux_update_state(self._ctx, C.byref(inputs), C.byref(outputs), float(time),
                                                 _stream_handle(stream)), self.lib)
 
+    # --- NormalizeSalinity (omip_simulation.jl:187-220) ---
+    def salinity_flux_sums(self, norm, device_sums_ptr, stream=None):
+        _abi.check(self.lib.coflux_salinity_flux_sums(self._ctx, C.byref(norm), device_sums_ptr, _stream_handle(stream)), self.lib)
+
+    def subtract_mean_flux(self, norm, device_sums_ptr, stream=None):
+        _abi.check(self.lib.coflux_subtract_mean_flux(self._ctx, C.byref(norm), device_sums_ptr, _stream_handle(stream)), self.lib)
+
+    def normalize_salinity_flux(self, norm, stream=None):
+        _abi.check(self.lib.coflux_normalize_salinity_flux(self._ctx, C.byref(norm), _stream_handle(stream)), self.lib)
+
     def update_state_host(self, series, step, time):
         h2d, d2h = C.c_int64(), C.c_int64()
         _abi.check(self.lib.coflux_update_state_host(self._ctx, C.byref(series), C.byref(step), float(time),

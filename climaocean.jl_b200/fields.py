@@ -148,6 +148,17 @@ class LatitudeLongitudeGrid:
         d = (self.z[1] - self.z[0]) / self.Nz
         return np.full(self.Nz + 2 * Hz, d, dtype=self.dtype)
 
+    def horizontal_areas(self, radius=6371e3):
+        """Az(j) of the (Center, Center) cells, R² Δλ (sin φ_{j+½} − sin φ_{j−½}), as a 1-D parent of Ny + 2Hy rows
+        (what Oceananigans' `Average(…, dims=(1,2))` weights a surface field with on a LatitudeLongitudeGrid)."""
+        Hy = self.halo[1]
+        P0, P1 = self.latitude
+        dphi = (P1 - P0) / self.Ny
+        j = np.arange(-Hy, self.Ny + Hy, dtype=np.float64)
+        south, north = np.deg2rad(P0 + j * dphi), np.deg2rad(P0 + (j + 1.0) * dphi)
+        dlam = np.deg2rad((self.longitude[1] - self.longitude[0]) / self.Nx)
+        return (radius ** 2 * dlam * (np.sin(north) - np.sin(south))).astype(self.dtype)
+
     def slab(self, rank, world_size):
         """Longitude slab of this grid owned by `rank`: Nx/P columns × full Ny."""
         assert self.Nx % world_size == 0, "Nx must divide evenly into longitude slabs"

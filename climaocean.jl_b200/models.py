@@ -474,3 +474,37 @@ def time_step(model, dt):
     model.clock.iteration += 1
     model.last_dt = dt
     update_state(model)
+
+
+class NormalizeSalinity:
+    """NormalizeSalinity(flux_field, additional_fluxes, additional_buffer, mean_total) — the callback of
+    /root/reference/src/OMIPConfigurations/omip_simulation.jl:187-220: at each call subtract the global (area-weighted)
+    mean of the combined surface salinity flux from the bulk-flux Field, over its whole parent, so that the global salt
+    budget integrates to zero.  `additional_fluxes`, when given, is a callable `(buffer_field, sim)` that materialises the
+    additional flux (e.g. a surface restoring) into `additional_buffer` — the reference's `_materialize_top_flux!` launch.
+    Multi-GPU: pass `dist`/`world`; the slabs' partial sums are all-reduced (climaocean.jl_b200/slabs.py)."""
+
+    def __init__(self, data, engine, additional_fluxes=None, dist=None, world=1):
+        self.data, self.engine = data, engine
+        self.flux_field = data.net["S"]
+        self.additional_fluxes = additional_fluxes
+        self.additional_buffer = None
+        if additional_fluxes is not None:
+            self.additional_buffer = self.flux_field.clone()
+            self.additional_buffer.data.zero_() if hasattr(self.additional_buffer.data, "zero_") else self.additional_buffer.data.fill(0)
+        self.dist, self.world = dist, world
+        self.mean_total = None          # device tensor (Σ f·Az, Σ Az) of the last call
+
+    def __call__(self, sim=None, stream=None):
+        from . import slabs
+        if self.additional_fluxes is not None:
+            self.additional_fluxes(self.additional_buffer, sim)
+        norm = self.data.salinity_normalization(self.additional_buffer)
+        self.mean_total = slabs.normalize_salinity_flux(self.engine, norm, self.dist, self.world, stream)
+        return None
+
+
+def salinity_normalizer(model, additional_fluxes=None, dist=None, world=1):
+    """salinity_normalizer(bc) of the reference (omip_simulation.jl:193-206), for a coupled model built here."""
+    itf = model.interfaces
+    return NormalizeSalinity(itf.data, itf.engine, additional_fluxes, dist, world)

@@ -63,3 +63,27 @@ def attach_seam(engine, dist, rank, world):
     handles = [bytes(p.cpu().tolist()) for p in parts]
     engine.seam_attach(handles[(rank - 1) % world], handles[(rank + 1) % world], rank, world)
     dist.barrier()
+
+
+def normalize_salinity_flux(engine, norm, dist=None, world=1, stream=None):
+    """NormalizeSalinity across longitude slabs (/root/reference/src/OMIPConfigurations/omip_simulation.jl:187-220):
+    every rank reduces its slab to (Σ f·Az, Σ Az) on the device, the two doubles are all-reduced (the one real collective
+    of this path: NCCL over NVLink for device tensors, gloo in the CPU tests), every rank subtracts the same mean.
+    Returns the device tensor holding the global sums."""
+    import torch
+    sums = torch.zeros(2, dtype=torch.float64, device=f"cuda:{torch.cuda.current_device()}")
+    engine.salinity_flux_sums(norm, sums.data_ptr(), stream)
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    engine.subtract_mean_flux(norm, sums.data_ptr(), stream)
+    return sums
+
+
+def combine_partial_sums(local_sums, dist=None, world=1):
+    """Host-side half of the above for backends without device tensors (gloo tests, the CPU oracle): all-reduce the
+    (Σ f·Az, Σ Az) pair and return the global mean."""
+    import torch
+    t = torch.tensor([float(local_sums[0]), float(local_sums[1])], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0] / t[1]) if float(t[1]) != 0.0 else 0.0

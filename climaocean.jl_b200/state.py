@@ -31,6 +31,7 @@ class SurfaceFluxData:
         self.fi = self.fj = None
         self.ocean = {}          # u v T S (3-D)
         self.dz = None           # 1-D Field (nk,1,1)
+        self.area = None         # 1-D Field (1,nj,1): horizontal cell areas Az(j) of the latitude–longitude grid
         self.mask = None
         self.ice = None          # dict or None
         self.exchange = {}
@@ -59,6 +60,7 @@ class SurfaceFluxData:
         for n in ("u", "v", "T", "S"):
             self.ocean[n] = Field(oc[n], grid.halo, "ocean_" + n)
         self.dz = Field(grid.dz().reshape(-1, 1, 1).copy(), (0, 0, grid.halo[2]), "dz")
+        self.area = Field(grid.horizontal_areas().reshape(1, -1, 1).copy(), (0, grid.halo[1], 0), "Az")
         if land_fraction > 0:
             self.mask = Field(synth.land_mask(grid, land_fraction), (grid.halo[0], grid.halo[1], 0), "mask")
         if with_ice:
@@ -87,6 +89,7 @@ class SurfaceFluxData:
         o.fi, o.fj = self.fi.to(device), self.fj.to(device)
         o.ocean = {n: f.to(device) for n, f in self.ocean.items()}
         o.dz = self.dz.to(device)
+        o.area = self.area.to(device) if self.area is not None else None
         o.mask = self.mask.to(device) if self.mask is not None else None
         o.ice = {n: f.to(device) for n, f in self.ice.items()} if self.ice is not None else None
         o.allocate_outputs()
@@ -192,6 +195,22 @@ class SurfaceFluxData:
         s = _abi.NetOceanFluxes()
         for n in NET_NAMES:
             setattr(s, n, arr(self.net[n]))
+        return s
+
+    def salinity_normalization(self, additional=None):
+        """coflux_salinity_normalization for NormalizeSalinity (omip_simulation.jl:187-220): the bulk salinity flux
+        net.S, an optional materialised additional flux, Az(j) (stride_i = 0) and the wet mask."""
+        s = _abi.SalinityNormalization()
+        s.flux = arr(self.net["S"])
+        s.additional = arr(additional)
+        a = self.area.array()
+        a.stride_i = 0
+        a.stride_j = 1
+        a.stride_k = 0
+        a.off_i = 0
+        s.area = a
+        s.mask = arr(self.mask)
+        self._keep_norm = (s, additional)
         return s
 
     def update_bundles(self, with_ice_terms=False):

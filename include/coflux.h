@@ -391,6 +391,30 @@ int coflux_update_state_host(coflux_ctx*, const coflux_atmos_series* atmosphere_
                              const coflux_host_step* step, double time,
                              int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ------------------------------------------------------------------------------------------------
+ * NormalizeSalinity — the per-step post-processing of the net salinity flux, SURVEY §8f row 4.
+ * Replaces /root/reference/src/OMIPConfigurations/omip_simulation.jl:187-220 (`NormalizeSalinity`,
+ * `salinity_normalizer`): `compute!(Field(Average(flux_field [+ additional_buffer], dims=(1,2))))`
+ * followed by `parent(flux_field) .-= mean_total` — the area-weighted global mean of the combined surface
+ * salinity flux is removed from the bulk-flux field over its WHOLE parent (halos included), so that the
+ * global salt budget integrates to zero.  Immersed (masked) cells do not enter the average.
+ * Multi-GPU: every slab computes its partial sums, the host all-reduces the two doubles (NCCL through
+ * torch.distributed / MPI — the one real collective of this path), every slab subtracts the same mean.
+ * The reduction is a fixed-order tree: bit-reproducible from run to run.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct coflux_salinity_normalization {
+  coflux_array flux;          /* bulk salinity flux field (= net_fluxes.ocean.S), corrected in place          */
+  coflux_array additional;    /* materialised additional flux (`additional_buffer`); ptr NULL: none           */
+  coflux_array area;          /* horizontal cell areas Az [m²]; stride_i = 0 on a latitude–longitude grid     */
+  coflux_array mask;          /* uint8, 1 = wet; ptr NULL: every cell is averaged                             */
+} coflux_salinity_normalization;
+/* device_sums[0] = Σ (flux + additional)·Az, device_sums[1] = Σ Az over this slab's wet interior cells       */
+int coflux_salinity_flux_sums(coflux_ctx*, const coflux_salinity_normalization*, double* device_sums, void* cu_stream);
+/* parent(flux) .-= device_sums[0] / device_sums[1]                                                           */
+int coflux_subtract_mean_flux(coflux_ctx*, const coflux_salinity_normalization*, const double* device_sums, void* cu_stream);
+/* single slab: both of the above (3 launches)                                                                */
+int coflux_normalize_salinity_flux(coflux_ctx*, const coflux_salinity_normalization*, void* cu_stream);
+
 /* Diagnostics */
 int coflux_launch_count(coflux_ctx*, int64_t* launches);   /* kernels launched through this context  */
 /* Per-kernel device timing of coflux_update_state: when enabled, CUDA events are recorded on the

@@ -761,6 +761,34 @@ int SUF(oracle_update_state)(const coflux_config* cfg, const coflux_update_input
 }
 
 /* scalar probes for unit tests */
+/* NormalizeSalinity — restatement of /root/reference/src/OMIPConfigurations/omip_simulation.jl:187-220:
+ *   compute!(mean_total)                        mean_total = Field(Average(flux_field [+ additional_buffer], dims=(1,2)))
+ *   parent(n.flux_field) .-= n.mean_total       (whole parent, halos included)
+ * Oceananigans' Average over (1,2) of a (Center, Center, Nothing) field is ∫ f dA / ∫ dA over the wet interior.
+ * Sums in long double, serial order (the checker does not care about speed here).  sums_out (may be NULL)
+ * receives {Σ f·Az, Σ Az}; when `mean_in` is non-NULL that mean is subtracted instead of the local one
+ * (multi-slab case: the caller combines the slabs' sums). */
+int SUF(oracle_normalize_salinity_flux)(const coflux_config* cfg, const coflux_salinity_normalization* n, double* sums_out,
+                                        const double* mean_in) {
+  const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny;
+  long double num = 0.0L, den = 0.0L;
+  for (int j = 0; j < Ny; ++j)
+    for (int i = 0; i < Nx; ++i) {
+      if (!SUF(active)(&n->mask, i, j)) continue;
+      long double f = (long double)SUF(ld)(&n->flux, i, j, 0, 0);
+      if (n->additional.ptr) f += (long double)SUF(ld)(&n->additional, i, j, 0, 0);
+      const long double A = (long double)SUF(ld)(&n->area, i, j, 0, 0);
+      num += f * A;
+      den += A;
+    }
+  if (sums_out) { sums_out[0] = (double)num; sums_out[1] = (double)den; }
+  const FT mean = mean_in ? (FT)*mean_in : ((den != 0.0L) ? (FT)(double)(num / den) : (FT)0);
+  const int Hi = n->flux.off_i, Hj = n->flux.off_j;
+  for (int j = -Hj; j < Ny + Hj; ++j)
+    for (int i = -Hi; i < Nx + Hi; ++i) SUF(st)(&n->flux, i, j, 0, SUF(ld)(&n->flux, i, j, 0, 0) - mean);
+  return 0;
+}
+
 void SUF(oracle_probe_psi)(int kind, int n, const FT* zeta, FT* psi_m, FT* psi_s) {
   for (int k = 0; k < n; ++k) { psi_m[k] = SUF(psi_momentum)(kind, zeta[k]); psi_s[k] = SUF(psi_scalar)(kind, zeta[k]); }
 }

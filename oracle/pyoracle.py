@@ -67,6 +67,17 @@ def update_state(cfg, inputs, outputs, time):
     assert f(C.byref(cfg), C.byref(inputs), C.byref(outputs), float(time)) == 0
 
 
+def normalize_salinity_flux(cfg, norm, mean=None):
+    """NormalizeSalinity (omip_simulation.jl:187-220) on host arrays; returns (Σ f·Az, Σ Az).  `mean`: subtract this
+    value instead of the local mean (multi-slab)."""
+    f = fn("oracle_normalize_salinity_flux", cfg)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sums = (C.c_double * 2)()
+    m = C.c_double(mean) if mean is not None else None
+    assert f(C.byref(cfg), C.byref(norm), sums, C.byref(m) if m is not None else None) == 0
+    return sums[0], sums[1]
+
+
 def set_threads(n):
     """Limit / set OpenMP threads of the oracle through libgomp's omp_set_num_threads."""
     gomp = C.CDLL("libgomp.so.1")

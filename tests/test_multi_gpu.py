@@ -111,3 +111,69 @@ def test_single_context_can_attach_to_itself():
     for k in ("net.u", "net.T", "net.S", "ao.x_momentum"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
     assert np.array_equal(outs[0]["net.v"][1:], outs[1]["net.v"][1:])
+
+
+def _norm_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    import climaocean.jl_b200 as cj
+    from climaocean.jl_b200 import slabs
+    from tests.common import QUERY_TIME
+    full = cj.LatitudeLongitudeGrid((256, 96, 4), latitude=(-60.0, 60.0), halo=(4, 4, 2))
+    grid = full.slab(rank, world)
+    host = cj.SurfaceFluxData.synthetic(grid, ring=1)
+    dev = host.to(f"cuda:{rank}")
+    cfg = cj.default_config(grid.Nx, grid.Ny, 4, 64)
+    cfg.device = rank
+    cfg.grid.ring = 1
+    cfg.grid.periodic_x = 0
+    eng = cj.Engine(cfg)
+    inp, out = dev.update_bundles()
+    eng.update_state(inp, out, QUERY_TIME)
+    sums = slabs.normalize_salinity_flux(eng, dev.salinity_normalization(), dist, world)   # NCCL all-reduce of 2 doubles
+    torch.cuda.synchronize()
+    res = slabs.gather_interior(dev.net["S"], dist, world)
+    if rank == 0:
+        q.put((res, sums.cpu().numpy()))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_salinity_normalization_across_slabs_nccl():
+    """NormalizeSalinity (omip_simulation.jl:187-220) on ≥ 2 slabs: partial sums per GPU, NCCL all-reduce, the same global
+    mean subtracted everywhere — equal to the single-GPU result up to the summation order of the slabs."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import climaocean.jl_b200 as cj
+    from tests.common import QUERY_TIME
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_norm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res, sums = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    full = cj.LatitudeLongitudeGrid((256, 96, 4), latitude=(-60.0, 60.0), halo=(4, 4, 2))
+    host = cj.SurfaceFluxData.synthetic(full, ring=1)
+    dev = host.to("cuda:0")
+    cfg = cj.default_config(256, 96, 4, 64)
+    eng = cj.Engine(cfg)
+    inp, out = dev.update_bundles()
+    eng.update_state(inp, out, QUERY_TIME)
+    eng.normalize_salinity_flux(dev.salinity_normalization())
+    torch.cuda.synchronize()
+    ref = dev.outputs()["net.S"]
+    assert np.max(np.abs(res - ref)) <= 1e-15 * np.max(np.abs(ref))
+    eng.close()
