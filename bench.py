@@ -359,6 +359,22 @@ def main():
         extras["quarter_degree_1440x600x10_f64"] = {"value": QNX * QNY / (mq * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": mq,
                                                     "flux_kernel_ms": fq, "stress_kernel_ms": sq}
         eq.close(); del dq, hq
+        # NormalizeSalinity (omip_simulation.jl:187-220) on the net salinity flux of the headline run: HBM bound, the
+        # flux plane is read twice (sums, subtraction) and written once = 3 words per cell
+        st0 = torch.cuda.current_stream()
+        norm = dev.salinity_normalization()
+        tn = []
+        for k in range(8):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(st0); eng.normalize_salinity_flux(norm, st0); b_.record(st0)
+            torch.cuda.synchronize()
+            if k >= 3:
+                tn.append(a_.elapsed_time(b_))
+        tnm = float(np.mean(tn))
+        extras["normalize_salinity_f64"] = {"ms": tnm, "launches": 3, "algorithmic_bytes_per_cell": 24,
+                                            "achieved_GBs": cells_global * 24 / (tnm * 1e-3) / 1e9,
+                                            "roofline_frac": cells_global * 24 / (tnm * 1e-3) / 1e9 / peak,
+                                            "note": "63 MB plane: the second read and the write-back hit the 126 MB L2"}
         # sea-ice–ocean kernel (HBM bound: 2·Nz + 13 words per column), 1/12°, Nz = 75
         gi = cj.LatitudeLongitudeGrid((NX, NY, 1), latitude=(-75.0, 75.0), halo=(7, 7, 0))
         hi = cj.SurfaceFluxData.synthetic(gi, with_ice=True)

@@ -169,4 +169,25 @@ function update_state!(model::OceanSeaIceModel)
     return invoke(update_state!, Tuple{Any}, model)     # the stock NumericalEarth method
 end
 
+# NormalizeSalinity (src/OMIPConfigurations/omip_simulation.jl:187-220) through coflux: the callable keeps its
+# fields; only `compute!(mean_total)` + `parent(flux_field) .-= mean_total` are replaced.  UNEXECUTED like the rest.
+struct SalinityNormalization; flux::CofluxArray; additional::CofluxArray; area::CofluxArray; mask::CofluxArray; end
+
+function normalize_salinity!(n, sim; area::CofluxArray, mask::CofluxArray = NULL_ARRAY)
+    model = sim.model.ocean.model
+    ctx = CONTEXTS[sim.model][1]            # created by the first coflux_update_state!(model)
+    if !isnothing(n.additional_fluxes)      # stock materialisation of the additional flux (omip_simulation.jl:210-216)
+        grid = model.grid
+        fields = merge(model.velocities, model.tracers)
+        launch!(architecture(grid), grid, :xy, ClimaOcean.OMIPConfigurations._materialize_top_flux!,
+                n.additional_buffer, n.additional_fluxes, grid, model.clock, fields)
+    end
+    add = isnothing(n.additional_buffer) ? NULL_ARRAY : CofluxArray(n.additional_buffer)
+    norm = Ref(SalinityNormalization(CofluxArray(n.flux_field), add, area, mask))
+    check(ccall((:coflux_normalize_salinity_flux, libcoflux), Cint, (Ptr{Cvoid}, Ref{SalinityNormalization}, Ptr{Cvoid}),
+                ctx.handle, norm, Ptr{Cvoid}(UInt(CUDA.stream().handle))))
+    # distributed: coflux_salinity_flux_sums → MPI.Allreduce!(sums, +, comm) → coflux_subtract_mean_flux
+    return nothing
+end
+
 end # module
