@@ -371,10 +371,24 @@ def main():
             if k >= 3:
                 tn.append(a_.elapsed_time(b_))
         tnm = float(np.mean(tn))
-        extras["normalize_salinity_f64"] = {"ms": tnm, "launches": 3, "algorithmic_bytes_per_cell": 24,
+        extras["normalize_salinity_f64"] = {"ms": tnm, "launches": 2, "algorithmic_bytes_per_cell": 24,
                                             "achieved_GBs": cells_global * 24 / (tnm * 1e-3) / 1e9,
                                             "roofline_frac": cells_global * 24 / (tnm * 1e-3) / 1e9 / peak,
-                                            "note": "63 MB plane: the second read and the write-back hit the 126 MB L2"}
+                                            "note": "two ~25 us kernels: launch ramps are a third of the time"}
+        # closure surface-forcing front ends (KPP u★, Bo; NEMO-TKE u★², e_surf): stand-alone kernel, 6 reads + 4 writes per cell
+        cf = dev.closure_forcing()
+        netb = dev.net_ocean_fluxes()
+        tc = []
+        for k in range(8):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(st0); eng.closure_surface_forcing(netb, cf, st0); b_.record(st0)
+            torch.cuda.synchronize()
+            if k >= 3:
+                tc.append(a_.elapsed_time(b_))
+        tcm = float(np.mean(tc))
+        extras["closure_surface_forcing_f64"] = {"ms": tcm, "algorithmic_bytes_per_cell": 80,
+                                                 "achieved_GBs": cells_global * 80 / (tcm * 1e-3) / 1e9,
+                                                 "roofline_frac": cells_global * 80 / (tcm * 1e-3) / 1e9 / peak}
         # sea-ice–ocean kernel (HBM bound: 2·Nz + 13 words per column), 1/12°, Nz = 75
         gi = cj.LatitudeLongitudeGrid((NX, NY, 1), latitude=(-75.0, 75.0), halo=(7, 7, 0))
         hi = cj.SurfaceFluxData.synthetic(gi, with_ice=True)

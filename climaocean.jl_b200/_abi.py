@@ -164,6 +164,12 @@ class HostStep(C.Structure):
                                           "net_S", "latent_heat", "sensible_heat")] + [("halo", i32), ("reserved", i32)]
 
 
+class ClosureForcing(C.Structure):
+    _fields_ = [("thermal_expansion", Array), ("haline_contraction", Array), ("friction_velocity", Array),
+                ("friction_velocity_squared", Array), ("surface_tke", Array), ("buoyancy_flux", Array),
+                ("minimum_friction_velocity", f64), ("minimum_surface_tke", f64), ("Cb", f64), ("gravitational_acceleration", f64)]
+
+
 class SalinityNormalization(C.Structure):
     _fields_ = [("flux", Array), ("additional", Array), ("area", Array), ("mask", Array)]
 
@@ -176,7 +182,7 @@ STRUCTS = {"array": Array, "air_viscosity": AirViscosity, "momentum_roughness": 
            "ocean_surface": OceanSurface, "interface_fluxes": InterfaceFluxes, "sea_ice_state": SeaIceState,
            "ocean_columns": OceanColumns, "ice_ocean_fluxes": IceOceanFluxes, "net_ocean_fluxes": NetOceanFluxes,
            "update_inputs": UpdateInputs, "update_outputs": UpdateOutputs, "host_step": HostStep,
-           "salinity_normalization": SalinityNormalization}
+           "salinity_normalization": SalinityNormalization, "closure_forcing": ClosureForcing}
 
 # every symbol include/coflux.h declares
 EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "coflux_sizeof", "coflux_default_config",
@@ -184,7 +190,8 @@ EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "cofl
            "coflux_interpolate_atmosphere", "coflux_atmosphere_ocean_fluxes", "coflux_atmosphere_sea_ice_fluxes",
            "coflux_sea_ice_ocean_fluxes", "coflux_assemble_net_ocean_fluxes", "coflux_update_state",
            "coflux_update_state_host", "coflux_launch_count", "coflux_profile_enable", "coflux_profile_read", "coflux_seam_export", "coflux_seam_attach",
-           "coflux_seam_detach", "coflux_salinity_flux_sums", "coflux_subtract_mean_flux", "coflux_normalize_salinity_flux")
+           "coflux_seam_detach", "coflux_salinity_flux_sums", "coflux_subtract_mean_flux", "coflux_normalize_salinity_flux",
+           "coflux_closure_surface_forcing", "coflux_attach_closure_forcing")
 
 
 class CofluxError(RuntimeError):
@@ -236,6 +243,8 @@ def load_library(path=None):
     lib.coflux_salinity_flux_sums.argtypes = [vp, P(SalinityNormalization), vp, vp]
     lib.coflux_subtract_mean_flux.argtypes = [vp, P(SalinityNormalization), vp, vp]
     lib.coflux_normalize_salinity_flux.argtypes = [vp, P(SalinityNormalization), vp]
+    lib.coflux_closure_surface_forcing.argtypes = [vp, P(NetOceanFluxes), P(ClosureForcing), vp]
+    lib.coflux_attach_closure_forcing.argtypes = [vp, P(ClosureForcing)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("coflux_abi_version", "coflux_sizeof"):

@@ -50,7 +50,7 @@ extern "C" int coflux_sizeof(const char* name) {
   SZ(array); SZ(air_viscosity); SZ(momentum_roughness); SZ(scalar_roughness); SZ(flux_params); SZ(thermodynamics);
   SZ(atmosphere_properties); SZ(ocean_properties); SZ(radiation_properties); SZ(ice_ocean_params); SZ(grid_desc);
   SZ(config); SZ(atmos_series); SZ(exchange_state); SZ(ocean_surface); SZ(interface_fluxes); SZ(sea_ice_state);
-  SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step); SZ(salinity_normalization);
+  SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step); SZ(salinity_normalization); SZ(closure_forcing);
 #undef SZ
   return -1;
 }
@@ -97,8 +97,10 @@ struct Profile {
   double flux_ms = 0, stress_ms = 0;
   long long calls = 0;
 };
-static const int SALT_BLOCKS = 148 * 4;   // CTAs of the salinity-flux reduction (fixed: the summation order must not depend on the grid size)
+static const int SALT_BLOCKS = 148 * 8;   // CTAs of the salinity-flux reduction (fixed: the summation order must not depend on the grid size)
 struct coflux_ctx {
+  bool closure_on = false;               // coflux_attach_closure_forcing: by-products emitted by the stress kernel
+  coflux_closure_forcing closure;
   double* salt_ws = nullptr;             // [2 * SALT_BLOCKS] CTA partials + [2] totals of the salinity-flux reduction
   coflux_config cfg;
   Profile prof;
@@ -886,6 +888,16 @@ extern "C" int coflux_sea_ice_ocean_fluxes(coflux_ctx* c, coflux_ocean_columns* 
 // a9
 // ---------------------------------------------------------------------------------------------
 template <typename FT>
+static void fill_closure(const coflux_closure_forcing& f, const coflux_net_ocean_fluxes* net, ClosureArgs<FT>& k) {
+  const size_t es = sizeof(FT);
+  k.on = 1;
+  k.JT = view2d(net->T, 0, es); k.JS = view2d(net->S, 0, es);
+  k.alpha = view2d(f.thermal_expansion, 0, es); k.beta = view2d(f.haline_contraction, 0, es);
+  k.ustar = view2d(f.friction_velocity, 0, es); k.ustar2 = view2d(f.friction_velocity_squared, 0, es);
+  k.tke = view2d(f.surface_tke, 0, es); k.Bo = view2d(f.buoyancy_flux, 0, es);
+  k.umin = (FT)f.minimum_friction_velocity; k.emin = (FT)f.minimum_surface_tke; k.Cb = (FT)f.Cb; k.g = (FT)f.gravitational_acceleration;
+}
+template <typename FT>
 static void fill_stress(const coflux_ctx* c, const coflux_ocean_surface* o, const coflux_interface_fluxes* ao,
                         const coflux_sea_ice_state* ice, const coflux_ice_ocean_fluxes* io, coflux_net_ocean_fluxes* out,
                         StressArgs<FT>& s) {
@@ -902,6 +914,7 @@ static void fill_stress(const coflux_ctx* c, const coflux_ocean_surface* o, cons
   s.seam_west = nullptr;
   s.rho0 = dev_params<FT>(c).rho0;
   s.cell0 = 0; s.cell1 = (long long)g.Nx * g.Ny;
+  if (c->closure_on) fill_closure<FT>(c->closure, out, s.closure);
 }
 template <typename FT>
 static int do_assemble(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, const coflux_interface_fluxes* ao,
@@ -1170,6 +1183,44 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
 }
 
 // ---------------------------------------------------------------------------------------------
+// closure surface-forcing front ends (KPP/kpp_surface_forcing.jl, NEMOTKE/nemo_tke_surface_forcing.jl)
+// ---------------------------------------------------------------------------------------------
+static int check_closure(const coflux_closure_forcing* f) {
+  REQUIRE(std::isfinite(f->minimum_friction_velocity) && std::isfinite(f->minimum_surface_tke) && std::isfinite(f->Cb) &&
+          std::isfinite(f->gravitational_acceleration), "closure forcing parameters must be finite");
+  return COFLUX_OK;
+}
+extern "C" int coflux_attach_closure_forcing(coflux_ctx* c, const coflux_closure_forcing* f) {
+  REQUIRE(c, "NULL context");
+  if (!f) { c->closure_on = false; return COFLUX_OK; }
+  int rc = check_closure(f);
+  if (rc) return rc;
+  c->closure = *f;
+  c->closure_on = true;
+  return COFLUX_OK;
+}
+template <typename FT>
+static int do_closure(coflux_ctx* c, const coflux_net_ocean_fluxes* net, const coflux_closure_forcing* f, cudaStream_t st) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  ClosureKernelArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.Nx = g.Nx; a.Ny = g.Ny;
+  a.taux = view2d(net->u, 0, sizeof(FT)); a.tauy = view2d(net->v, 0, sizeof(FT));
+  fill_closure<FT>(*f, net, a.closure);
+  closure_forcing_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_closure_surface_forcing(coflux_ctx* c, const coflux_net_ocean_fluxes* net, const coflux_closure_forcing* f, void* stream) {
+  REQUIRE(c && net && f, "NULL argument");
+  REQUIRE(net->u.ptr && net->v.ptr, "net momentum fluxes are required");
+  int rc = check_closure(f);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_closure<double>(c, net, f, st) : do_closure<float>(c, net, f, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // NormalizeSalinity (omip_simulation.jl:187-220)
 // ---------------------------------------------------------------------------------------------
 static int salt_workspace(coflux_ctx* c) {
@@ -1187,6 +1238,7 @@ static int do_salt_sums(coflux_ctx* c, const coflux_salinity_normalization* n, d
   a.mask = view2d(n->mask, 0, 1);
   a.partial = c->salt_ws;
   salt_sums_kernel<FT><<<SALT_BLOCKS, 256, 0, st>>>(a);
+  if (!sums) return check_launch(c, 1);                 // single-slab form: the subtraction reduces the partials itself
   salt_sums_final_kernel<<<1, 32, 0, st>>>(c->salt_ws, SALT_BLOCKS, sums);
   return check_launch(c, 2);
 }
@@ -1197,7 +1249,8 @@ static int do_subtract_mean(coflux_ctx* c, const coflux_salinity_normalization* 
   a.p = static_cast<char*>(n->flux.ptr) + (int64_t)n->flux.off_k * n->flux.stride_k * (int64_t)sizeof(FT);
   a.si = n->flux.stride_i; a.sj = n->flux.stride_j;
   a.ni = g.Nx + 2 * n->flux.off_i; a.nj = g.Ny + 2 * n->flux.off_j;
-  a.sums = sums;
+  a.sums = sums ? sums : c->salt_ws;
+  a.nblocks = sums ? 0 : SALT_BLOCKS;
   const long long cells = (long long)a.ni * a.nj;
   const unsigned grid = (unsigned)std::min<long long>((cells + 255) / 256, 148LL * 8);
   subtract_mean_kernel<FT><<<grid, 256, 0, st>>>(a);
@@ -1233,10 +1286,10 @@ extern "C" int coflux_normalize_salinity_flux(coflux_ctx* c, const coflux_salini
   CUDA_TRY(cudaSetDevice(c->device));
   rc = salt_workspace(c);
   if (rc) return rc;
-  double* sums = c->salt_ws + 2 * SALT_BLOCKS;
-  rc = coflux_salinity_flux_sums(c, n, sums, stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = c->cfg.dtype == COFLUX_F64 ? do_salt_sums<double>(c, n, nullptr, st) : do_salt_sums<float>(c, n, nullptr, st);
   if (rc) return rc;
-  return coflux_subtract_mean_flux(c, n, sums, stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_subtract_mean<double>(c, n, nullptr, st) : do_subtract_mean<float>(c, n, nullptr, st);
 }
 
 // ---------------------------------------------------------------------------------------------

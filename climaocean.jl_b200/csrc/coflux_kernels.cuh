@@ -224,6 +224,26 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
 // ---------------------------------------------------------------------------------------------
 // centre → face momentum fluxes (A9)
 // ---------------------------------------------------------------------------------------------
+// by-products of the net fluxes for the ocean mixing closures (KPP/kpp_surface_forcing.jl:18-29,
+// NEMOTKE/nemo_tke_surface_forcing.jl:14-22); all pointers optional
+template <typename FT> struct ClosureArgs {
+  int on;
+  DArr JT, JS, alpha, beta;
+  DArr ustar, ustar2, tke, Bo;
+  FT umin, emin, Cb, g;
+};
+template <typename FT>
+__device__ __forceinline__ void closure_forcing(const ClosureArgs<FT>& c, int i, int j, FT tx, FT ty) {
+  const FT ustar2 = M<FT>::sqrt(tx * tx + ty * ty);                 // u★² = |τ| (kinematic stress)
+  stg<FT>(c.ustar2, i, j, ustar2);
+  stg<FT>(c.ustar, i, j, M<FT>::max(M<FT>::sqrt(ustar2), c.umin));   // max(√√(τx²+τy²), u★_min)
+  stg<FT>(c.tke, i, j, M<FT>::max(c.emin, c.Cb * ustar2));
+  if (c.Bo.p && c.alpha.p && c.beta.p && c.JT.p && c.JS.p) {
+    const FT JT = ldg<FT>(c.JT, i, j), JS = ldg<FT>(c.JS, i, j);
+    stg<FT>(c.Bo, i, j, -(c.g * (ldg<FT>(c.alpha, i, j) * JT - ldg<FT>(c.beta, i, j) * JS)));
+  }
+}
+
 template <typename FT> struct StressArgs {
   int Nx, Ny, wrap_x;      // wrap_x: i-1 at i == 0 → Nx-1 (single-slab periodic, ring == 0)
   long long cell0, cell1;  // linear interior cell range [cell0, cell1) handled by this launch
@@ -231,6 +251,7 @@ template <typename FT> struct StressArgs {
   DArr taux, tauy;
   const char* seam_west;   // ρτx of the west neighbour's last column (Ny elements), or nullptr
   FT rho0;
+  ClosureArgs<FT> closure;
 };
 template <typename FT>
 __device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, int j, FT& tx, FT& ty) {
@@ -263,6 +284,19 @@ template <typename FT> __global__ void __launch_bounds__(256) stress_kernel(cons
   assemble_stress<FT>(a, i, j, tx, ty);
   stg<FT>(a.taux, i, j, tx);
   stg<FT>(a.tauy, i, j, ty);
+  if (a.closure.on) closure_forcing<FT>(a.closure, i, j, tx, ty);
+}
+// stand-alone closure front end: τx, τy read back from the net fluxes
+template <typename FT> struct ClosureKernelArgs {
+  int Nx, Ny;
+  DArr taux, tauy;
+  ClosureArgs<FT> closure;
+};
+template <typename FT> __global__ void __launch_bounds__(256) closure_forcing_kernel(const __grid_constant__ ClosureKernelArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.Nx * a.Ny) return;
+  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  closure_forcing<FT>(a.closure, i, j, ldg<FT>(a.taux, i, j), ldg<FT>(a.tauy, i, j));
 }
 
 // stand-alone compute_net_ocean_fluxes! (reads the interface fluxes back from memory)
@@ -428,15 +462,29 @@ template <typename FT> struct SaltSumArgs {
 };
 template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(const __grid_constant__ SaltSumArgs<FT> a) {
   const long long n = (long long)a.Nx * a.Ny;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   double num = 0.0, den = 0.0;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
-    if (!is_active(a.mask, i, j)) continue;
-    double f = (double)ldg<FT>(a.flux, i, j);
-    if (a.add.p) f += (double)ldg<FT>(a.add, i, j);
-    const double A = (double)ldg<FT>(a.area, i, j);
-    num = fma(f, A, num);
-    den += A;
+  // 4 independent loads in flight per thread; the order in which a thread adds its elements is fixed, so the
+  // result stays bit-reproducible
+  // (i, j) advance incrementally — a 64-bit division per element would make this streaming kernel compute bound
+  const int di = (int)(stride % a.Nx), dj = (int)(stride / a.Nx);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  while (idx < n) {
+    double f[4], A[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      f[u] = 0.0; A[u] = 0.0;
+      if (idx < n && is_active(a.mask, i, j)) {
+        f[u] = (double)ldg<FT>(a.flux, i, j);
+        if (a.add.p) f[u] += (double)ldg<FT>(a.add, i, j);
+        A[u] = (double)ldg<FT>(a.area, i, j);
+      }
+      idx += stride; i += di; j += dj;
+      if (i >= a.Nx) { i -= a.Nx; ++j; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { num = fma(f[u], A[u], num); den += A[u]; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
@@ -449,28 +497,60 @@ template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(c
     a.partial[2 * blockIdx.x] = tn; a.partial[2 * blockIdx.x + 1] = td;
   }
 }
-__global__ void __launch_bounds__(32) salt_sums_final_kernel(const double* partial, int nblocks, double* sums) {
-  // one warp, fixed order: lane l adds partials l, l+32, …; then a shuffle tree
-  double num = 0.0, den = 0.0;
-  for (int b = threadIdx.x; b < nblocks; b += 32) { num += partial[2 * b]; den += partial[2 * b + 1]; }
+// one warp, fixed order: lane l adds partials l, l+32, …; then a shuffle tree
+__device__ __forceinline__ void salt_reduce_partials(const double* partial, int nblocks, double& num, double& den) {
+  num = 0.0; den = 0.0;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) { num += partial[2 * b]; den += partial[2 * b + 1]; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
+}
+__global__ void __launch_bounds__(32) salt_sums_final_kernel(const double* partial, int nblocks, double* sums) {
+  double num, den;
+  salt_reduce_partials(partial, nblocks, num, den);
   if (threadIdx.x == 0) { sums[0] = num; sums[1] = den; }
 }
 template <typename FT> struct SubMeanArgs {
   char* p;              // first element of the parent
   int64_t si, sj;
   int ni, nj;           // parent extents (interior + 2 halos)
-  const double* sums;
+  const double* sums;   // {Σ f·Az, Σ Az}, or (nblocks > 0) the CTA partials of salt_sums_kernel
+  int nblocks;
 };
 template <typename FT> __global__ void __launch_bounds__(256) subtract_mean_kernel(const __grid_constant__ SubMeanArgs<FT> a) {
-  const double den = a.sums[1];
-  const FT mean = (den != 0.0) ? (FT)(a.sums[0] / den) : FT(0);
+  __shared__ double tot[2];
+  if (a.nblocks > 0) {                 // single-slab form: every CTA reduces the partials itself (same order as the
+    if (threadIdx.x < 32) {            // final kernel → same bits), which saves a launch
+      double num, den;
+      salt_reduce_partials(a.sums, a.nblocks, num, den);
+      if (threadIdx.x == 0) { tot[0] = num; tot[1] = den; }
+    }
+    __syncthreads();
+  } else if (threadIdx.x == 0) {
+    tot[0] = a.sums[0]; tot[1] = a.sums[1];
+  }
+  if (a.nblocks <= 0) __syncthreads();
+  const double den = tot[1];
+  const FT mean = (den != 0.0) ? (FT)(tot[0] / den) : FT(0);
   const long long n = (long long)a.ni * a.nj;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx / a.ni), i = (int)(idx - (long long)j * a.ni);
-    FT* q = reinterpret_cast<FT*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj);
-    *q -= mean;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int di = (int)(stride % a.ni), dj = (int)(stride / a.ni);
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int j = (int)(idx / a.ni), i = (int)(idx - (long long)j * a.ni);
+  while (idx < n) {
+    FT v[4];
+    FT* q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      q[u] = nullptr;
+      if (idx < n) {
+        q[u] = reinterpret_cast<FT*>(a.p) + ((int64_t)i * a.si + (int64_t)j * a.sj);
+        v[u] = *q[u];
+      }
+      idx += stride; i += di; j += dj;
+      if (i >= a.ni) { i -= a.ni; ++j; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (q[u]) *q[u] = v[u] - mean;
   }
 }
 

@@ -89,6 +89,15 @@ class Engine:
         _abi.check(self.lib.coflux_update_state(self._ctx, C.byref(inputs), C.byref(outputs), float(time),
                                                 _stream_handle(stream)), self.lib)
 
+    # --- closure surface-forcing front ends (KPP/kpp_surface_forcing.jl, NEMOTKE/nemo_tke_surface_forcing.jl) ---
+    def closure_surface_forcing(self, net, forcing, stream=None):
+        _abi.check(self.lib.coflux_closure_surface_forcing(self._ctx, C.byref(net), C.byref(forcing), _stream_handle(stream)), self.lib)
+
+    def attach_closure_forcing(self, forcing):
+        """Every following update_state emits the closure by-products from the stress kernel; None detaches."""
+        self._closure_keep = forcing
+        _abi.check(self.lib.coflux_attach_closure_forcing(self._ctx, C.byref(forcing) if forcing is not None else None), self.lib)
+
     # --- NormalizeSalinity (omip_simulation.jl:187-220) ---
     def salinity_flux_sums(self, norm, device_sums_ptr, stream=None):
         _abi.check(self.lib.coflux_salinity_flux_sums(self._ctx, C.byref(norm), device_sums_ptr, _stream_handle(stream)), self.lib)

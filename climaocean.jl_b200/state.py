@@ -93,6 +93,8 @@ class SurfaceFluxData:
         o.mask = self.mask.to(device) if self.mask is not None else None
         o.ice = {n: f.to(device) for n, f in self.ice.items()} if self.ice is not None else None
         o.allocate_outputs()
+        if getattr(self, "eos", None):
+            o.eos = {k: f.to(device) for k, f in self.eos.items()}
         return o
 
     def to_device_columns(self, device, Nz, Hz=7, fill_columns=False):
@@ -196,6 +198,33 @@ class SurfaceFluxData:
         for n in NET_NAMES:
             setattr(s, n, arr(self.net[n]))
         return s
+
+    def closure_forcing(self, minimum_friction_velocity=1e-6, minimum_surface_tke=1e-4, Cb=3.75, gravitational_acceleration=9.80665,
+                        with_buoyancy=True):
+        """coflux_closure_forcing with freshly allocated output Fields (self.closure) and synthetic α, β of the surface cell
+        (defaults: kpp_parameters.jl:98, nemo_tke_parameters.jl:45,54)."""
+        g = self.grid
+        h2, size2 = (g.halo[0], g.halo[1], 0), (g.Nx, g.Ny, 1)
+        if not getattr(self, "closure", None):
+            self.closure = {n: Field.zeros(size2, h2, self.dtype, self.device, "closure_" + n)
+                            for n in ("friction_velocity", "friction_velocity_squared", "surface_tke", "buoyancy_flux")}
+        if with_buoyancy and not getattr(self, "eos", None):
+            T = self.ocean["T"].numpy()[-1 - self.ocean["T"].halo[2]] if self.ocean["T"].data.shape[0] > 1 else self.ocean["T"].numpy()[0]
+            # smooth stand-ins for α(T), β: the EOS itself belongs to the host ocean model
+            alpha = (5e-5 + 1.1e-5 * np.clip(T, -2.0, 32.0)).astype(self.dtype)[None]
+            beta = np.full_like(alpha, 7.6e-4)
+            self.eos = {"alpha": Field.from_numpy(alpha, (self.ocean["T"].halo[0], self.ocean["T"].halo[1], 0), self.device, "alpha"),
+                        "beta": Field.from_numpy(beta, (self.ocean["T"].halo[0], self.ocean["T"].halo[1], 0), self.device, "beta")}
+        f = _abi.ClosureForcing()
+        f.thermal_expansion = arr(self.eos["alpha"]) if with_buoyancy else arr(None)
+        f.haline_contraction = arr(self.eos["beta"]) if with_buoyancy else arr(None)
+        f.friction_velocity = arr(self.closure["friction_velocity"])
+        f.friction_velocity_squared = arr(self.closure["friction_velocity_squared"])
+        f.surface_tke = arr(self.closure["surface_tke"])
+        f.buoyancy_flux = arr(self.closure["buoyancy_flux"]) if with_buoyancy else arr(None)
+        f.minimum_friction_velocity, f.minimum_surface_tke = minimum_friction_velocity, minimum_surface_tke
+        f.Cb, f.gravitational_acceleration = Cb, gravitational_acceleration
+        return f
 
     def salinity_normalization(self, additional=None):
         """coflux_salinity_normalization for NormalizeSalinity (omip_simulation.jl:187-220): the bulk salinity flux

@@ -412,8 +412,36 @@ typedef struct coflux_salinity_normalization {
 int coflux_salinity_flux_sums(coflux_ctx*, const coflux_salinity_normalization*, double* device_sums, void* cu_stream);
 /* parent(flux) .-= device_sums[0] / device_sums[1]                                                           */
 int coflux_subtract_mean_flux(coflux_ctx*, const coflux_salinity_normalization*, const double* device_sums, void* cu_stream);
-/* single slab: both of the above (3 launches)                                                                */
+/* single slab: both of the above in 2 launches (the subtraction reduces the CTA partials itself)              */
 int coflux_normalize_salinity_flux(coflux_ctx*, const coflux_salinity_normalization*, void* cu_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Surface-forcing front ends of the ocean vertical-mixing closures — the immediate consumers of the net
+ * fluxes inside the ocean step.  Each is a by-product of net_fluxes.ocean.{u,v,T,S} at the
+ * SAME (i, j) (the reference indexes the face-located stresses with the cell's own indices, no averaging):
+ *   KPP       u★  = max(√√(τx² + τy²), u★_min)              /root/reference/src/OMIPConfigurations/KPP/kpp_surface_forcing.jl:18-22
+ *             Bo  = −g (α Jᵀ − β Jˢ)   (stabilising positive)  …/KPP/kpp_surface_forcing.jl:28-29 (−top_buoyancy_flux)
+ *   NEMO-TKE  u★² = √(τx² + τy²),  e_surf = max(e_min0, Cᵇ u★²)  …/NEMOTKE/nemo_tke_surface_forcing.jl:14-22,
+ *                                                                 …/NEMOTKE/nemo_tke_compute_closure_fields.jl:82-90
+ * α, β (thermal expansion, haline contraction of the surface cell) are INPUTS: the equation of state belongs to
+ * the host ocean model.  Any output / α / β pointer may be NULL (that by-product is skipped).
+ * coflux_attach_closure_forcing makes every following coflux_update_state emit the by-products from the
+ * centre→face stress kernel itself (τx, τy are in registers there; no extra launch, no re-read of the stresses);
+ * coflux_closure_surface_forcing is the stand-alone form (one launch, reads the net fluxes back).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct coflux_closure_forcing {
+  coflux_array thermal_expansion, haline_contraction;   /* α [1/K], β [kg/g] at k = Nz-1 (2-D)                */
+  coflux_array friction_velocity;                       /* KPP u★                                              */
+  coflux_array friction_velocity_squared;               /* NEMO-TKE u★²                                        */
+  coflux_array surface_tke;                             /* NEMO-TKE e_surf                                     */
+  coflux_array buoyancy_flux;                           /* KPP Bo                                              */
+  double minimum_friction_velocity;                     /* 1e-6   kpp_parameters.jl:98                         */
+  double minimum_surface_tke;                           /* 1e-4   nemo_tke_parameters.jl:54 (rn_emin0)         */
+  double Cb;                                            /* 3.75   nemo_tke_parameters.jl:45 (rn_ebb)           */
+  double gravitational_acceleration;                    /* buoyancy.formulation.gravitational_acceleration     */
+} coflux_closure_forcing;
+int coflux_closure_surface_forcing(coflux_ctx*, const coflux_net_ocean_fluxes* net, const coflux_closure_forcing*, void* cu_stream);
+int coflux_attach_closure_forcing(coflux_ctx*, const coflux_closure_forcing* forcing_or_null);
 
 /* Diagnostics */
 int coflux_launch_count(coflux_ctx*, int64_t* launches);   /* kernels launched through this context  */

@@ -761,6 +761,30 @@ int SUF(oracle_update_state)(const coflux_config* cfg, const coflux_update_input
 }
 
 /* scalar probes for unit tests */
+/* Closure surface-forcing front ends — literal restatement of the in-tree consumers of the net fluxes:
+ *   /root/reference/src/OMIPConfigurations/KPP/kpp_surface_forcing.jl:18-22    u★  = max(sqrt(sqrt(τx^2 + τy^2)), minimum_friction_velocity)
+ *   …/KPP/kpp_surface_forcing.jl:28-29                                         Bo  = − top_buoyancy_flux = −g (α Jᵀ − β Jˢ)
+ *   …/NEMOTKE/nemo_tke_surface_forcing.jl:14-22                                u★² = sqrt(τx^2 + τy^2);  e = max(minimum_surface_TKE, Cᵇ u★²)
+ * τx, τy are taken at the cell's own (i, j), as the reference does. */
+int SUF(oracle_closure_surface_forcing)(const coflux_config* cfg, const coflux_net_ocean_fluxes* net, const coflux_closure_forcing* f) {
+  const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny;
+  for (int j = 0; j < Ny; ++j)
+    for (int i = 0; i < Nx; ++i) {
+      const FT tx = SUF(ld)(&net->u, i, j, 0, 0), ty = SUF(ld)(&net->v, i, j, 0, 0);
+      const FT ustar2 = SQRT(tx * tx + ty * ty);
+      SUF(st)(&f->friction_velocity_squared, i, j, 0, ustar2);
+      SUF(st)(&f->friction_velocity, i, j, 0, FMAX(SQRT(SQRT(tx * tx + ty * ty)), (FT)f->minimum_friction_velocity));
+      SUF(st)(&f->surface_tke, i, j, 0, FMAX((FT)f->minimum_surface_tke, (FT)f->Cb * ustar2));
+      if (f->buoyancy_flux.ptr && f->thermal_expansion.ptr && f->haline_contraction.ptr) {
+        const FT JT = SUF(ld)(&net->T, i, j, 0, 0), JS = SUF(ld)(&net->S, i, j, 0, 0);
+        const FT top = (FT)f->gravitational_acceleration *
+                       (SUF(ld)(&f->thermal_expansion, i, j, 0, 0) * JT - SUF(ld)(&f->haline_contraction, i, j, 0, 0) * JS);
+        SUF(st)(&f->buoyancy_flux, i, j, 0, -top);
+      }
+    }
+  return 0;
+}
+
 /* NormalizeSalinity — restatement of /root/reference/src/OMIPConfigurations/omip_simulation.jl:187-220:
  *   compute!(mean_total)                        mean_total = Field(Average(flux_field [+ additional_buffer], dims=(1,2)))
  *   parent(n.flux_field) .-= n.mean_total       (whole parent, halos included)

@@ -67,6 +67,12 @@ def update_state(cfg, inputs, outputs, time):
     assert f(C.byref(cfg), C.byref(inputs), C.byref(outputs), float(time)) == 0
 
 
+def closure_surface_forcing(cfg, net, forcing):
+    """KPP / NEMO-TKE surface-forcing front ends (kpp_surface_forcing.jl:18-29, nemo_tke_surface_forcing.jl:14-22)."""
+    f = fn("oracle_closure_surface_forcing", cfg)
+    assert f(C.byref(cfg), C.byref(net), C.byref(forcing)) == 0
+
+
 def normalize_salinity_flux(cfg, norm, mean=None):
     """NormalizeSalinity (omip_simulation.jl:187-220) on host arrays; returns (Σ f·Az, Σ Az).  `mean`: subtract this
     value instead of the local mean (multi-slab)."""
