@@ -411,6 +411,21 @@ def main():
                                               "algorithmic_bytes_per_cell": words * 8,
                                               "achieved_GBs": cells_global * words * 8 / (tio * 1e-3) / 1e9,
                                               "roofline_frac": cells_global * words * 8 / (tio * 1e-3) / 1e9 / peak}
+        # atmosphere–sea-ice solve with skin temperature (row a7; one cell per thread, SHEBA/Paulson ψ, fixed roughness)
+        xch_i, oc_i, ai_i = di.exchange_state(), di.ocean_surface(), di.interface_fluxes("ai")
+        ei.interpolate_atmosphere_state(di.atmos_series(), QUERY_TIME, xch_i, st)
+        Ttop0 = di.ice["top_temperature"].data.clone()
+        tai = []
+        for k in range(6):
+            di.ice["top_temperature"].data.copy_(Ttop0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); ei.compute_atmosphere_sea_ice_fluxes(xch_i, oc_i, ice, ai_i, st); b.record(st)
+            torch.cuda.synchronize()
+            if k >= 2:
+                tai.append(a.elapsed_time(b))
+        tam = float(np.mean(tai))
+        extras["atmosphere_sea_ice_kernel_f64"] = {"ms": tam, "Mcells/s": cells_global / (tam * 1e-3) / 1e6,
+                                                   "ice_covered_fraction": float((di.ice["concentration"].data > 0).double().mean())}
         ei.close(); del di, hi, T0
 
     if world > 1:

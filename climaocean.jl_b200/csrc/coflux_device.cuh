@@ -13,6 +13,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include "../../include/coflux.h"
+#include "coflux_fastmath.cuh"
 
 namespace coflux {
 
@@ -84,6 +85,27 @@ template <> struct M<float> {
   static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
   static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
 };
+
+// Lean Float64 math policy: pow, exp, division and square root from coflux_fastmath.cuh (tables read from global
+// memory), everything else — including the ORDER of operations of the callers — unchanged.  Measured on B200 against the
+// CUDA math library / IEEE operations on 4.2 M arguments each (tools/fm_check.cu): div and sqrt agree bit for bit, exp
+// and log (hence pow) to ≤ 1 ulp.  Against the oracle on 256×128 cells q★ deviates 1.6e-13 (relative, floor 1e-3) with this
+// policy; a fused single-exponential form of p_sat that is mathematically identical deviates 5.2e-13 and pushes the
+// salt flux past the 1e-12 bar — hence the policy swaps functions, never formulas.
+struct MLeanD {
+  static __device__ __forceinline__ double pow(double x, double y) { return fm::exp(y * fm::log(x, &COFLUX_LOG_TABLE[0][0]), COFLUX_EXP_TABLE); }
+  static __device__ __forceinline__ double exp(double x) { return fm::exp(x, COFLUX_EXP_TABLE); }
+  static __device__ __forceinline__ double log(double x) { return fm::log(x, &COFLUX_LOG_TABLE[0][0]); }
+  static __device__ __forceinline__ double div(double a, double b) { return fm::div(a, b); }
+  static __device__ __forceinline__ double sqrt(double x) { return (x > 0.0) ? fm::sqrt(x) : ::sqrt(x); }
+};
+#ifndef COFLUX_LEAN_V1
+#define COFLUX_LEAN_V1 1      /* one-cell-per-thread kernels (Large–Yeager, sea ice): lean policy in Float64 */
+#endif
+template <typename FT> struct DefaultMP { using type = M<FT>; };
+#if COFLUX_LEAN_V1
+template <> struct DefaultMP<double> { using type = MLeanD; };
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Device parameter block (built once per context on the host, in FT arithmetic)
@@ -168,60 +190,83 @@ template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> p
 // ---------------------------------------------------------------------------------------------
 // Stability functions (A5) — only the taken branch is evaluated
 // ---------------------------------------------------------------------------------------------
+// LM: the math policy (M<FT>: CUDA math library; MLeanD in Float64: lean log / cbrt / sqrt / division, ≤ 1 ulp apart)
+template <typename FT> struct LMath { using P = typename DefaultMP<FT>::type;
+  static __device__ __forceinline__ FT log(FT x) { return P::log(x); }
+  static __device__ __forceinline__ FT sqrt(FT x) { return P::sqrt(x); }
+  static __device__ __forceinline__ FT div(FT a, FT b) { return P::div(a, b); }
+  static __device__ __forceinline__ FT cbrt(FT x);
+};
+template <> __device__ __forceinline__ double LMath<double>::cbrt(double x) {
+#if COFLUX_LEAN_V1
+  return (x > 1e-30 && x < 1e30) ? fm::cbrt(x) : ::cbrt(x);
+#else
+  return ::cbrt(x);
+#endif
+}
+template <> __device__ __forceinline__ float LMath<float>::cbrt(float x) { return ::cbrtf(x); }
+
 template <typename FT> __device__ __forceinline__ FT psi_conv_cbrt(FT y) {  // convective (cube-root) limb shared by Edson ψu, ψθ
-  const FT rt3 = M<FT>::sqrt(FT(3));
-  return FT(1.5) * M<FT>::log((FT(1) + y + y * y) / FT(3)) - rt3 * M<FT>::atan((FT(1) + FT(2) * y) / rt3) + M<FT>::pi() / rt3;
+  using L = LMath<FT>;
+  const FT rt3 = FT(1.7320508075688772935);
+  return FT(1.5) * L::log(L::div(FT(1) + y + y * y, FT(3))) - rt3 * M<FT>::atan(L::div(FT(1) + FT(2) * y, rt3)) + L::div(M<FT>::pi(), rt3);
 }
 template <typename FT> __device__ __forceinline__ FT psi_businger_momentum(FT x) {  // Kansas limb, x = (1 − γ ζ)^{1/4}
-  return FT(2) * M<FT>::log((FT(1) + x) / FT(2)) + M<FT>::log((FT(1) + x * x) / FT(2)) - FT(2) * M<FT>::atan(x) + M<FT>::pi() / FT(2);
+  using L = LMath<FT>;
+  return FT(2) * L::log((FT(1) + x) / FT(2)) + L::log((FT(1) + x * x) / FT(2)) - FT(2) * M<FT>::atan(x) + M<FT>::pi() / FT(2);
 }
 template <typename FT> __device__ __noinline__ FT psi_momentum(int kind, FT z) {
+  using L = LMath<FT>;
   if (kind == COFLUX_STABILITY_EDSON) {
     if (z >= FT(0)) {
       FT dz = M<FT>::min(FT(50), FT(0.35) * z);
       return -FT(0.7) * z - FT(0.75) * (z - FT(5) / FT(0.35)) * M<FT>::exp(-dz) - FT(0.75) * FT(5) / FT(0.35);
     }
-    FT x = M<FT>::sqrt(M<FT>::sqrt(FT(1) - FT(15) * z));
+    FT x = L::sqrt(L::sqrt(FT(1) - FT(15) * z));
     FT psik = psi_businger_momentum(x);
-    FT psic = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(10.15) * z));
-    FT f = z * z / (FT(1) + z * z);
+    FT psic = psi_conv_cbrt(L::cbrt(FT(1) - FT(10.15) * z));
+    FT f = L::div(z * z, FT(1) + z * z);
     return (FT(1) - f) * psik + f * psic;
   }
   if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
   // SHEBA_PAULSON and LARGE_YEAGER share the Paulson unstable limb
-  if (z < FT(0)) return psi_businger_momentum(M<FT>::sqrt(M<FT>::sqrt(FT(1) - FT(16) * z)));
+  if (z < FT(0)) return psi_businger_momentum(L::sqrt(L::sqrt(FT(1) - FT(16) * z)));
   if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
-  // Grachev et al. (2007) SHEBA, stable
+  // Grachev et al. (2007) SHEBA, stable.  B = ∛((1 − b_m)/b_m) and the constant arctangent depend only on a_m, b_m:
+  // written as literals (the correctly rounded values of the FT expressions) instead of a ∛ and an atan per call.
   const FT a = FT(5), b = FT(5) / FT(6.5);   // a_m, b_m = a_m/6.5
-  const FT rt3 = M<FT>::sqrt(FT(3));
-  FT x = M<FT>::cbrt(FT(1) + z);
-  FT B = M<FT>::cbrt((FT(1) - b) / b);
-  FT p1 = -FT(3) * a * (x - FT(1)) / b;
-  FT p2 = a * B / (FT(2) * b) *
-          (FT(2) * M<FT>::log((x + B) / (FT(1) + B)) - M<FT>::log((x * x - B * x + B * B) / (FT(1) - B + B * B)) +
-           FT(2) * rt3 * (M<FT>::atan((FT(2) * x - B) / (rt3 * B)) - M<FT>::atan((FT(2) - B) / (rt3 * B))));
+  const FT rt3 = FT(1.7320508075688772935);
+  FT x = L::cbrt(FT(1) + z);
+  const FT B = (sizeof(FT) == 8) ? FT(0.6694329500821695) : FT(0.6694329380989075);
+  const FT atanB = (sizeof(FT) == 8) ? FT(0.8539936329836121) : FT(0.8539936542510986);   // atan((2 − B)/(√3 B))
+  FT p1 = L::div(-FT(3) * a * (x - FT(1)), b);
+  FT p2 = L::div(a * B, FT(2) * b) *
+          (FT(2) * L::log(L::div(x + B, FT(1) + B)) - L::log(L::div(x * x - B * x + B * B, FT(1) - B + B * B)) +
+           FT(2) * rt3 * (M<FT>::atan(L::div(FT(2) * x - B, rt3 * B)) - atanB));
   return p1 + p2;
 }
 template <typename FT> __device__ __noinline__ FT psi_scalar(int kind, FT z) {
+  using L = LMath<FT>;
   if (kind == COFLUX_STABILITY_EDSON) {
     if (z >= FT(0)) {
       FT dz = M<FT>::min(FT(50), FT(0.35) * z);
       return -M<FT>::pow(FT(1) + FT(2) / FT(3) * z, FT(1.5)) - FT(2) / FT(3) * (z - FT(14.28)) * M<FT>::exp(-dz) - FT(8.525);
     }
-    FT x = M<FT>::sqrt(FT(1) - FT(15) * z);
-    FT psik = FT(2) * M<FT>::log((FT(1) + x) / FT(2));
-    FT psic = psi_conv_cbrt(M<FT>::cbrt(FT(1) - FT(34.15) * z));
-    FT f = z * z / (FT(1) + z * z);
+    FT x = L::sqrt(FT(1) - FT(15) * z);
+    FT psik = FT(2) * L::log((FT(1) + x) / FT(2));
+    FT psic = psi_conv_cbrt(L::cbrt(FT(1) - FT(34.15) * z));
+    FT f = L::div(z * z, FT(1) + z * z);
     return (FT(1) - f) * psik + f * psic;
   }
   if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
-  if (z < FT(0)) return FT(2) * M<FT>::log((FT(1) + M<FT>::sqrt(FT(1) - FT(16) * z)) / FT(2));
+  if (z < FT(0)) return FT(2) * L::log((FT(1) + L::sqrt(FT(1) - FT(16) * z)) / FT(2));
   if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
   const FT a = FT(5), b = FT(5), c = FT(3);
-  FT B = M<FT>::sqrt(c * c - FT(4));
-  FT p1 = -b / FT(2) * M<FT>::log(FT(1) + c * z + z * z);
-  FT p2 = (-a / B + b * c / (FT(2) * B)) *
-          (M<FT>::log((FT(2) * z + c - B) / (FT(2) * z + c + B)) - M<FT>::log((c - B) / (c + B)));
+  const FT B = (sizeof(FT) == 8) ? FT(2.23606797749979) : FT(2.2360680103302);              // √(c² − 4)
+  const FT logB = (sizeof(FT) == 8) ? FT(-1.9248473002384139) : FT(-1.9248473644256592);    // ln((c − B)/(c + B))
+  FT p1 = -b / FT(2) * L::log(FT(1) + c * z + z * z);
+  FT p2 = (L::div(-a, B) + L::div(b * c, FT(2) * B)) *
+          (L::log(L::div(FT(2) * z + c - B, FT(2) * z + c + B)) - logB);
   return p1 + p2;
 }
 
@@ -260,10 +305,10 @@ __device__ __forceinline__ FT similarity_profile(int form, int stab, FT h, FT l,
   return chi;
 }
 
-template <typename FT> __device__ __forceinline__ FT ly_cdn(FT U) {
+template <typename FT, class MP = M<FT>> __device__ __forceinline__ FT ly_cdn(FT U) {
   if (U >= FT(33)) return FT(2.34e-3);
   FT U2 = U * U, U6 = U2 * U2 * U2;
-  return FT(1e-3) * (FT(2.7) / U + FT(0.142) + U / FT(13.09) - FT(3.14807e-10) * U6);
+  return FT(1e-3) * (MP::div(FT(2.7), U) + FT(0.142) + MP::div(U, FT(13.09)) - FT(3.14807e-10) * U6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,41 +348,60 @@ __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P
   return s;
 }
 
-template <typename FT, int SURF>
-__device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const CellIn<FT>& in, CellOut<FT>& out) {
-  const ThermoC<FT>& c = P.th;
-  const FT g = P.g, h = P.h, kappa = F.kappa;
-  Thermo<FT> atm = phase_equil_pTq(c, in.pa, in.Ta, in.qa);
-  FT du, dv;
+// One cell's interface solve as an object: init() hoists everything invariant under the iteration, pass() is one
+// fixed-point pass (sets `go`), finish() hands the scales back.  solve_cell() runs it start to finish in one thread
+// (flux_kernel); flux_refill_kernel keeps one solver per lane and refills a lane as soon as its cell has converged.
+template <typename FT, int SURF> struct CellSolver {
+  using MP = typename DefaultMP<FT>::type;
+  CellIn<FT> in;
+  Thermo<FT> atm;
+  SurfaceState<FT> S;
+  FT du, dv, x, theta_a, delta, du2dv2, lnh10, U_ly;
+  FT Ts, ustar, tstar, qstar, rcdn_ly;
+  FT su, st, sq, sT, sr;                       // Brent snapshot, refreshed after 1, 2, 4, … passes
+  int it, snap_it, window, stop_at;
+  bool ly, fixed, go;
+
+  __device__ __forceinline__ void init(const DevParams<FT>& P, const FluxP<FT>& F, const CellIn<FT>& in_) {
+    in = in_;
+    const ThermoC<FT>& c = P.th;
+    const FT g = P.g, h = P.h;
+  atm = phase_equil_pTq<FT, MP>(c, in.pa, in.Ta, in.qa);
   if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = in.ua - in.us; dv = in.va - in.vs; }
   else { du = in.ua; dv = in.va; }
-  FT x = FT(1);
-  if (SURF == 0) { FT s = in.So / FT(1000); x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s); }
-  const FT theta_a = in.Ta + g * h / atm.cp_m;
-  const FT delta = c.eps - FT(1);
-  const FT du2dv2 = du * du + dv * dv;
+  x = FT(1);
+  if (SURF == 0) { FT s = MP::div(in.So, FT(1000)); x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s); }
+  theta_a = in.Ta + MP::div(g * h, atm.cp_m);
+  delta = c.eps - FT(1);
+  du2dv2 = du * du + dv * dv;
 
-  FT Ts = in.Ts0;
-  SurfaceState<FT> S = surface_state<FT, SURF>(P, F, atm, in.pa, theta_a, x, Ts);
+  Ts = in.Ts0;
+  S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
 
-  FT ustar = F.init, tstar = F.init, qstar = F.init;
-  const bool ly = (F.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER);
-  FT U_ly = FT(0), rcdn_ly = FT(0);
-  const FT lnh10 = ly ? M<FT>::log(h / FT(10)) : FT(0);
+  ustar = F.init; tstar = F.init; qstar = F.init;
+  ly = (F.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER);
+  U_ly = FT(0); rcdn_ly = FT(0);
+  lnh10 = ly ? M<FT>::log(h / FT(10)) : FT(0);
   if (ly) {
-    U_ly = M<FT>::max(M<FT>::sqrt(du2dv2), F.ly_umin);
-    FT cdn = ly_cdn(U_ly);
-    FT rcdn = M<FT>::sqrt(cdn);
+    U_ly = M<FT>::max(MP::sqrt(du2dv2), F.ly_umin);
+    FT cdn = ly_cdn<FT, MP>(U_ly);
+    FT rcdn = MP::sqrt(cdn);
     FT chn = ((S.dtheta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
     FT cen = FT(34.6e-3) * rcdn;
     rcdn_ly = rcdn;
-    ustar = rcdn * U_ly; tstar = chn / rcdn * S.dtheta; qstar = cen / rcdn * S.dq;
+    ustar = rcdn * U_ly; tstar = MP::div(chn, rcdn) * S.dtheta; qstar = MP::div(cen, rcdn) * S.dq;
   }
 
-  const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
-  int it = 0;
-  bool go = fixed ? (F.maxit > 0) : true;
-  while (go) {
+  fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+  it = 0;
+  go = fixed ? (F.maxit > 0) : true;
+  su = ustar; st = tstar; sq = qstar; sT = Ts; sr = rcdn_ly;   // Brent snapshot, refreshed after 1, 2, 4, … passes
+  snap_it = 0; window = 1; stop_at = -1;
+  }
+
+  __device__ __forceinline__ void pass(const DevParams<FT>& P, const FluxP<FT>& F) {
+    const ThermoC<FT>& c = P.th;
+    const FT g = P.g, h = P.h, kappa = F.kappa;
     const FT u0 = ustar, t0 = tstar, q0 = qstar;
     if (SURF == 1 && F.itemp == COFLUX_TEMPERATURE_SKIN) {
       // conductive flux balance through the slab (row a7)
@@ -357,28 +421,28 @@ __device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const Cel
       FT adT = M<FT>::min(F.skin_max_dT, M<FT>::abs(dT));
       FT sgn = (dT > FT(0)) ? FT(1) : ((dT < FT(0)) ? FT(-1) : FT(0));
       Ts = M<FT>::min(Ts + adT * sgn, Tm);
-      S = surface_state<FT, SURF>(P, F, atm, in.pa, theta_a, x, Ts);
+      S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
     }
     const FT bstar = g / S.T_v * (t0 * (FT(1) + delta * S.q_vap) + delta * S.T_v * q0);
     if (ly) {
-      FT zeta = kappa * bstar * h / (u0 * u0);
+      FT zeta = MP::div(kappa * bstar * h, u0 * u0);
       zeta = M<FT>::max(FT(-10), M<FT>::min(FT(10), zeta));
       FT psim = psi_momentum(COFLUX_STABILITY_LARGE_YEAGER, zeta);
       FT psih = psi_scalar(COFLUX_STABILITY_LARGE_YEAGER, zeta);
-      FT U10N = U_ly / (FT(1) + rcdn_ly / kappa * (lnh10 - psim));
+      FT U10N = MP::div(U_ly, FT(1) + MP::div(rcdn_ly, kappa) * (lnh10 - psim));
       U10N = M<FT>::max(U10N, F.ly_umin);
-      FT cdn = ly_cdn(U10N);
-      FT rcdn = M<FT>::sqrt(cdn);
+      FT cdn = ly_cdn<FT, MP>(U10N);
+      FT rcdn = MP::sqrt(cdn);
       FT cen = FT(34.6e-3) * rcdn;
       FT chn = ((zeta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
-      FT xm = FT(1) + rcdn / kappa * (lnh10 - psim);
-      FT cd = cdn / (xm * xm);
-      FT rr = M<FT>::sqrt(cd / cdn);
-      FT ch = chn / (FT(1) + chn / (kappa * rcdn) * (lnh10 - psih)) * rr;
-      FT ce = cen / (FT(1) + cen / (kappa * rcdn) * (lnh10 - psih)) * rr;
+      FT xm = FT(1) + MP::div(rcdn, kappa) * (lnh10 - psim);
+      FT cd = MP::div(cdn, xm * xm);
+      FT rr = MP::sqrt(MP::div(cd, cdn));
+      FT ch = MP::div(chn, FT(1) + MP::div(chn, kappa * rcdn) * (lnh10 - psih)) * rr;
+      FT ce = MP::div(cen, FT(1) + MP::div(cen, kappa * rcdn) * (lnh10 - psih)) * rr;
       rcdn_ly = rcdn;
-      FT rcd = M<FT>::sqrt(cd);
-      ustar = rcd * U_ly; tstar = ch / rcd * S.dtheta; qstar = ce / rcd * S.dq;
+      FT rcd = MP::sqrt(cd);
+      ustar = rcd * U_ly; tstar = MP::div(ch, rcd) * S.dtheta; qstar = MP::div(ce, rcd) * S.dq;
     } else {
       const FT Jb = -u0 * bstar;
       FT UG = F.beta * M<FT>::cbrt(Jb * P.hbl);
@@ -413,13 +477,41 @@ __device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const Cel
     ++it;
     if (fixed) {
       go = it < F.maxit;
+    } else if (stop_at >= 0) {                  // finishing a detected limit cycle
+      go = it < stop_at;
+      if (!go) it = F.maxit;
     } else {
       FT drift = M<FT>::abs(ustar - u0) + M<FT>::abs(tstar - t0) + M<FT>::abs(qstar - q0);
       go = !((drift < F.tol) || (it >= F.maxit));
+      // Brent cycle detection.  The pass is a pure function of (u★, θ★, q★, T_s, √Cd_N); with a skin temperature
+      // (ΔT clamp, melting cap) one cell in nine never meets the stop rule but flips between two states for ever.
+      // The reference iterates such a cell to maxiter; the state it ends in is the one (maxiter − it) mod λ passes
+      // further along the orbit, λ the period — run just those.  Bit-identical to iterating on.
+      if (go) {
+        if (ustar == su && tstar == st && qstar == sq && Ts == sT && rcdn_ly == sr) {
+          const int lambda = it - snap_it;
+          stop_at = it + (F.maxit - it) % lambda;
+          go = it < stop_at;
+          if (!go) it = F.maxit;
+        } else if (it - snap_it == window) {
+          su = ustar; st = tstar; sq = qstar; sT = Ts; sr = rcdn_ly; snap_it = it; window *= 2;
+        }
+      }
     }
+    }
+
+  __device__ __forceinline__ void finish(CellOut<FT>& out) const {
+    out.ustar = ustar; out.tstar = tstar; out.qstar = qstar; out.Ts = Ts;
+    out.rho_a = atm.rho; out.cp_a = atm.cp_m; out.du = du; out.dv = dv; out.it = it;
   }
-  out.ustar = ustar; out.tstar = tstar; out.qstar = qstar; out.Ts = Ts;
-  out.rho_a = atm.rho; out.cp_a = atm.cp_m; out.du = du; out.dv = dv; out.it = it;
+};
+
+template <typename FT, int SURF>
+__device__ void solve_cell(const DevParams<FT>& P, const FluxP<FT>& F, const CellIn<FT>& in, CellOut<FT>& out) {
+  CellSolver<FT, SURF> s;
+  s.init(P, F, in);
+  while (s.go) s.pass(P, F);
+  s.finish(out);
 }
 
 }  // namespace coflux

@@ -222,6 +222,99 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lane-refill form of the stand-alone interface solve (rows a4–a7 without interpolation / assembly), for the
+// solves whose pass count varies strongly from cell to cell — above all the atmosphere–sea-ice solve with a skin
+// temperature: 29 passes on average, but one cell in nine runs to maxiter (limit cycle of the clamped T_s update), so
+// with one cell per thread virtually every warp waits for a 100-pass lane.  Here every lane owns a CellSolver; a lane
+// whose cell has converged stores its result and pops the next cell of the CTA's tile from a shared counter.  The
+// loads / stores of a popped cell are not coalesced (≈ 25 words per cell against ≈ 29 passes × 2 000 instructions).
+// Arithmetic per cell is exactly that of flux_kernel → bit-identical results.
+// ---------------------------------------------------------------------------------------------
+template <typename FT, int SURF, int TILE>
+__global__ void __launch_bounds__(128) flux_refill_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  __shared__ int head;
+  if (threadIdx.x == 0) head = 0;
+  __syncthreads();
+  const DevParams<FT>& P = a.P;
+  const FluxP<FT>& F = (SURF == 0) ? P.ao : P.ai;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
+  const int ntile = (int)((a.ncell - tile0 < TILE) ? (a.ncell - tile0) : TILE);
+  CellSolver<FT, SURF> s;
+  int cur = -1, ci = 0, cj = 0;
+  FT Tunits = FT(0);
+
+  auto store = [&](bool act) {
+    FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0), Tsout = Tunits, us = FT(0), ts = FT(0), qs = FT(0);
+    int its = 0;
+    if (act) {
+      CellOut<FT> o;
+      s.finish(o);
+      const FT dU = M<FT>::sqrt(o.du * o.du + o.dv * o.dv);
+      const FT taux = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.du / dU;
+      const FT tauy = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.dv / dU;
+      const ThermoC<FT>& c = P.th;
+      const FT Ta = s.in.Ta;
+      const FT LH = (SURF == 0) ? c.LH_v0 + (c.cp_v - c.cp_l) * (Ta - c.T_0) : c.LH_s0 + (c.cp_v - c.cp_i) * (Ta - c.T_0);
+      Qv = -o.rho_a * o.ustar * o.qstar * LH;
+      Qc = -o.rho_a * o.cp_a * o.ustar * o.tstar;
+      Fv = -o.rho_a * o.ustar * o.qstar;
+      rtx = o.rho_a * taux; rty = o.rho_a * tauy;
+      Tsout = o.Ts - P.T_offset;
+      us = o.ustar; ts = o.tstar; qs = o.qstar; its = o.it;
+    }
+    const int i = ci, j = cj;
+    stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
+    stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tsout);
+    stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
+    if (SURF == 1) stg<FT>(a.Ttop_out, i, j, Tsout);
+    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = its;
+    if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
+  };
+  // pop cells until one needs passes (inactive cells and cells that stop at pass 0 are finished on the spot)
+  auto pop = [&]() {
+    for (;;) {
+      cur = atomicAdd(&head, 1);
+      if (cur >= ntile) { cur = -1; return; }
+      const long long idx = tile0 + cur;
+      const int jj = (int)(idx / a.nxr);
+      const int ii = (int)(idx - (long long)jj * a.nxr);
+      ci = ii - a.ring; cj = jj - a.ring;
+      const int i = ci, j = cj;
+      CellIn<FT> in;
+      in.ua = ldg<FT>(a.xu, i, j); in.va = ldg<FT>(a.xv, i, j); in.Ta = ldg<FT>(a.xT, i, j); in.pa = ldg<FT>(a.xp, i, j);
+      in.qa = ldg<FT>(a.xq, i, j); in.Qs = ldg<FT>(a.xQs, i, j); in.Ql = ldg<FT>(a.xQl, i, j);
+      in.us = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+      in.vs = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+      Tunits = ldg<FT>(a.oT, i, j);
+      in.Ts0 = Tunits + P.T_offset;
+      in.So = (SURF == 0) ? ldg<FT>(a.oS, i, j) : FT(0);
+      bool act = is_active(a.mask, i, j);
+      if (SURF == 1) {
+        in.h_ice = ldg<FT>(a.ih, i, j);
+        in.S_ice = ldg<FT>(a.iS, i, j);
+        in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+        const FT conc = ldg<FT>(a.iconc, i, j);
+        act = act && (conc > FT(0)) && (in.h_ice > FT(0));
+      } else {
+        in.h_ice = in.S_ice = in.albedo = FT(0);
+      }
+      if (act) {
+        s.init(P, F, in);
+        if (s.go) return;
+      }
+      store(act);
+    }
+  };
+  pop();
+  while (__any_sync(0xffffffffu, cur >= 0)) {
+    if (cur >= 0) {
+      s.pass(P, F);
+      if (!s.go) { store(true); pop(); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // centre → face momentum fluxes (A9)
 // ---------------------------------------------------------------------------------------------
 // by-products of the net fluxes for the ocean mixing closures (KPP/kpp_surface_forcing.jl:18-29,

@@ -36,7 +36,6 @@
 #pragma once
 #include "coflux_kernels.cuh"
 #include "coflux_psi_table.h"
-#include "coflux_fastmath.cuh"
 #include <type_traits>
 
 namespace coflux {
@@ -482,19 +481,6 @@ __device__ __noinline__ D3<FT> lean_cold_pass(const DevParams<FT>* P, FT U2, FT 
 template <typename FT> __device__ __forceinline__ bool same_bits(FT a, FT b);
 template <> __device__ __forceinline__ bool same_bits<double>(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
-
-// Math policy of the phase-A thermodynamics in the lean Float64 kernel: pow and exp from coflux_fastmath.cuh
-// (tables read from global memory here: three evaluations per cell), everything else — including the IEEE divisions
-// and the order of operations — exactly as in coflux_device.cuh.  Measured against the oracle on 256×128 cells:
-// q★ deviates 8.7e-14 (relative, floor 1e-3) with this policy; a fused single-exponential form of p_sat that is
-// mathematically identical deviates 5.2e-13 and pushes the salt flux past the 1e-12 bar — hence this form.
-struct MLeanD {
-  static __device__ __forceinline__ double pow(double x, double y) { return fm::exp(y * fm::log(x, &COFLUX_LOG_TABLE[0][0]), COFLUX_EXP_TABLE); }
-  static __device__ __forceinline__ double exp(double x) { return fm::exp(x, COFLUX_EXP_TABLE); }
-  // a/b by reciprocal + residual correction: agrees with the IEEE quotient on every one of 4.2 M random arguments
-  // (tools/fm_check.cu) at half the instructions and without the slow-path branch
-  static __device__ __forceinline__ double div(double a, double b) { return fm::div(a, b); }
-};
 
 // Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`, lean loop; tools/ab_variants.py, profiles/README.md):
 //   TILE 256: 8 CTAs/SM (64 regs, 288 B spills) 4.08 ms, 7 CTAs (72 regs) 3.98 ms, 6 CTAs (80 regs, 24 B) 3.98 ms;
