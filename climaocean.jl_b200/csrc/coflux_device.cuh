@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include "../../include/coflux.h"
 #include "coflux_fastmath.cuh"
+#include "coflux_psi_table.h"
 
 namespace coflux {
 
@@ -206,6 +207,48 @@ template <> __device__ __forceinline__ double LMath<double>::cbrt(double x) {
 }
 template <> __device__ __forceinline__ float LMath<float>::cbrt(float x) { return ::cbrtf(x); }
 
+// Table evaluation of a stability function (coflux_psi_table.h): z ∈ [2^KMIN, 2^KMAX) positive (−ζ for the unstable
+// tables, ζ for the stable one); which = 0 momentum, 1 scalar.  Degree-7 piecewise polynomials, error ≤ 3e-16·max(1,|ψ|).
+#define COFLUX_PSI_ROWS ((COFLUX_PSI_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
+__device__ __forceinline__ bool psi_tab_in_range(double z) { return z >= 9.313225746154785e-10 && z < 8192.0; }
+__device__ __forceinline__ bool psi_tab_in_range(float z) { return z >= 9.313225746154785e-10f && z < 8192.0f; }
+static_assert(COFLUX_PSI_KMIN == -30 && COFLUX_PSI_KMAX == 13, "psi_tab_in_range assumes [2^-30, 2^13)");
+__device__ __forceinline__ double psi_tab_eval(const double (*tab)[2][8], double z, int which) {
+  const long long bits = __double_as_longlong(z);
+  const int hi = (int)(bits >> 32);
+  int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
+  row = max(0, min(row, COFLUX_PSI_ROWS - 1));
+  const double t = fma(2.0, __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL), -3.0);
+  const double2* q = reinterpret_cast<const double2*>(&tab[row][which][0]);
+  const double2 c0 = __ldg(q), c1 = __ldg(q + 1), c2 = __ldg(q + 2), c3 = __ldg(q + 3);
+  double a = fma(c3.y, t, c3.x);
+  a = fma(a, t, c2.y); a = fma(a, t, c2.x); a = fma(a, t, c1.y); a = fma(a, t, c1.x); a = fma(a, t, c0.y);
+  return fma(a, t, c0.x);
+}
+__device__ __forceinline__ float psi_tab_eval(const float (*tab)[2][8], float z, int which) {
+  const int bits = __float_as_int(z);
+  int row = (bits >> 19) - ((127 + COFLUX_PSI_KMIN) << 4);
+  row = max(0, min(row, COFLUX_PSI_ROWS - 1));
+  const float t = fmaf(2.0f, __int_as_float(((bits & 0x0007ffff) << 4) | 0x3f800000), -3.0f);
+  const float4* q = reinterpret_cast<const float4*>(&tab[row][which][0]);
+  const float4 c0 = __ldg(q), c1 = __ldg(q + 1);
+  float a = fmaf(c1.w, t, c1.z);
+  a = fmaf(a, t, c1.y); a = fmaf(a, t, c1.x); a = fmaf(a, t, c0.w); a = fmaf(a, t, c0.z); a = fmaf(a, t, c0.y);
+  return fmaf(a, t, c0.x);
+}
+template <typename FT> struct PsiTabs;
+template <> struct PsiTabs<double> {
+  static __device__ __forceinline__ const double (*paulson())[2][8] { return COFLUX_PSI_PAULSON_F64; }
+  static __device__ __forceinline__ const double (*sheba())[2][8] { return COFLUX_PSI_SHEBA_F64; }
+};
+template <> struct PsiTabs<float> {
+  static __device__ __forceinline__ const float (*paulson())[2][8] { return COFLUX_PSI_PAULSON_F32; }
+  static __device__ __forceinline__ const float (*sheba())[2][8] { return COFLUX_PSI_SHEBA_F32; }
+};
+#ifndef COFLUX_PSI_TABLES_V1
+#define COFLUX_PSI_TABLES_V1 1      /* Paulson / SHEBA ψ from tables in the one-cell-per-thread and refill solves */
+#endif
+
 template <typename FT> __device__ __forceinline__ FT psi_conv_cbrt(FT y) {  // convective (cube-root) limb shared by Edson ψu, ψθ
   using L = LMath<FT>;
   const FT rt3 = FT(1.7320508075688772935);
@@ -230,8 +273,12 @@ template <typename FT> __device__ __noinline__ FT psi_momentum(int kind, FT z) {
   }
   if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
   // SHEBA_PAULSON and LARGE_YEAGER share the Paulson unstable limb
-  if (z < FT(0)) return psi_businger_momentum(L::sqrt(L::sqrt(FT(1) - FT(16) * z)));
+  if (z < FT(0)) {
+    if (COFLUX_PSI_TABLES_V1 && psi_tab_in_range(-z)) return psi_tab_eval(PsiTabs<FT>::paulson(), -z, 0);
+    return psi_businger_momentum(L::sqrt(L::sqrt(FT(1) - FT(16) * z)));
+  }
   if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
+  if (COFLUX_PSI_TABLES_V1 && psi_tab_in_range(z)) return psi_tab_eval(PsiTabs<FT>::sheba(), z, 0);
   // Grachev et al. (2007) SHEBA, stable.  B = ∛((1 − b_m)/b_m) and the constant arctangent depend only on a_m, b_m:
   // written as literals (the correctly rounded values of the FT expressions) instead of a ∛ and an atan per call.
   const FT a = FT(5), b = FT(5) / FT(6.5);   // a_m, b_m = a_m/6.5
@@ -259,8 +306,12 @@ template <typename FT> __device__ __noinline__ FT psi_scalar(int kind, FT z) {
     return (FT(1) - f) * psik + f * psic;
   }
   if (kind == COFLUX_STABILITY_NEUTRAL) return FT(0);
-  if (z < FT(0)) return FT(2) * L::log((FT(1) + L::sqrt(FT(1) - FT(16) * z)) / FT(2));
+  if (z < FT(0)) {
+    if (COFLUX_PSI_TABLES_V1 && psi_tab_in_range(-z)) return psi_tab_eval(PsiTabs<FT>::paulson(), -z, 1);
+    return FT(2) * L::log((FT(1) + L::sqrt(FT(1) - FT(16) * z)) / FT(2));
+  }
   if (kind == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * z;
+  if (COFLUX_PSI_TABLES_V1 && psi_tab_in_range(z)) return psi_tab_eval(PsiTabs<FT>::sheba(), z, 1);
   const FT a = FT(5), b = FT(5), c = FT(3);
   const FT B = (sizeof(FT) == 8) ? FT(2.23606797749979) : FT(2.2360680103302);              // √(c² − 4)
   const FT logB = (sizeof(FT) == 8) ? FT(-1.9248473002384139) : FT(-1.9248473644256592);    // ln((c − B)/(c + B))
@@ -357,10 +408,11 @@ template <typename FT, int SURF> struct CellSolver {
   Thermo<FT> atm;
   SurfaceState<FT> S;
   FT du, dv, x, theta_a, delta, du2dv2, lnh10, U_ly;
+  FT lnh_lu, lnh_lt, lnh_lq;                   // ln(h/ℓ) of the fixed roughness lengths (ice_fast)
   FT Ts, ustar, tstar, qstar, rcdn_ly;
   FT su, st, sq, sT, sr;                       // Brent snapshot, refreshed after 1, 2, 4, … passes
   int it, snap_it, window, stop_at;
-  bool ly, fixed, go;
+  bool ly, fixed, go, ice_fast;
 
   __device__ __forceinline__ void init(const DevParams<FT>& P, const FluxP<FT>& F, const CellIn<FT>& in_) {
     in = in_;
@@ -397,13 +449,72 @@ template <typename FT, int SURF> struct CellSolver {
   go = fixed ? (F.maxit > 0) : true;
   su = ustar; st = tstar; sq = qstar; sT = Ts; sr = rcdn_ly;   // Brent snapshot, refreshed after 1, 2, 4, … passes
   snap_it = 0; window = 1; stop_at = -1;
+  // the sea-ice parameter sets of omip_simulation.jl:52-69,91-113 (similarity theory, fixed roughness lengths, standard
+  // log profile, SHEBA or Large–Yeager ψ) take the compact pass_ice(): ψ from the tables, ln(h/ℓ) hoisted
+  ice_fast = COFLUX_PSI_TABLES_V1 && SURF == 1 && !ly && F.form == COFLUX_PROFILE_LOGARITHMIC &&
+             F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
+             (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) &&
+             F.beta >= FT(0) && F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0);
+  lnh_lu = lnh_lt = lnh_lq = FT(0);
+  if (ice_fast) {
+    lnh_lu = M<FT>::log(h / F.mr.fixed); lnh_lt = M<FT>::log(h / F.tr.fixed); lnh_lq = M<FT>::log(h / F.qr.fixed);
+  }
   }
 
-  __device__ __forceinline__ void pass(const DevParams<FT>& P, const FluxP<FT>& F) {
-    const ThermoC<FT>& c = P.th;
+  // ψ of the ice-solve parameter sets at one argument: Paulson table (ζ < 0), SHEBA table or −5ζ (ζ ≥ 0); the
+  // first-order term below the table (|x| < 2⁻³⁰: the quadratic term is < 1e-18), the formulas above it
+  __device__ __forceinline__ FT psi_ice(int stab, FT zz, int which) const {
+    if (zz < FT(0)) {
+      const FT mz = -zz;
+      if (psi_tab_in_range(mz)) return psi_tab_eval(PsiTabs<FT>::paulson(), mz, which);
+      if (mz < FT(1)) return (which ? FT(-8) : FT(-4)) * zz;
+      return which ? psi_scalar(stab, zz) : psi_momentum(stab, zz);
+    }
+    if (stab == COFLUX_STABILITY_LARGE_YEAGER) return -FT(5) * zz;
+    if (psi_tab_in_range(zz)) return psi_tab_eval(PsiTabs<FT>::sheba(), zz, which);
+    if (zz < FT(1)) return FT(-5) * zz;
+    return which ? psi_scalar(stab, zz) : psi_momentum(stab, zz);
+  }
+  // compact pass for the sea-ice parameter sets (see init): same formulas as pass(), one code path
+  __device__ __forceinline__ void pass_ice(const DevParams<FT>& P, const FluxP<FT>& F) {
     const FT g = P.g, h = P.h, kappa = F.kappa;
     const FT u0 = ustar, t0 = tstar, q0 = qstar;
-    if (SURF == 1 && F.itemp == COFLUX_TEMPERATURE_SKIN) {
+    if (F.itemp == COFLUX_TEMPERATURE_SKIN) skin_temperature(P, F, u0, t0, q0);
+    const FT bstar = MP::div(g, S.T_v) * (t0 * (FT(1) + delta * S.q_vap) + delta * S.T_v * q0);
+    const FT Jb = -u0 * bstar;
+    FT UG = F.ugmin;
+    if (Jb > FT(0)) UG = M<FT>::max(F.beta * LMath<FT>::cbrt(Jb * P.hbl), F.ugmin);
+    const FT U = MP::sqrt(du2dv2 + UG * UG);
+    if (U == FT(0) || !(u0 > FT(0))) {
+      if (U == FT(0)) { ustar = tstar = qstar = FT(0); advance(F, u0, t0, q0); }
+      else pass_generic(P, F);                       // u★ = 0: the generic pass knows the limits
+      return;
+    }
+    const FT invL = MP::div(kappa * bstar, u0 * u0);  // 1/L★ (0 when b★ = 0)
+    const FT zeta = h * invL;
+    const int stab = F.stability;
+    const FT psi_hm = psi_ice(stab, zeta, 0), psi_hs = psi_ice(stab, zeta, 1);
+    const FT prof_u = (lnh_lu - psi_hm) + psi_ice(stab, F.mr.fixed * invL, 0);
+    if (!(prof_u > FT(0))) {
+      ustar = tstar = qstar = FT(0);
+    } else {
+      const FT prof_q = (lnh_lq - psi_hs) + psi_ice(stab, F.qr.fixed * invL, 1);
+      const FT prof_t = (lnh_lt - psi_hs) + psi_ice(stab, F.tr.fixed * invL, 1);
+      const FT chi_u = MP::div(kappa, prof_u);
+      const FT chi_q = (prof_q > FT(0)) ? MP::div(kappa, prof_q) : FT(0);
+      const FT chi_t = (prof_t > FT(0)) ? MP::div(kappa, prof_t) : FT(0);
+      ustar = chi_u * U; tstar = chi_t * S.dtheta; qstar = chi_q * S.dq;
+    }
+    advance(F, u0, t0, q0);
+  }
+  __device__ __forceinline__ void pass(const DevParams<FT>& P, const FluxP<FT>& F) {
+    if (ice_fast) pass_ice(P, F);
+    else pass_generic(P, F);
+  }
+  // conductive flux balance through the slab (row a7): T_s relaxes towards the balance temperature, clamped
+  __device__ __forceinline__ void skin_temperature(const DevParams<FT>& P, const FluxP<FT>& F, FT u0, FT t0, FT q0) {
+    const ThermoC<FT>& c = P.th;
+    {
       // conductive flux balance through the slab (row a7)
       FT Tb = P.io.T0 - P.io.slope * in.S_ice + P.T_offset;
       FT Tm = P.io.T0 + P.T_offset;
@@ -423,6 +534,12 @@ template <typename FT, int SURF> struct CellSolver {
       Ts = M<FT>::min(Ts + adT * sgn, Tm);
       S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
     }
+  }
+  __device__ __forceinline__ void pass_generic(const DevParams<FT>& P, const FluxP<FT>& F) {
+    const ThermoC<FT>& c = P.th;
+    const FT g = P.g, h = P.h, kappa = F.kappa;
+    const FT u0 = ustar, t0 = tstar, q0 = qstar;
+    if (SURF == 1 && F.itemp == COFLUX_TEMPERATURE_SKIN) skin_temperature(P, F, u0, t0, q0);
     const FT bstar = g / S.T_v * (t0 * (FT(1) + delta * S.q_vap) + delta * S.T_v * q0);
     if (ly) {
       FT zeta = MP::div(kappa * bstar * h, u0 * u0);
@@ -474,6 +591,10 @@ template <typename FT, int SURF> struct CellSolver {
         }
       }
     }
+    advance(F, u0, t0, q0);
+  }
+  // bookkeeping after a pass: iteration count, stop rule, Brent cycle detection
+  __device__ __forceinline__ void advance(const FluxP<FT>& F, FT u0, FT t0, FT q0) {
     ++it;
     if (fixed) {
       go = it < F.maxit;

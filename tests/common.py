@@ -13,7 +13,7 @@ QUERY_TIME = 1.37 * 3 * 3600.0   # exercises the time weights
 # nearly equal inputs (Δθ = θ_a − T_s, Δq = q_a − q_s, signed sums in the assembly), so a result near
 # zero carries an ABSOLUTE rounding error of a few ulp of the operands — i.e. a few ulp of the field's
 # own scale — no matter who computes it (measured: ≤ 8e-16·max|b| in Float64, ≤ 5e-7·max|b| in Float32
-# between oracle and CUDA, tools/parity_report.py).  The denominator is therefore floored at a
+# between oracle and CUDA, tests/diag/parity_report.py).  The denominator is therefore floored at a
 # fraction of the field's largest magnitude: 1e-3 in Float64 (absolute error ≤ 1e-15·max|b| ≈ 9 ulp)
 # and 1e-1 in Float32 (≤ 1e-6·max|b| ≈ 17 ulp).  Stated once here, used by every parity test.
 RTOL = {64: 1e-12, 32: 1e-5}

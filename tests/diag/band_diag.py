@@ -1,6 +1,6 @@
 """Diagnostic (GPU box): CUDA vs oracle on the first rows of the 1/12° grid — worst cells per field."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import climaocean.jl_b200 as cj

@@ -1,7 +1,7 @@
 """Diagnostic (run on the GPU box): per-field CUDA-vs-oracle error at several denominator floors,
 iteration-count agreement, and the cells carrying the largest errors."""
 import sys, os, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 from tests.common import make_case, oracle_update, gpu_update
