@@ -723,13 +723,18 @@ static bool force_v1() {
   static const bool f = [] { const char* e = std::getenv("COFLUX_FORCE_V1"); return e && e[0] == '1'; }();
   return f;
 }
-// Float64 stand-alone solves with a convergence stop rule run the lane-refill kernel (COFLUX_REFILL=0: one cell per
-// thread; measured at 1/12°, sea-ice solve: Float64 56.4 → 53.3 ms, Float32 18.3 → 22.1 ms, hence Float64 only)
+// The stand-alone solves run one cell per thread (flux_kernel).  COFLUX_REFILL=1 selects the lane-refill kernel instead
+// (flux_refill_kernel): measured at 1/12° on the sea-ice solve it only pays when a cell's pass is cheap relative to
+// popping a new cell — with the compact sea-ice pass, Brent cycle detection and the ψ tables: one cell per thread
+// 20.9 ms, refill with batches of 8 / 16 / 32 lanes 28.4 / 25.5 / 21.7 ms (`:default`), 34.2 vs 30.2 ms (`:ncar`).
+#ifndef COFLUX_REFILL_F32
+#define COFLUX_REFILL_F32 0
+#endif
 #ifndef COFLUX_REFILL_TILE
 #define COFLUX_REFILL_TILE 1024
 #endif
 static bool refill_v1() {
-  static const bool f = [] { const char* e = std::getenv("COFLUX_REFILL"); return !(e && e[0] == '0'); }();
+  static const bool f = [] { const char* e = std::getenv("COFLUX_REFILL"); return e && e[0] == '1'; }();
   return f;
 }
 template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
@@ -813,7 +818,7 @@ static int do_ao(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   if (tile_eligible<FT>(c)) {
     rc = launch_tile<FT, false, false>(c, a, st);
     if (rc) return rc;
-  } else if (refill_v1() && sizeof(FT) == 8 && dev_params<FT>(c).ao.stop_kind != COFLUX_STOP_FIXED_ITERATIONS) {
+  } else if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32) && dev_params<FT>(c).ao.stop_kind != COFLUX_STOP_FIXED_ITERATIONS) {
     flux_refill_kernel<FT, 0, COFLUX_REFILL_TILE><<<grid_for(a.ncell - a.cell0, COFLUX_REFILL_TILE), 128, 0, st>>>(a);
   } else {
     flux_kernel<FT, 0, false, true, false><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
@@ -850,7 +855,7 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   a.iconc = view2d(ice->concentration, 0, es);
   fill_interface_out<FT>(f, a);
   a.Ttop_out = view2d(ice->top_temperature, 0, es);
-  if (refill_v1() && sizeof(FT) == 8) flux_refill_kernel<FT, 1, COFLUX_REFILL_TILE><<<grid_for(a.ncell, COFLUX_REFILL_TILE), 128, 0, st>>>(a);
+  if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32)) flux_refill_kernel<FT, 1, COFLUX_REFILL_TILE><<<grid_for(a.ncell, COFLUX_REFILL_TILE), 128, 0, st>>>(a);
   else flux_kernel<FT, 1, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
   return check_launch(c, 1);
 }

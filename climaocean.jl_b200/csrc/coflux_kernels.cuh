@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
 // loads / stores of a popped cell are not coalesced (≈ 25 words per cell against ≈ 29 passes × 2 000 instructions).
 // Arithmetic per cell is exactly that of flux_kernel → bit-identical results.
 // ---------------------------------------------------------------------------------------------
+#ifndef COFLUX_REFILL_BATCH
+#define COFLUX_REFILL_BATCH 8
+#endif
 template <typename FT, int SURF, int TILE>
 __global__ void __launch_bounds__(128) flux_refill_kernel(const __grid_constant__ FluxArgs<FT> a) {
   __shared__ int head;
@@ -305,11 +308,23 @@ __global__ void __launch_bounds__(128) flux_refill_kernel(const __grid_constant_
       store(act);
     }
   };
+  // Finished lanes store and refill TOGETHER: popping a cell costs ≈ 600 instructions (loads, both thermodynamic states)
+  // and a lane finishes every ≈ 29 passes, so refilling each lane on its own would run that code in almost every pass of
+  // the warp with one lane active.  A finished lane therefore waits until COFLUX_REFILL_BATCH lanes are waiting (or nobody
+  // is iterating any more); the wait idles ≈ 4 of 32 lanes, the batching divides the refill cost by the batch size.
+  bool waiting = false;          // this lane's cell has converged, its result is still in registers
   pop();
-  while (__any_sync(0xffffffffu, cur >= 0)) {
-    if (cur >= 0) {
+  for (;;) {
+    const bool iterating = (cur >= 0) && !waiting;
+    if (iterating) {
       s.pass(P, F);
-      if (!s.go) { store(true); pop(); }
+      if (!s.go) waiting = true;
+    }
+    const unsigned want = __ballot_sync(0xffffffffu, waiting);
+    const unsigned busy = __ballot_sync(0xffffffffu, (cur >= 0) && !waiting);
+    if (want == 0u && busy == 0u) break;
+    if (__popc(want) >= COFLUX_REFILL_BATCH || busy == 0u) {
+      if (waiting) { store(true); waiting = false; pop(); }
     }
   }
 }

@@ -11,11 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "b6_t384": [],
-    "b7_t256": ["COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=7"],
-    "b7_t320": ["COFLUX_TILE_CELLS=320", "COFLUX_TILE_MIN_BLOCKS=7"],
-    "b8_t256": ["COFLUX_TILE_CELLS=256", "COFLUX_TILE_MIN_BLOCKS=8"],
-    "b5_t448": ["COFLUX_TILE_CELLS=448", "COFLUX_TILE_MIN_BLOCKS=5"],
+    "batch16": ["COFLUX_REFILL_BATCH=16"],
+    "batch24": ["COFLUX_REFILL_BATCH=24"],
+    "batch32": ["COFLUX_REFILL_BATCH=32"],
+    "batch16_f32": ["COFLUX_REFILL_BATCH=16", "COFLUX_REFILL_F32=1"],
+    "batch16_t2048": ["COFLUX_REFILL_BATCH=16", "COFLUX_REFILL_TILE=2048"],
 }
 
 
@@ -42,7 +42,7 @@ def run(args):
             continue
         env = dict(os.environ, COFLUX_LIB=os.path.join(VDIR, name))
         print(f"--- {name}", flush=True)
-        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_bench.py")] + args, env=env)
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", os.environ.get("AB_SCRIPT", "quick_bench.py"))] + args, env=env)
 
 
 if __name__ == "__main__":
