@@ -418,47 +418,47 @@ template <typename FT, int SURF> struct CellSolver {
     in = in_;
     const ThermoC<FT>& c = P.th;
     const FT g = P.g, h = P.h;
-  atm = phase_equil_pTq<FT, MP>(c, in.pa, in.Ta, in.qa);
-  if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = in.ua - in.us; dv = in.va - in.vs; }
-  else { du = in.ua; dv = in.va; }
-  x = FT(1);
-  if (SURF == 0) { FT s = MP::div(in.So, FT(1000)); x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s); }
-  theta_a = in.Ta + MP::div(g * h, atm.cp_m);
-  delta = c.eps - FT(1);
-  du2dv2 = du * du + dv * dv;
+    atm = phase_equil_pTq<FT, MP>(c, in.pa, in.Ta, in.qa);
+    if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = in.ua - in.us; dv = in.va - in.vs; }
+    else { du = in.ua; dv = in.va; }
+    x = FT(1);
+    if (SURF == 0) { FT s = MP::div(in.So, FT(1000)); x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s); }
+    theta_a = in.Ta + MP::div(g * h, atm.cp_m);
+    delta = c.eps - FT(1);
+    du2dv2 = du * du + dv * dv;
 
-  Ts = in.Ts0;
-  S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
+    Ts = in.Ts0;
+    S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
 
-  ustar = F.init; tstar = F.init; qstar = F.init;
-  ly = (F.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER);
-  U_ly = FT(0); rcdn_ly = FT(0);
-  lnh10 = ly ? M<FT>::log(h / FT(10)) : FT(0);
-  if (ly) {
-    U_ly = M<FT>::max(MP::sqrt(du2dv2), F.ly_umin);
-    FT cdn = ly_cdn<FT, MP>(U_ly);
-    FT rcdn = MP::sqrt(cdn);
-    FT chn = ((S.dtheta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
-    FT cen = FT(34.6e-3) * rcdn;
-    rcdn_ly = rcdn;
-    ustar = rcdn * U_ly; tstar = MP::div(chn, rcdn) * S.dtheta; qstar = MP::div(cen, rcdn) * S.dq;
-  }
+    ustar = F.init; tstar = F.init; qstar = F.init;
+    ly = (F.formulation == COFLUX_FLUXES_COEFFICIENT_LARGE_YEAGER);
+    U_ly = FT(0); rcdn_ly = FT(0);
+    lnh10 = ly ? M<FT>::log(h / FT(10)) : FT(0);
+    if (ly) {
+      U_ly = M<FT>::max(MP::sqrt(du2dv2), F.ly_umin);
+      FT cdn = ly_cdn<FT, MP>(U_ly);
+      FT rcdn = MP::sqrt(cdn);
+      FT chn = ((S.dtheta > FT(0)) ? FT(18e-3) : FT(32.7e-3)) * rcdn;
+      FT cen = FT(34.6e-3) * rcdn;
+      rcdn_ly = rcdn;
+      ustar = rcdn * U_ly; tstar = MP::div(chn, rcdn) * S.dtheta; qstar = MP::div(cen, rcdn) * S.dq;
+    }
 
-  fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
-  it = 0;
-  go = fixed ? (F.maxit > 0) : true;
-  su = ustar; st = tstar; sq = qstar; sT = Ts; sr = rcdn_ly;   // Brent snapshot, refreshed after 1, 2, 4, … passes
-  snap_it = 0; window = 1; stop_at = -1;
-  // the sea-ice parameter sets of omip_simulation.jl:52-69,91-113 (similarity theory, fixed roughness lengths, standard
-  // log profile, SHEBA or Large–Yeager ψ) take the compact pass_ice(): ψ from the tables, ln(h/ℓ) hoisted
-  ice_fast = COFLUX_PSI_TABLES_V1 && SURF == 1 && !ly && F.form == COFLUX_PROFILE_LOGARITHMIC &&
-             F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
-             (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) &&
-             F.beta >= FT(0) && F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0);
-  lnh_lu = lnh_lt = lnh_lq = FT(0);
-  if (ice_fast) {
-    lnh_lu = M<FT>::log(h / F.mr.fixed); lnh_lt = M<FT>::log(h / F.tr.fixed); lnh_lq = M<FT>::log(h / F.qr.fixed);
-  }
+    fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+    it = 0;
+    go = fixed ? (F.maxit > 0) : true;
+    su = ustar; st = tstar; sq = qstar; sT = Ts; sr = rcdn_ly;   // Brent snapshot, refreshed after 1, 2, 4, … passes
+    snap_it = 0; window = 1; stop_at = -1;
+    // the sea-ice parameter sets of omip_simulation.jl:52-69,91-113 (similarity theory, fixed roughness lengths, standard
+    // log profile, SHEBA or Large–Yeager ψ) take the compact pass_ice(): ψ from the tables, ln(h/ℓ) hoisted
+    ice_fast = COFLUX_PSI_TABLES_V1 && SURF == 1 && !ly && F.form == COFLUX_PROFILE_LOGARITHMIC &&
+               F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
+               (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) &&
+               F.beta >= FT(0) && F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0);
+    lnh_lu = lnh_lt = lnh_lq = FT(0);
+    if (ice_fast) {
+      lnh_lu = M<FT>::log(h / F.mr.fixed); lnh_lt = M<FT>::log(h / F.tr.fixed); lnh_lq = M<FT>::log(h / F.qr.fixed);
+    }
   }
 
   // ψ of the ice-solve parameter sets at one argument: Paulson table (ζ < 0), SHEBA table or −5ζ (ζ ≥ 0); the
@@ -514,26 +514,24 @@ template <typename FT, int SURF> struct CellSolver {
   // conductive flux balance through the slab (row a7): T_s relaxes towards the balance temperature, clamped
   __device__ __forceinline__ void skin_temperature(const DevParams<FT>& P, const FluxP<FT>& F, FT u0, FT t0, FT q0) {
     const ThermoC<FT>& c = P.th;
-    {
-      // conductive flux balance through the slab (row a7)
-      FT Tb = P.io.T0 - P.io.slope * in.S_ice + P.T_offset;
-      FT Tm = P.io.T0 + P.T_offset;
-      FT Ls = c.LH_s0 + (c.cp_v - c.cp_i) * (in.Ta - c.T_0);
-      FT Qu = P.emis_i * P.sigma * Ts * Ts * Ts * Ts;
-      FT Qd = -(FT(1) - in.albedo) * in.Qs - P.emis_i * in.Ql;
-      FT Qc = -atm.rho * atm.cp_m * u0 * t0;
-      FT Qv = -atm.rho * Ls * u0 * q0;
-      FT Qa = Qv + Qu + Qc + Qd;
-      FT Tstar = Tb - Qa * in.h_ice / P.io.k_ice;
-      if (Tstar != Tstar) Tstar = Ts;
-      Tstar = M<FT>::max(FT(0), Tstar);
-      FT Tnew = (in.h_ice >= P.io.h_c) ? Tstar : Tb;
-      FT dT = Tnew - Ts;
-      FT adT = M<FT>::min(F.skin_max_dT, M<FT>::abs(dT));
-      FT sgn = (dT > FT(0)) ? FT(1) : ((dT < FT(0)) ? FT(-1) : FT(0));
-      Ts = M<FT>::min(Ts + adT * sgn, Tm);
-      S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
-    }
+    // conductive flux balance through the slab (row a7)
+    FT Tb = P.io.T0 - P.io.slope * in.S_ice + P.T_offset;
+    FT Tm = P.io.T0 + P.T_offset;
+    FT Ls = c.LH_s0 + (c.cp_v - c.cp_i) * (in.Ta - c.T_0);
+    FT Qu = P.emis_i * P.sigma * Ts * Ts * Ts * Ts;
+    FT Qd = -(FT(1) - in.albedo) * in.Qs - P.emis_i * in.Ql;
+    FT Qc = -atm.rho * atm.cp_m * u0 * t0;
+    FT Qv = -atm.rho * Ls * u0 * q0;
+    FT Qa = Qv + Qu + Qc + Qd;
+    FT Tstar = Tb - Qa * in.h_ice / P.io.k_ice;
+    if (Tstar != Tstar) Tstar = Ts;
+    Tstar = M<FT>::max(FT(0), Tstar);
+    FT Tnew = (in.h_ice >= P.io.h_c) ? Tstar : Tb;
+    FT dT = Tnew - Ts;
+    FT adT = M<FT>::min(F.skin_max_dT, M<FT>::abs(dT));
+    FT sgn = (dT > FT(0)) ? FT(1) : ((dT < FT(0)) ? FT(-1) : FT(0));
+    Ts = M<FT>::min(Ts + adT * sgn, Tm);
+    S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
   }
   __device__ __forceinline__ void pass_generic(const DevParams<FT>& P, const FluxP<FT>& F) {
     const ThermoC<FT>& c = P.th;
@@ -619,7 +617,7 @@ template <typename FT, int SURF> struct CellSolver {
         }
       }
     }
-    }
+  }
 
   __device__ __forceinline__ void finish(CellOut<FT>& out) const {
     out.ustar = ustar; out.tstar = tstar; out.qstar = qstar; out.Ts = Ts;
