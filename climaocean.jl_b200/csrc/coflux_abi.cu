@@ -737,6 +737,20 @@ static bool refill_v1() {
   static const bool f = [] { const char* e = std::getenv("COFLUX_REFILL"); return e && e[0] == '1'; }();
   return f;
 }
+// The sea-ice parameter sets that take CellSolver::pass_ice run the tile form of the solve (COFLUX_ICE_TILE=0: one cell
+// per thread).  The conditions are those of CellSolver::init's `ice_fast`, plus a skin temperature and a convergence stop.
+#ifndef COFLUX_ICE_TILE_CELLS
+#define COFLUX_ICE_TILE_CELLS 256
+#endif
+template <typename FT> static bool ice_tile_eligible(const coflux_ctx* c) {
+  static const bool off = [] { const char* e = std::getenv("COFLUX_ICE_TILE"); return e && e[0] == '0'; }();
+  const FluxP<FT>& F = dev_params<FT>(c).ai;
+  return !off && COFLUX_PSI_TABLES_V1 && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.form == COFLUX_PROFILE_LOGARITHMIC &&
+         F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
+         (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) && F.beta >= FT(0) &&
+         F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0) && F.itemp == COFLUX_TEMPERATURE_SKIN &&
+         F.stop_kind == COFLUX_STOP_CONVERGENCE && F.maxit >= 1;
+}
 template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
   const FluxP<FT>& F = dev_params<FT>(c).ao;
   return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1;
@@ -855,8 +869,21 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   a.iconc = view2d(ice->concentration, 0, es);
   fill_interface_out<FT>(f, a);
   a.Ttop_out = view2d(ice->top_temperature, 0, es);
-  if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32)) flux_refill_kernel<FT, 1, COFLUX_REFILL_TILE><<<grid_for(a.ncell, COFLUX_REFILL_TILE), 128, 0, st>>>(a);
-  else flux_kernel<FT, 1, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  if (ice_tile_eligible<FT>(c)) {
+    constexpr int TILE = COFLUX_ICE_TILE_CELLS;
+    auto kern = ice_tile_kernel<FT, TILE>;
+    const size_t smem = sizeof(IceTileSmem<FT, TILE>);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    kern<<<grid_for(a.ncell, TILE), 128, smem, st>>>(a);
+  } else if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32)) {
+    flux_refill_kernel<FT, 1, COFLUX_REFILL_TILE><<<grid_for(a.ncell, COFLUX_REFILL_TILE), 128, 0, st>>>(a);
+  } else {
+    flux_kernel<FT, 1, false, true, false><<<grid_for(a.ncell, 128), 128, 0, st>>>(a);
+  }
   return check_launch(c, 1);
 }
 extern "C" int coflux_atmosphere_sea_ice_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,

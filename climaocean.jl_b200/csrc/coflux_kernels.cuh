@@ -330,6 +330,159 @@ __global__ void __launch_bounds__(128) flux_refill_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tile form of the atmosphere–sea-ice solve (row a7) for the sea-ice parameter sets that take CellSolver::pass_ice
+// (skin temperature, fixed roughness lengths, SHEBA / Large–Yeager ψ).  Same three phases as flux_tile_kernel:
+//   A  per cell, all lanes busy: loads and CellSolver::init (both thermodynamic states — the expensive part of starting a
+//      cell); the 16 numbers a pass needs go to shared memory, the cell is queued;
+//   B  lanes pop a cell (17 shared-memory loads rebuild the solver), iterate pass() until it stops, write the state
+//      back and pop the next one — so a warp is not held up by its slowest cell (29 passes on average, up to 100);
+//   C  per cell: fluxes and coalesced stores.
+// Every arithmetic operation is CellSolver's, i.e. results are bit-identical to flux_kernel<FT,1,…>.
+// ---------------------------------------------------------------------------------------------
+template <typename FT, int TILE> struct IceTileSmem {
+  FT Ta[TILE], pa[TILE], Qs[TILE], Ql[TILE], S_ice[TILE], h_ice[TILE], albedo[TILE];   // CellIn fields a pass reads
+  FT rho[TILE], cp[TILE], qv[TILE], theta_a[TILE], du2dv2[TILE];                        // hoisted by init()
+  FT us[TILE], ts[TILE], qs[TILE], Ts[TILE];                                             // state / result
+  int it[TILE];
+  unsigned short queue[TILE];
+  int n_queued, head;
+};
+template <typename FT, int TILE>
+__global__ void __launch_bounds__(128) ice_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IceTileSmem<FT, TILE>& sm = *reinterpret_cast<IceTileSmem<FT, TILE>*>(smem_raw);
+  const DevParams<FT>& P = a.P;
+  const FluxP<FT>& F = P.ai;
+  const int tid = threadIdx.x;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
+  if (tid == 0) { sm.n_queued = 0; sm.head = 0; }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase A
+  for (int cidx = tid; cidx < TILE; cidx += 128) {
+    const long long idx = tile0 + cidx;
+    if (idx >= a.ncell) { sm.it[cidx] = -1; continue; }
+    const int jj = (int)(idx / a.nxr);
+    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const int i = ii - a.ring, j = jj - a.ring;
+    CellIn<FT> in;
+    in.ua = ldg<FT>(a.xu, i, j); in.va = ldg<FT>(a.xv, i, j); in.Ta = ldg<FT>(a.xT, i, j); in.pa = ldg<FT>(a.xp, i, j);
+    in.qa = ldg<FT>(a.xq, i, j); in.Qs = ldg<FT>(a.xQs, i, j); in.Ql = ldg<FT>(a.xQl, i, j);
+    in.us = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+    in.vs = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+    in.Ts0 = ldg<FT>(a.oT, i, j) + P.T_offset;
+    in.So = FT(0);
+    in.h_ice = ldg<FT>(a.ih, i, j);
+    in.S_ice = ldg<FT>(a.iS, i, j);
+    in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+    const FT conc = ldg<FT>(a.iconc, i, j);
+    const bool act = is_active(a.mask, i, j) && (conc > FT(0)) && (in.h_ice > FT(0));
+    FT us = FT(0), ts = FT(0), qs = FT(0), Ts = in.Ts0;
+    int it = 0;
+    if (act) {
+      CellSolver<FT, 1> s;
+      s.init(P, F, in);
+      us = s.ustar; ts = s.tstar; qs = s.qstar; Ts = s.Ts;
+      sm.Ta[cidx] = in.Ta; sm.pa[cidx] = in.pa; sm.Qs[cidx] = in.Qs; sm.Ql[cidx] = in.Ql; sm.S_ice[cidx] = in.S_ice;
+      sm.h_ice[cidx] = in.h_ice; sm.albedo[cidx] = in.albedo;
+      sm.rho[cidx] = s.atm.rho; sm.cp[cidx] = s.atm.cp_m; sm.qv[cidx] = s.atm.q_vap; sm.theta_a[cidx] = s.theta_a;
+      sm.du2dv2[cidx] = s.du2dv2;
+      if (s.go) sm.queue[atomicAdd(&sm.n_queued, 1)] = (unsigned short)cidx;
+    } else {
+      sm.rho[cidx] = FT(0); sm.cp[cidx] = FT(0); sm.Ta[cidx] = in.Ta;
+      it = -2;                       // inactive: phase C writes zeros
+    }
+    sm.us[cidx] = us; sm.ts[cidx] = ts; sm.qs[cidx] = qs; sm.Ts[cidx] = Ts; sm.it[cidx] = it;
+  }
+  __syncthreads();
+  const int n_total = sm.n_queued;
+
+  // ------------------------------------------------------------------ phase B: lane refill
+  {
+    CellSolver<FT, 1> s;
+    int slot = -1;
+    // everything init() derives from the parameters alone
+    {
+      CellIn<FT> z{};
+      z.Ta = FT(280); z.pa = FT(1e5); z.qa = FT(1e-3); z.Ts0 = FT(270); z.h_ice = FT(1);
+      s.in = z;
+      s.x = FT(1);
+      s.delta = P.th.eps - FT(1);
+      s.ly = false; s.U_ly = FT(0); s.rcdn_ly = FT(0); s.lnh10 = FT(0);
+      s.fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+      s.ice_fast = true;
+      s.lnh_lu = M<FT>::log(P.h / F.mr.fixed); s.lnh_lt = M<FT>::log(P.h / F.tr.fixed); s.lnh_lq = M<FT>::log(P.h / F.qr.fixed);
+      s.du = s.dv = FT(0);
+    }
+    auto pop = [&]() {
+      const int pos = atomicAdd(&sm.head, 1);
+      slot = -1;
+      if (pos < n_total) {
+        slot = sm.queue[pos];
+        s.in.Ta = sm.Ta[slot]; s.in.pa = sm.pa[slot]; s.in.Qs = sm.Qs[slot]; s.in.Ql = sm.Ql[slot]; s.in.S_ice = sm.S_ice[slot];
+        s.in.h_ice = sm.h_ice[slot]; s.in.albedo = sm.albedo[slot];
+        s.atm.rho = sm.rho[slot]; s.atm.cp_m = sm.cp[slot]; s.atm.q_vap = sm.qv[slot]; s.theta_a = sm.theta_a[slot];
+        s.du2dv2 = sm.du2dv2[slot];
+        s.ustar = sm.us[slot]; s.tstar = sm.ts[slot]; s.qstar = sm.qs[slot]; s.Ts = sm.Ts[slot];
+        s.it = 0; s.go = true;
+        s.su = s.ustar; s.st = s.tstar; s.sq = s.qstar; s.sT = s.Ts; s.sr = s.rcdn_ly;
+        s.snap_it = 0; s.window = 1; s.stop_at = -1;
+      }
+    };
+    pop();
+    while (__any_sync(0xffffffffu, slot >= 0)) {
+      if (slot >= 0) {
+        s.pass(P, F);
+        if (!s.go) {
+          sm.us[slot] = s.ustar; sm.ts[slot] = s.tstar; sm.qs[slot] = s.qstar; sm.Ts[slot] = s.Ts; sm.it[slot] = s.it;
+          pop();
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase C
+  for (int cidx = tid; cidx < TILE; cidx += 128) {
+    const long long idx = tile0 + cidx;
+    if (idx >= a.ncell) continue;
+    const int jj = (int)(idx / a.nxr);
+    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const int i = ii - a.ring, j = jj - a.ring;
+    const int it = sm.it[cidx];
+    const bool act = it != -2;
+    const FT Tunits = ldg<FT>(a.oT, i, j);
+    FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0), Tsout = Tunits, us = FT(0), ts = FT(0), qs = FT(0);
+    if (act) {
+      us = sm.us[cidx]; ts = sm.ts[cidx]; qs = sm.qs[cidx];
+      const FT ua = ldg<FT>(a.xu, i, j), va = ldg<FT>(a.xv, i, j);
+      FT du, dv;
+      if (F.velocity == COFLUX_VELOCITY_RELATIVE) {
+        du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+        dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+      } else { du = ua; dv = va; }
+      const FT rho = sm.rho[cidx], cp = sm.cp[cidx], Ta = sm.Ta[cidx];
+      const FT dU = M<FT>::sqrt(du * du + dv * dv);
+      const FT taux = (dU == FT(0)) ? dU : -us * us * du / dU;
+      const FT tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
+      const ThermoC<FT>& c = P.th;
+      const FT LH = c.LH_s0 + (c.cp_v - c.cp_i) * (Ta - c.T_0);
+      Qv = -rho * us * qs * LH;
+      Qc = -rho * cp * us * ts;
+      Fv = -rho * us * qs;
+      rtx = rho * taux; rty = rho * tauy;
+      Tsout = sm.Ts[cidx] - P.T_offset;
+    }
+    stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
+    stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tsout);
+    stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
+    stg<FT>(a.Ttop_out, i, j, Tsout);
+    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? it : 0;
+    if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // centre → face momentum fluxes (A9)
 // ---------------------------------------------------------------------------------------------
 // by-products of the net fluxes for the ocean mixing closures (KPP/kpp_surface_forcing.jl:18-29,
