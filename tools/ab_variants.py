@@ -11,11 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "batch16": ["COFLUX_REFILL_BATCH=16"],
-    "batch24": ["COFLUX_REFILL_BATCH=24"],
-    "batch32": ["COFLUX_REFILL_BATCH=32"],
-    "batch16_f32": ["COFLUX_REFILL_BATCH=16", "COFLUX_REFILL_F32=1"],
-    "batch16_t2048": ["COFLUX_REFILL_BATCH=16", "COFLUX_REFILL_TILE=2048"],
+    "t256_b4": [],
+    "t384_b4": ["COFLUX_ICE_TILE_CELLS=384"],
+    "t512_b3": ["COFLUX_ICE_TILE_CELLS=512", "COFLUX_ICE_MIN_BLOCKS=3"],
+    "t256_b5": ["COFLUX_ICE_MIN_BLOCKS=5"],
+    "t256_b6": ["COFLUX_ICE_MIN_BLOCKS=6"],
 }
 
 
