@@ -773,15 +773,17 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   constexpr int TILE = TileTraits<FT, SPEC>::TILE;
   auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, TILE, SPEC>;
   const size_t smem = sizeof(TileSmem<FT, TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
-  static bool configured = false;     // per instantiation
-  if (!configured) {
+  static unsigned long long configured = 0;     // per instantiation, one bit per device (function attributes are per device)
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!(configured >> (dev & 63) & 1ull)) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // shared-memory carve-out: exactly what COFLUX_TILE_MIN_BLOCKS resident CTAs need (+1 KB each of system use); the rest
     // of the 256 KB stays L1, which holds the psi table rows and the gathered atmosphere tiles
     const int min_blocks = TileTraits<FT, SPEC>::MIN_BLOCKS;
     const int carve = (int)((min_blocks * (smem + 1024 + 2560) * 100 + 228 * 1024 - 1) / (228 * 1024));   // + static log/exp tables
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
-    configured = true;
+    configured |= 1ull << (dev & 63);
   }
   kern<<<grid_for(a.ncell - a.cell0, TILE), 128, smem, st>>>(a);
   return COFLUX_OK;
@@ -873,10 +875,12 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
     constexpr int TILE = COFLUX_ICE_TILE_CELLS;
     auto kern = ice_tile_kernel<FT, TILE>;
     const size_t smem = sizeof(IceTileSmem<FT, TILE>);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // one bit per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!(configured >> (dev & 63) & 1ull)) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
+      configured |= 1ull << (dev & 63);
     }
     kern<<<grid_for(a.ncell, TILE), 128, smem, st>>>(a);
   } else if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32)) {

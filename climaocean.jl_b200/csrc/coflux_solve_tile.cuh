@@ -310,9 +310,6 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 #ifndef COFLUX_LEAN_F32
 #define COFLUX_LEAN_F32 1
 #endif
-#ifndef COFLUX_PSI_PREFETCH
-#define COFLUX_PSI_PREFETCH 0
-#endif
 struct LeanTabs { const double* lg; const double* ex; };     // shared-memory log / exp tables (Float64 only)
 template <typename FT> struct LeanCell { FT U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
 template <typename FT> struct D3 { FT u, t, q; };
