@@ -479,15 +479,17 @@ template <typename FT, int SURF> struct CellSolver {
   __device__ __forceinline__ void pass_ice(const DevParams<FT>& P, const FluxP<FT>& F) {
     const FT g = P.g, h = P.h, kappa = F.kappa;
     const FT u0 = ustar, t0 = tstar, q0 = qstar;
+    if (!(u0 > FT(0))) { pass_generic(P, F); return; }   // u★ = 0 (after a zero-scales guard): the generic pass knows the
+                                                         // limits — decided BEFORE the skin update, which it does itself
     if (F.itemp == COFLUX_TEMPERATURE_SKIN) skin_temperature(P, F, u0, t0, q0);
     const FT bstar = MP::div(g, S.T_v) * (t0 * (FT(1) + delta * S.q_vap) + delta * S.T_v * q0);
     const FT Jb = -u0 * bstar;
     FT UG = F.ugmin;
     if (Jb > FT(0)) UG = M<FT>::max(F.beta * LMath<FT>::cbrt(Jb * P.hbl), F.ugmin);
     const FT U = MP::sqrt(du2dv2 + UG * UG);
-    if (U == FT(0) || !(u0 > FT(0))) {
-      if (U == FT(0)) { ustar = tstar = qstar = FT(0); advance(F, u0, t0, q0); }
-      else pass_generic(P, F);                       // u★ = 0: the generic pass knows the limits
+    if (U == FT(0)) {                                  // calm-cell guard, as in the generic pass
+      ustar = tstar = qstar = FT(0);
+      advance(F, u0, t0, q0);
       return;
     }
     const FT invL = MP::div(kappa * bstar, u0 * u0);  // 1/L★ (0 when b★ = 0)
