@@ -745,7 +745,8 @@ static bool refill_v1() {
 template <typename FT> static bool ice_tile_eligible(const coflux_ctx* c) {
   static const bool off = [] { const char* e = std::getenv("COFLUX_ICE_TILE"); return e && e[0] == '0'; }();
   const FluxP<FT>& F = dev_params<FT>(c).ai;
-  return !off && COFLUX_PSI_TABLES_V1 && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.form == COFLUX_PROFILE_LOGARITHMIC &&
+  return !off && COFLUX_PSI_TABLES_V1 && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY &&
+         (COFLUX_ICE_COARE || F.form == COFLUX_PROFILE_LOGARITHMIC) &&
          F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
          (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) && F.beta >= FT(0) &&
          F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0) && F.itemp == COFLUX_TEMPERATURE_SKIN &&

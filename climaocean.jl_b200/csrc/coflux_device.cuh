@@ -245,6 +245,10 @@ template <> struct PsiTabs<float> {
   static __device__ __forceinline__ const float (*paulson())[2][8] { return COFLUX_PSI_PAULSON_F32; }
   static __device__ __forceinline__ const float (*sheba())[2][8] { return COFLUX_PSI_SHEBA_F32; }
 };
+#ifndef COFLUX_ICE_COARE
+#define COFLUX_ICE_COARE 0            /* 1: the compact sea-ice pass also takes the COARE log form (`:corrected`, `:ncar` ice;
+                                         measured 13.0 / 12.2 ms instead of 34 ms — needs one GPU parity run, profiles/README.md) */
+#endif
 #ifndef COFLUX_PSI_TABLES_V1
 #define COFLUX_PSI_TABLES_V1 1      /* Paulson / SHEBA ψ from tables in the one-cell-per-thread and refill solves */
 #endif
@@ -451,7 +455,7 @@ template <typename FT, int SURF> struct CellSolver {
     snap_it = 0; window = 1; stop_at = -1;
     // the sea-ice parameter sets of omip_simulation.jl:52-69,91-113 (similarity theory, fixed roughness lengths, standard
     // log profile, SHEBA or Large–Yeager ψ) take the compact pass_ice(): ψ from the tables, ln(h/ℓ) hoisted
-    ice_fast = COFLUX_PSI_TABLES_V1 && SURF == 1 && !ly && F.form == COFLUX_PROFILE_LOGARITHMIC &&
+    ice_fast = COFLUX_PSI_TABLES_V1 && SURF == 1 && !ly && (COFLUX_ICE_COARE || F.form == COFLUX_PROFILE_LOGARITHMIC) &&
                F.mr.kind == COFLUX_ROUGHNESS_FIXED && F.tr.kind == COFLUX_ROUGHNESS_FIXED && F.qr.kind == COFLUX_ROUGHNESS_FIXED &&
                (F.stability == COFLUX_STABILITY_SHEBA_PAULSON || F.stability == COFLUX_STABILITY_LARGE_YEAGER) &&
                F.beta >= FT(0) && F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0);
@@ -496,12 +500,17 @@ template <typename FT, int SURF> struct CellSolver {
     const FT zeta = h * invL;
     const int stab = F.stability;
     const FT psi_hm = psi_ice(stab, zeta, 0), psi_hs = psi_ice(stab, zeta, 1);
-    const FT prof_u = (lnh_lu - psi_hm) + psi_ice(stab, F.mr.fixed * invL, 0);
+    const bool logform = (F.form == COFLUX_PROFILE_LOGARITHMIC);     // the COARE form drops the ψ(ℓ/L★) terms
+    FT prof_u = lnh_lu - psi_hm;
+    if (logform) prof_u += psi_ice(stab, F.mr.fixed * invL, 0);
     if (!(prof_u > FT(0))) {
       ustar = tstar = qstar = FT(0);
     } else {
-      const FT prof_q = (lnh_lq - psi_hs) + psi_ice(stab, F.qr.fixed * invL, 1);
-      const FT prof_t = (lnh_lt - psi_hs) + psi_ice(stab, F.tr.fixed * invL, 1);
+      FT prof_q = lnh_lq - psi_hs, prof_t = lnh_lt - psi_hs;
+      if (logform) {
+        prof_q += psi_ice(stab, F.qr.fixed * invL, 1);
+        prof_t += psi_ice(stab, F.tr.fixed * invL, 1);
+      }
       const FT chi_u = MP::div(kappa, prof_u);
       const FT chi_q = (prof_q > FT(0)) ? MP::div(kappa, prof_q) : FT(0);
       const FT chi_t = (prof_t > FT(0)) ? MP::div(kappa, prof_t) : FT(0);
