@@ -1,38 +1,37 @@
 // coflux_solve_tile.cuh — the production atmosphere–ocean flux kernel (similarity theory, bulk
-// interface temperature), organised to keep the FP64 pipe busy.
+// interface temperature).
 //
-// The v1 kernel (coflux_kernels.cuh::flux_kernel, still used for the Large–Yeager and sea-ice
-// variants) runs one cell per thread start to finish.  Its ncu profile (profiles/r01_*_v1_*) shows
-// what limits it: 21 of 32 lanes active on average (cells of one warp need 9…25 iterations and take
-// different ψ branches), 128 registers → 16 warps/SM, FP64 pipe 37 % busy.  This kernel splits the
-// work of a tile of TILE cells into three convergent phases separated by __syncthreads():
+// The one-cell-per-thread kernel (coflux_kernels.cuh::flux_kernel, still used for the Large–Yeager solve and for
+// parameter sets this kernel is not eligible for) showed what limits a straightforward mapping: 21 of 32 lanes active on
+// average (cells of one warp need 9…27 passes and take different ψ branches), 128 registers → 16 warps/SM.  This
+// kernel splits the work of a tile of TILE cells into three convergent phases separated by __syncthreads():
 //
-//   A  per cell: coalesced loads, atmosphere interpolation, exchange-state stores, both
-//      thermodynamic states, and the FIRST similarity iteration (which is uniform: the reference's
-//      initial guess u★=θ★=q★=1e-4 always produces a stable first pass).  The few scalars the
+//   A  per cell: coalesced loads, atmosphere interpolation, exchange-state stores, both thermodynamic states
+//      (COFLUX_TILE_PRE lock-step similarity passes could follow here; measured best: none).  The few scalars the
 //      iteration needs go to shared memory as a "task"; tasks are queued sorted by stability class.
 //   B  lanes pop tasks from the shared queue and iterate; a lane whose cell has converged writes
 //      its result back and immediately pops the next task ("lane refill"), so a warp has no idle
-//      lanes until the tile's queue drains, and — because the queue is class-sorted and the first
-//      iteration is already done — all lanes of a warp take the same ψ branch.
+//      lanes until the tile's queue drains, and — because the queue is class-sorted — the lanes of a warp take the
+//      same ψ branch.
 //   C  per cell: fluxes, net-flux assembly, coalesced stores.
 //
-// The iteration itself is algebraically the reference iteration (SURVEY Appendix A4–A6) with
-// rounding-level reformulations (each ≤ a few ulp, covered by the 1e-12 parity tests):
+// Two forms of the pass live here.  iterate_fast (any precision, any eligible parameter set; the exact fall-back of
+// the lean pass) is algebraically the reference iteration (SURVEY Appendix A4–A6) with rounding-level reformulations
+// (each ≤ a few ulp, covered by the 1e-12 parity tests):
 //   * 1/L★ = κ b★/u★² once, then ζ = h/L★ and ℓ/L★ are products (three divisions fewer);
 //   * g/T_v, 1+δq_v, δT_v hoisted out of the loop (exactly the same values);
 //   * the gustiness cube root is skipped when the buoyancy flux is ≤ 0 (the floor wins anyway);
 //   * Reynolds-scaling scalar roughness ℓ = A·R★^(−b): ln(h/ℓ) = ln(h/A) + b·ln R★ — one log instead
 //     of pow + log; ℓ itself (needed only inside ψ(ℓ/L)) from one exp;
 //   * the Edson ψ_u/ψ_θ pair at the same ζ shares √(1−15ζ), ζ²/(1+ζ²), exp(−0.35ζ); x^1.5 = x·√x;
-//   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ (virtually always after the transient) by the Taylor series of the same
-//     function (tools/gen_psi_taylor.py; |error| < 3e-18) instead of 5–7 transcendental calls;
-//   * the unstable Edson ψ_u, ψ_θ on −ζ ∈ [2⁻⁹, 2¹³) from a 44 KB table of degree-7 piecewise polynomials
+//   * ψ(ℓ/L) at |ℓ/L| ≤ 2⁻⁹ by the Taylor series of the same function (tools/gen_psi_taylor.py; |error| < 3e-18);
+//   * the unstable Edson ψ_u, ψ_θ on −ζ ∈ [2⁻⁹, 2¹³) from the table of degree-7 piecewise polynomials
 //     (16 per binade, tools/gen_psi_table.py; error ≤ 3e-16·max(1,|ψ|), i.e. rounding level) instead of
 //     4 log + 3 atan + 2 cbrt + 2 sqrt + 5 divisions; outside that range the exact formulas are used;
 //   * a limit cycle of the iterate (common in Float32, where Σ|Δ| < 1e-8 is below the resolution:
 //     8 % of the cells never "converge") is detected exactly (Brent) and the state the reference
 //     reaches at maxiter is produced after < period extra passes — bit-identical to iterating on.
+// iterate_lean (SPEC 1 / SPEC 2, both precisions) is the pass the hot loop runs; see its own header below.
 #pragma once
 #include "coflux_kernels.cuh"
 #include "coflux_psi_table.h"
@@ -296,7 +295,8 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 //   * the sign of b★ selects ONE of two blocks (unstable: gustiness cube root, ψ pair from the table, 5-term
 //     series for ψ(ℓ/L); stable: closed forms with the lean exp/√, 3-term series) — the queue is sorted by
 //     that sign, so warps do not diverge;
-//   * anything outside the domain of the short path (u★ ≤ 1e-30, a calm cell, −ζ outside [2⁻²⁰, 2¹³),
+//   * anything outside the domain of the short path (u★ ≤ 2⁻¹⁰⁰, a calm cell, −ζ outside [2⁻²⁰, 2¹³) — the table
+//     itself reaches down to 2⁻³⁰ —,
 //     an out-of-range buoyancy-flux argument) sets one flag, and the caller redoes the whole pass
 //     with the exact code behind a single by-value call (lean_cold_pass) — rare after the start-up transient;
 //   * all literals come from constant memory (LeanLit), not 64-bit immediates.
