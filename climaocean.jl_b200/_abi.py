@@ -268,6 +268,8 @@ def default_config(Nx, Ny, Nz, dtype=F64, flux_configuration="default", velocity
     cfg = Config()
     check(lib.coflux_default_config(C.byref(cfg), Nx, Ny, Nz, dtype), lib)
     vel = {"relative": VELOCITY_RELATIVE, "wind": VELOCITY_WIND}.get(velocity_formulation)
+    if flux_configuration == "default":
+        vel = VELOCITY_RELATIVE    # `:default` returns before velocity_formulation is looked at (omip_simulation.jl:127-133)
     if vel is None:
         raise ValueError(f"Unknown velocity_formulation: {velocity_formulation}. Options: :relative, :wind")
     check(lib.coflux_apply_flux_configuration(C.byref(cfg), flux_configuration.encode(), vel), lib)

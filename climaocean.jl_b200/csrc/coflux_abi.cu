@@ -234,9 +234,12 @@ extern "C" int coflux_default_config(coflux_config* cfg, int32_t Nx, int32_t Ny,
 
 extern "C" int coflux_apply_flux_configuration(coflux_config* cfg, const char* name, int32_t velocity) {
   if (!cfg || !name) return fail(COFLUX_ERR_INVALID_ARGUMENT, "NULL argument");
-  if (velocity != COFLUX_VELOCITY_RELATIVE && velocity != COFLUX_VELOCITY_WIND)
+  // `:default` returns before velocity_formulation is looked at (omip_simulation.jl:127-133): the ComponentInterfaces
+  // default (relative velocity) is used and the argument is neither validated nor applied
+  const bool is_default = !strcmp(name, "default");
+  if (!is_default && velocity != COFLUX_VELOCITY_RELATIVE && velocity != COFLUX_VELOCITY_WIND)
     return fail(COFLUX_ERR_INVALID_ARGUMENT, "Unknown velocity_formulation: %d. Options: relative (0), wind (1)", velocity);
-  if (!strcmp(name, "default")) {
+  if (is_default) {
     cfg->atmosphere_ocean = default_similarity_fluxes(COFLUX_STABILITY_EDSON);
     cfg->atmosphere_sea_ice = default_similarity_fluxes(COFLUX_STABILITY_SHEBA_PAULSON);
     cfg->atmosphere_sea_ice.interface_temperature = COFLUX_TEMPERATURE_SKIN;
@@ -283,8 +286,10 @@ extern "C" int coflux_apply_flux_configuration(coflux_config* cfg, const char* n
   } else {
     return fail(COFLUX_ERR_INVALID_ARGUMENT, "Unknown flux_configuration: %s. Options: default, corrected, ncar", name);
   }
-  cfg->atmosphere_ocean.velocity_formulation = velocity;
-  cfg->atmosphere_sea_ice.velocity_formulation = velocity;
+  if (!is_default) {
+    cfg->atmosphere_ocean.velocity_formulation = velocity;
+    cfg->atmosphere_sea_ice.velocity_formulation = velocity;
+  }
   return COFLUX_OK;
 }
 
@@ -651,6 +656,17 @@ static inline DCol view3d(const coflux_array& a, size_t esize) {
     if (!(cond)) return fail(COFLUX_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
   } while (0)
 
+// A descriptor must cover the cells a kernel touches: `need_i` / `need_j` halo cells on the low side (and, the parents
+// being symmetric, on the high side).  Guards against out-of-bounds access through a too-small Julia-side halo.
+static int check_halo(const coflux_array& a, int need_i, int need_j, const char* name) {
+  if (!a.ptr) return COFLUX_OK;
+  if ((a.stride_i != 0 && a.off_i < need_i) || (a.stride_j != 0 && a.off_j < need_j))
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: halo offsets (%d, %d) smaller than the (%d, %d) cells the surface kernels touch", name,
+                a.off_i, a.off_j, need_i, need_j);
+  return COFLUX_OK;
+}
+#define HALO(arr, ni, nj, name) do { int rc__ = check_halo(arr, ni, nj, name); if (rc__) return rc__; } while (0)
+
 static int check_launch(coflux_ctx* c, int n) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(COFLUX_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -678,6 +694,12 @@ static int fill_interp(const coflux_ctx* c, const coflux_atmos_series* in, doubl
   int rc = coflux_time_indices(in->times, in->Nt, in->time_indexing, in->cycle_period, time, &n1, &n2, &frac);
   if (rc) return rc;
   const size_t es = sizeof(FT);
+  {
+    const int ring = c->cfg.grid.ring;
+    HALO(in->fi, ring, ring, "fi"); HALO(in->fj, ring, ring, "fj"); HALO(in->cos_theta, ring, ring, "cos_theta"); HALO(in->sin_theta, ring, ring, "sin_theta");
+    const coflux_array* xs[8] = {&out->u, &out->v, &out->T, &out->p, &out->q, &out->Qs, &out->Ql, &out->Mp};
+    for (const coflux_array* p : xs) HALO(*p, ring, ring, "exchange state");
+  }
   a.su = view_series(in->u, n1, n2, es); a.sv = view_series(in->v, n1, n2, es); a.sT = view_series(in->T, n1, n2, es);
   a.sq = view_series(in->q, n1, n2, es); a.sp = view_series(in->p, n1, n2, es); a.sQs = view_series(in->Qs, n1, n2, es);
   a.sQl = view_series(in->Ql, n1, n2, es); a.srain = view_series(in->rain, n1, n2, es); a.ssnow = view_series(in->snow, n1, n2, es);
@@ -702,8 +724,19 @@ template <typename FT> static int fill_ocean(const coflux_ctx* c, const coflux_o
   REQUIRE(o->u.ptr && o->v.ptr && o->T.ptr && o->S.ptr, "ocean u, v, T, S are required");
   const int kN = c->cfg.grid.Nz - 1;
   const size_t es = sizeof(FT);
+  const int ring = c->cfg.grid.ring;
+  HALO(o->u, ring + 1, ring, "ocean u");     // u is averaged to the centre: read at i + 1 of the last ring cell
+  HALO(o->v, ring, ring + 1, "ocean v");
+  HALO(o->T, ring, ring, "ocean T"); HALO(o->S, ring, ring, "ocean S"); HALO(o->mask, ring, ring, "ocean mask");
   a.ou = view2d(o->u, kN, es); a.ov = view2d(o->v, kN, es); a.oT = view2d(o->T, kN, es); a.oS = view2d(o->S, kN, es);
   a.mask = view2d(o->mask, 0, 1);
+  return COFLUX_OK;
+}
+template <typename FT> static int check_interface_halos(const coflux_ctx* c, const coflux_interface_fluxes* f) {
+  const int ring = c->cfg.grid.ring;
+  const coflux_array* arr[10] = {&f->latent_heat, &f->sensible_heat, &f->water_vapor, &f->x_momentum, &f->y_momentum,
+                                 &f->interface_temperature, &f->friction_velocity, &f->temperature_scale, &f->humidity_scale, &f->iterations};
+  for (const coflux_array* p : arr) HALO(*p, ring, ring, "interface flux");
   return COFLUX_OK;
 }
 template <typename FT> static void fill_interface_out(coflux_interface_fluxes* f, FluxArgs<FT>& a) {
@@ -752,14 +785,11 @@ template <typename FT> static bool ice_tile_eligible(const coflux_ctx* c) {
          F.ugmin >= FT(0) && F.mr.fixed > FT(0) && F.tr.fixed > FT(0) && F.qr.fixed > FT(0) && F.itemp == COFLUX_TEMPERATURE_SKIN &&
          F.stop_kind == COFLUX_STOP_CONVERGENCE && F.maxit >= 1;
 }
-template <typename FT> static bool tile_eligible(const coflux_ctx* c) {
+// (the tile kernel parks ρ_a, c_p,m in the ρτx / ρτy output arrays between its phases: both must be present)
+template <typename FT> static bool tile_eligible(const coflux_ctx* c, const FluxArgs<FT>& a) {
   const FluxP<FT>& F = dev_params<FT>(c).ao;
-  return !force_v1() && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1;
+  return !force_v1() && a.rtx.p && a.rty.p && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1;
 }
-#ifndef COFLUX_TILE_CELLS
-#define COFLUX_TILE_CELLS 384
-#endif
-constexpr int COFLUX_TILE = COFLUX_TILE_CELLS;   // cells per CTA of the tile kernel (multiple of 128)
 // compile-time specialisation of the hot loop for the OMIP parameter sets (0 = generic)
 template <typename FT> static int tile_spec(const coflux_ctx* c) {
   const DevParams<FT>& P = dev_params<FT>(c);
@@ -771,22 +801,20 @@ template <typename FT> static int tile_spec(const coflux_ctx* c) {
   return 0;
 }
 template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_tile_spec(const FluxArgs<FT>& a, cudaStream_t st) {
-  constexpr int TILE = TileTraits<FT, SPEC>::TILE;
+  using TT = TileTraits<FT, SPEC>;
+  constexpr int TILE = TT::TILE;
   auto kern = flux_tile_kernel<FT, INTERP, ASSEMBLE, TILE, SPEC>;
-  const size_t smem = sizeof(TileSmem<FT, TILE, TileTraits<FT, SPEC>::VARNU, TileTraits<FT, SPEC>::LEAN>);
+  const size_t smem = sizeof(TileSmem<FT, TILE, TT::VARNU, TT::LEAN>);
   static unsigned long long configured = 0;     // per instantiation, one bit per device (function attributes are per device)
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (!(configured >> (dev & 63) & 1ull)) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // shared-memory carve-out: exactly what COFLUX_TILE_MIN_BLOCKS resident CTAs need (+1 KB each of system use); the rest
-    // of the 256 KB stays L1, which holds the psi table rows and the gathered atmosphere tiles
-    const int min_blocks = TileTraits<FT, SPEC>::MIN_BLOCKS;
-    const int carve = (int)((min_blocks * (smem + 1024 + 2560) * 100 + 228 * 1024 - 1) / (228 * 1024));   // + static log/exp tables
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve > 100 ? 100 : carve));
+    // the tiles and the staged ψ rows want all of the SM's shared memory; the kernel keeps nothing hot in L1 any more
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured |= 1ull << (dev & 63);
   }
-  kern<<<grid_for(a.ncell - a.cell0, TILE), 128, smem, st>>>(a);
+  kern<<<grid_for(a.ncell - a.cell0, TILE), TT::NT, smem, st>>>(a);
   return COFLUX_OK;
 }
 template <typename FT, bool INTERP, bool ASSEMBLE> static int launch_tile(const coflux_ctx* c, const FluxArgs<FT>& a, cudaStream_t st) {
@@ -831,8 +859,10 @@ static int do_ao(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   if (rc) return rc;
   rc = fill_ocean<FT>(c, o, a);
   if (rc) return rc;
+  rc = check_interface_halos<FT>(c, f);
+  if (rc) return rc;
   fill_interface_out<FT>(f, a);
-  if (tile_eligible<FT>(c)) {
+  if (tile_eligible<FT>(c, a)) {
     rc = launch_tile<FT, false, false>(c, a, st);
     if (rc) return rc;
   } else if (refill_v1() && (sizeof(FT) == 8 || COFLUX_REFILL_F32) && dev_params<FT>(c).ao.stop_kind != COFLUX_STOP_FIXED_ITERATIONS) {
@@ -870,6 +900,8 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   a.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
   a.ih = view2d(ice->thickness, 0, es); a.iS = view2d(ice->salinity, 0, es); a.ialb = view2d(ice->albedo, 0, es);
   a.iconc = view2d(ice->concentration, 0, es);
+  rc = check_interface_halos<FT>(c, f);
+  if (rc) return rc;
   fill_interface_out<FT>(f, a);
   a.Ttop_out = view2d(ice->top_temperature, 0, es);
   if (ice_tile_eligible<FT>(c)) {
@@ -1022,6 +1054,8 @@ static int build_update_args(coflux_ctx* c, const coflux_update_inputs* in, cofl
   if (rc) return rc;
   rc = fill_ocean<FT>(c, in->ocean, a);
   if (rc) return rc;
+  rc = check_interface_halos<FT>(c, out->atmosphere_ocean);
+  if (rc) return rc;
   fill_interface_out<FT>(out->atmosphere_ocean, a);
   const coflux_sea_ice_state* ice = in->sea_ice;
   const coflux_ice_ocean_fluxes* io = in->ice_ocean;
@@ -1041,7 +1075,7 @@ template <typename FT> static int launch_flux_rows(coflux_ctx* c, FluxArgs<FT> a
   a.cell0 = (long long)jj_lo * a.nxr;
   a.ncell = (long long)jj_hi * a.nxr;
   if (a.ncell <= a.cell0) return COFLUX_OK;
-  if (tile_eligible<FT>(c)) {
+  if (tile_eligible<FT>(c, a)) {
     int rc = launch_tile<FT, true, true>(c, a, st);
     if (rc) return rc;
   } else {
@@ -1429,9 +1463,10 @@ extern "C" int coflux_seam_attach(coflux_ctx* c, const void* west, const void* e
   if (rc) return rc;
   if (memcmp(&ww, &we, sizeof(ww)) == 0) { s.west = s.east; s.west_is_ipc = false; }   // two slabs: the same neighbour on both sides
   else { rc = open_peer(c, ww, &s.west, &s.west_is_ipc); if (rc) return rc; }
-  s.rank = rank; s.world = world; s.step = 0; s.attached = true;
-  CUDA_TRY(cudaMemset(s.local, 0, SEAM_DATA_OFFSET));
-  CUDA_TRY(cudaDeviceSynchronize());
+  // The flag / ack words are NOT reset here: the buffer was zeroed before it was exported (ensure_seam_buffer), and a
+  // neighbour that attached earlier may already have published its first column into it.  The step counter is not
+  // reset either (flags are monotone step ids), so a detach / re-attach of the same ring continues the sequence.
+  s.rank = rank; s.world = world; s.attached = true;
   return COFLUX_OK;
 }
 extern "C" int coflux_seam_detach(coflux_ctx* c) {

@@ -310,7 +310,26 @@ template <typename FT> __device__ __forceinline__ bool keep_going(const FluxP<FT
 #ifndef COFLUX_LEAN_F32
 #define COFLUX_LEAN_F32 1
 #endif
-struct LeanTabs { const double* lg; const double* ex; };     // shared-memory log / exp tables (Float64 only)
+// Shared-memory tables of the lean pass: log / exp tables (Float64 only) and the HOT part of the unstable Edson ψ table.
+//
+// Why the ψ table is staged in shared memory (round 2, profiles/README.md): every lane looks up its own row (128 B in
+// Float64), so one LDG.128 of a warp touches up to 32 different cache lines = 32 L1 wavefronts, 8 such loads per pass.
+// ncu showed the L1 data pipe 84 % busy (l1tex__data_pipe_lsu_wavefronts) — THAT, not FP64 latency, bounded the kernel.
+// Shared memory serves 8 different rows per wavefront when their 16-byte pieces fall into different bank groups, so the
+// rows are stored XOR-swizzled: piece p of row r lives at piece position p ^ (r & 7).  Lanes hold unrelated rows, hence
+// a lane's bank group is uniformly random: ≈ 7 wavefronts per LDS.128 instead of 32.  Values, evaluation order and
+// therefore results are bit-identical to the global-memory path, which still serves the rows outside the hot range.
+// Hot range: −ζ ∈ [2^KLO, 2^KHI) = [2⁻⁷, 2⁶) holds 96.6 % of the unstable passes on the SURVEY §8d inputs (26 KB).
+#ifndef COFLUX_PSI_SM_KLO
+#define COFLUX_PSI_SM_KLO (-7)
+#endif
+#ifndef COFLUX_PSI_SM_KHI
+#define COFLUX_PSI_SM_KHI 6
+#endif
+#define COFLUX_PSI_SM_ROW0 ((COFLUX_PSI_SM_KLO - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
+#define COFLUX_PSI_SM_ROWS ((COFLUX_PSI_SM_KHI - COFLUX_PSI_SM_KLO) * COFLUX_PSI_NS)
+static_assert(COFLUX_PSI_SM_KLO >= COFLUX_PSI_KMIN && COFLUX_PSI_SM_KHI <= COFLUX_PSI_KMAX && COFLUX_PSI_SM_KLO < COFLUX_PSI_SM_KHI, "hot range outside the table");
+struct LeanTabs { const double* lg; const double* ex; unsigned psi; };   // psi: shared-window byte address of the swizzled rows
 template <typename FT> struct LeanCell { FT U2, Ustab, dth, dq, cb1, cb2, bnu, inv_nu; };   // b★ = cb1·θ★ + cb2·q★
 template <typename FT> struct D3 { FT u, t, q; };
 
@@ -330,25 +349,25 @@ template <> __device__ __forceinline__ const LeanLit<double>& lean_lit<double>()
 template <> __device__ __forceinline__ const LeanLit<float>& lean_lit<float>() { return LL32; }
 #define COFLUX_NROWS ((COFLUX_PSI_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
 
-// Row of the ψ table for z (clamped into the table, so that the loads are safe for ANY z: the caller may then
+// Row index of the ψ table for z (clamped into the table, so that the loads are safe for ANY z: the caller may then
 // issue them before it knows whether z is in range, and the scheduler can hoist them above the cube root) and
 // the local coordinate t ∈ [−1, 1).  A row holds the 8 coefficients of ψ_u followed by the 8 of ψ_θ.
-__device__ __forceinline__ const double* psi_table_row(double z, double& t) {
+__device__ __forceinline__ int psi_table_row(double z, double& t) {
   const long long bits = __double_as_longlong(z);
   const int hi = (int)(bits >> 32);
   int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);              // (exponent − KMIN)·16 + top 4 mantissa bits
   row = max(0, min(row, COFLUX_NROWS - 1));
   const double one_plus_u = __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL);
   t = fm::fma_(2.0, one_plus_u, -3.0);
-  return &COFLUX_PSI_TABLE_F64[row][0][0];
+  return row;
 }
-__device__ __forceinline__ const float* psi_table_row(float z, float& t) {
+__device__ __forceinline__ int psi_table_row(float z, float& t) {
   const int bits = __float_as_int(z);
   int row = (bits >> 19) - ((127 + COFLUX_PSI_KMIN) << 4);
   row = max(0, min(row, COFLUX_NROWS - 1));
   const float one_plus_u = __int_as_float(((bits & 0x0007ffff) << 4) | 0x3f800000);
   t = fm::fma_(2.0f, one_plus_u, -3.0f);
-  return &COFLUX_PSI_TABLE_F32[row][0][0];
+  return row;
 }
 template <typename FT> struct Coef8 { FT c[8]; };
 __device__ __forceinline__ Coef8<double> ld_coef8(const double* p) {       // 4 × LDG.128
@@ -360,6 +379,60 @@ __device__ __forceinline__ Coef8<float> ld_coef8(const float* p) {         // 2 
   const float4* q = reinterpret_cast<const float4*>(p);
   const float4 a = __ldg(q), b = __ldg(q + 1);
   return Coef8<float>{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+  double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr)); return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr) {
+  float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)); return v;
+}
+// Swizzled shared-memory address of piece 0 of local row rl; piece p is at (that address) ^ (p << 4).
+//   Float64: 128-byte rows of 8 pieces (ψ_u: 0–3, ψ_θ: 4–7), swizzle rl & 7.
+//   Float32:  64-byte rows of 4 pieces (ψ_u: 0–1, ψ_θ: 2–3), swizzle (rl >> 1) & 3 (bit 2 of the bank group is rl & 1).
+__device__ __forceinline__ unsigned psi_sm_addr(unsigned base, unsigned rl, double) { return base + (rl << 7) + ((rl & 7u) << 4); }
+__device__ __forceinline__ unsigned psi_sm_addr(unsigned base, unsigned rl, float) { return base + (rl << 6) + (((rl >> 1) & 3u) << 4); }
+// coefficients of ψ_u (which = 0) or ψ_θ (which = 1) of table row `row`
+__device__ __forceinline__ Coef8<double> ld_psi(const LeanTabs& tb, int row, int which, double tag) {
+  const unsigned rl = (unsigned)(row - COFLUX_PSI_SM_ROW0);
+  if (__builtin_expect(rl < (unsigned)COFLUX_PSI_SM_ROWS, 1)) {
+    const unsigned a0 = psi_sm_addr(tb.psi, rl, tag) ^ (which ? 64u : 0u);
+    const double2 a = lds_f64x2(a0), b = lds_f64x2(a0 ^ 16u), c = lds_f64x2(a0 ^ 32u), d = lds_f64x2(a0 ^ 48u);
+    return Coef8<double>{{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y}};
+  }
+  return ld_coef8(&COFLUX_PSI_TABLE_F64[row][which][0]);
+}
+__device__ __forceinline__ Coef8<float> ld_psi(const LeanTabs& tb, int row, int which, float tag) {
+  const unsigned rl = (unsigned)(row - COFLUX_PSI_SM_ROW0);
+  if (__builtin_expect(rl < (unsigned)COFLUX_PSI_SM_ROWS, 1)) {
+    const unsigned a0 = psi_sm_addr(tb.psi, rl, tag) ^ (which ? 32u : 0u);
+    const float4 a = lds_f32x4(a0), b = lds_f32x4(a0 ^ 16u);
+    return Coef8<float>{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+  }
+  return ld_coef8(&COFLUX_PSI_TABLE_F32[row][which][0]);
+}
+// both functions of one row (the ψ(h/L★) pair): one range test for the 8 (4) loads
+__device__ __forceinline__ void ld_psi_pair(const LeanTabs& tb, int row, Coef8<double>& km, Coef8<double>& ks, double tag) {
+  const unsigned rl = (unsigned)(row - COFLUX_PSI_SM_ROW0);
+  if (__builtin_expect(rl < (unsigned)COFLUX_PSI_SM_ROWS, 1)) {
+    const unsigned a0 = psi_sm_addr(tb.psi, rl, tag);
+    const double2 a = lds_f64x2(a0), b = lds_f64x2(a0 ^ 16u), c = lds_f64x2(a0 ^ 32u), d = lds_f64x2(a0 ^ 48u);
+    const double2 e = lds_f64x2(a0 ^ 64u), f = lds_f64x2(a0 ^ 80u), g = lds_f64x2(a0 ^ 96u), h = lds_f64x2(a0 ^ 112u);
+    km = Coef8<double>{{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y}};
+    ks = Coef8<double>{{e.x, e.y, f.x, f.y, g.x, g.y, h.x, h.y}};
+  } else {
+    km = ld_coef8(&COFLUX_PSI_TABLE_F64[row][0][0]); ks = ld_coef8(&COFLUX_PSI_TABLE_F64[row][1][0]);
+  }
+}
+__device__ __forceinline__ void ld_psi_pair(const LeanTabs& tb, int row, Coef8<float>& km, Coef8<float>& ks, float tag) {
+  const unsigned rl = (unsigned)(row - COFLUX_PSI_SM_ROW0);
+  if (__builtin_expect(rl < (unsigned)COFLUX_PSI_SM_ROWS, 1)) {
+    const unsigned a0 = psi_sm_addr(tb.psi, rl, tag);
+    const float4 a = lds_f32x4(a0), b = lds_f32x4(a0 ^ 16u), c = lds_f32x4(a0 ^ 32u), d = lds_f32x4(a0 ^ 48u);
+    km = Coef8<float>{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+    ks = Coef8<float>{{c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w}};
+  } else {
+    km = ld_coef8(&COFLUX_PSI_TABLE_F32[row][0][0]); ks = ld_coef8(&COFLUX_PSI_TABLE_F32[row][1][0]);
+  }
 }
 template <typename FT> __device__ __forceinline__ FT poly8v(const Coef8<FT>& k, FT t) {
   FT a = fm::fma_(k.c[7], t, k.c[6]);
@@ -387,16 +460,20 @@ template <typename FT> __device__ __forceinline__ FT dmax_(FT a, FT b) { return 
 // One pass.  Returns false when the pass left the short path (the scales are then unchanged and the
 // caller must run lean_cold_pass).  Float32 runs the same pass with the CUDA single-precision functions
 // (fm:: overloads), the Float32 ψ table and the same series.
-template <typename FT, int SPEC>
+// FIRST: the pass that starts from the initial guess u★ = θ★ = q★ = init > 0.  Its buoyancy scale is positive whatever
+// the cell (b★ = init·(cb1 + cb2), both coefficients positive), so only the stable block is compiled; phase A runs it
+// for every cell in lock step.  chi_out (optional) receives χ_q: θ★ = χ_q·Δθ and q★ = χ_q·Δq are then reproducible
+// from ONE stored number.
+template <typename FT, int SPEC, bool FIRST = false>
 __device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP<FT>& F, const FastConsts<FT>& K,
-                                             const LeanTabs& tb, const LeanCell<FT>& c, FT& us, FT& ts, FT& qs) {
+                                             const LeanTabs& tb, const LeanCell<FT>& c, FT& us, FT& ts, FT& qs, FT* chi_out = nullptr) {
   const LeanLit<FT>& LL = lean_lit<FT>();
   constexpr FT TINY = FT(0.0001220703125);                   // 2⁻¹³: |ℓ/L★| below which the short series are exact to rounding
   constexpr FT Z_LO = FT(9.5367431640625e-07), Z_HI = FT(8192.0);   // table domain of −ζ: [2⁻²⁰, 2¹³)
   constexpr FT SMALL = FT(7.888609052210118e-31), BIG = FT(1.2676506002282294e30);   // 2⁻¹⁰⁰, 2¹⁰⁰
   const FT u0 = us, t0 = ts, q0 = qs;
   const FT bstar = fm::fma_(c.cb1, t0, c.cb2 * q0);
-  const bool unstable = bstar < FT(0);
+  const bool unstable = FIRST ? false : (bstar < FT(0));
   bool ok = (u0 > SMALL) && (c.Ustab > FT(0));
   const FT r = fm::rcp(u0);
   const FT invL = (F.kappa * bstar) * (r * r);
@@ -419,8 +496,8 @@ __device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP
   FT psi_hm, psi_hs, sm_ = FT(0), ss_ = FT(0);
   if (unstable) {
     FT t;
-    const FT* row = psi_table_row(-zeta, t);                 // loads first: the cube root below hides their latency
-    const Coef8<FT> km = ld_coef8(row), ks = ld_coef8(row + 8);
+    Coef8<FT> km, ks;
+    ld_psi_pair(tb, psi_table_row(-zeta, t), km, ks, FT(0)); // loads first: the cube root below hides their latency
     const FT w = (-u0 * bstar) * P.hbl;                      // Jᵇ·h_bl > 0
     ok = ok && (w > SMALL) && (w < BIG) && (-zeta >= Z_LO) && (-zeta < Z_HI);
     const FT UG = dmax_<FT>(F.beta * fm::cbrt(w), F.ugmin);
@@ -433,8 +510,8 @@ __device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP
         sm_ = a * xm;
       } else {
         FT tt;
-        const FT* rr = psi_table_row(-xm, tt);
-        sm_ = poly8v<FT>(ld_coef8(rr), tt);
+        const int rr = psi_table_row(-xm, tt);
+        sm_ = poly8v<FT>(ld_psi(tb, rr, 0, FT(0)), tt);
       }
       if (-xs <= TINY) {
         FT b = fm::fma_(FT(-39314.5625), xs, FT(-3548.0859375));
@@ -442,8 +519,8 @@ __device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP
         ss_ = b * xs;
       } else {
         FT tt;
-        const FT* rr = psi_table_row(-xs, tt);
-        ss_ = poly8v<FT>(ld_coef8(rr + 8), tt);
+        const int rr = psi_table_row(-xs, tt);
+        ss_ = poly8v<FT>(ld_psi(tb, rr, 1, FT(0)), tt);
       }
     }
     psi_hm = poly8v<FT>(km, t);
@@ -463,10 +540,11 @@ __device__ __forceinline__ bool iterate_lean(const DevParams<FT>& P, const FluxP
   if (!__builtin_expect(ok, 1)) return false;
   const FT prof_u = ((K.lnh - ll) - psi_hm) + sm_;
   const FT prof_q = (lnq - psi_hs) + ss_;
-  if (!(prof_u > FT(0))) { us = ts = qs = FT(0); return true; }
+  if (!(prof_u > FT(0))) { us = ts = qs = FT(0); if (chi_out) *chi_out = FT(0); return true; }
   const FT chi_u = F.kappa * fm::rcp(prof_u);
   const FT chi_q = (prof_q > FT(0)) ? F.kappa * fm::rcp(prof_q) : FT(0);
   us = chi_u * U; ts = chi_q * c.dth; qs = chi_q * c.dq;
+  if (chi_out) *chi_out = chi_q;
   return true;
 }
 // the exact pass behind one by-value call, so that the lean loop stays small and its state stays in registers
@@ -479,86 +557,129 @@ template <typename FT> __device__ __forceinline__ bool same_bits(FT a, FT b);
 template <> __device__ __forceinline__ bool same_bits<double>(double a, double b) { return __double_as_longlong(a) == __double_as_longlong(b); }
 template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) { return __float_as_int(a) == __float_as_int(b); }
 
-// Occupancy knobs (A/B-measured on B200, 1/12° Float64 `:default`, lean loop; tools/ab_variants.py, profiles/README.md):
-//   TILE 256: 8 CTAs/SM (64 regs, 288 B spills) 4.08 ms, 7 CTAs (72 regs) 3.98 ms, 6 CTAs (80 regs, 24 B) 3.98 ms;
-//   TILE 384: 6 CTAs 3.86 ms, 5 CTAs (96 regs) 3.95 ms;  TILE 512: 5 CTAs 4.11 ms.
-//   The kernel is latency bound (in-order issue over ~9-cycle FP64 dependencies, IPC ≈ 0.45/SMSP): resident warps and
-//   a long tile (fewer idle lanes while a tile's queue drains) matter, spills to L1 cost more than they buy.
-//   COFLUX_TILE_CARRY = 1 keeps ρ_a and c_p,m of every cell in shared memory between phase A and phase C.
-#ifndef COFLUX_TILE_CARRY
-#define COFLUX_TILE_CARRY 1
+// Launch shape (round 2).  One copy of the hot ψ rows per CTA (26 KB in Float64) wants few, large CTAs; the phases of
+// different CTAs overlap on an SM (A is latency bound on gathers, B on the FP64 / issue pipes), which wants several.
+//   Float64 `:default`   256 threads × 3 CTAs/SM, 768 cells per CTA (58 B/cell + 29 KB of tables = 73.7 KB), 80 registers
+//   Float64 `:corrected` 384 threads × 2 CTAs/SM, 1152 cells (74 B/cell: ν and 1/ν vary), 80 registers
+//   Float32              256 threads × 4 CTAs/SM, 1024 cells (30 / 38 B/cell + 13 KB table), 64 registers
+// Round-1 shape for reference (table in global memory): 128 threads × 6 CTAs, 384 cells (profiles/README.md).
+#ifndef COFLUX_TILE_PRE1
+#define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A (A/B knob) */
 #endif
-#ifndef COFLUX_TILE_MIN_BLOCKS
-#define COFLUX_TILE_MIN_BLOCKS 6
+#ifndef COFLUX_TILE_NT64
+#define COFLUX_TILE_NT64 256
 #endif
-#ifndef COFLUX_TILE_CELLS
-#define COFLUX_TILE_CELLS 384
+#ifndef COFLUX_TILE_CELLS64
+#define COFLUX_TILE_CELLS64 768
 #endif
-#ifndef COFLUX_TILE_MIN_BLOCKS_F32
-#define COFLUX_TILE_MIN_BLOCKS_F32 8
+#ifndef COFLUX_TILE_MIN_BLOCKS64
+#define COFLUX_TILE_MIN_BLOCKS64 3
 #endif
-#ifndef COFLUX_TILE_PRE
-#define COFLUX_TILE_PRE 0      /* similarity passes done in lock step in phase A before a cell is queued (A/B on B200, 1/12° F64 default / corrected / F32: 2 → 3.99 / 3.77 / 2.67 ms, 1 → 3.95 / 3.70 / 2.53, 0 → 3.90 / 3.56 / 2.50) */
+#ifndef COFLUX_TILE_NT64_S2
+#define COFLUX_TILE_NT64_S2 384
+#endif
+#ifndef COFLUX_TILE_CELLS64_S2
+#define COFLUX_TILE_CELLS64_S2 1152
+#endif
+#ifndef COFLUX_TILE_MIN_BLOCKS64_S2
+#define COFLUX_TILE_MIN_BLOCKS64_S2 2
+#endif
+#ifndef COFLUX_TILE_NT32
+#define COFLUX_TILE_NT32 256
+#endif
+#ifndef COFLUX_TILE_CELLS32
+#define COFLUX_TILE_CELLS32 1024
+#endif
+#ifndef COFLUX_TILE_MIN_BLOCKS32
+#define COFLUX_TILE_MIN_BLOCKS32 4
 #endif
 
-// shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts)
+// shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts).
+// A cell's slots are reused over its life:
+//   queued      U2, dth, dq, c1, c2 (+ nu, inu): invariants of the iteration (lean pass: c1, c2 = the coefficients of
+//               b★ = c1·θ★ + c2·q★; generic pass: T_v, q_v);  us1, chi1: u★ and χ_q after the first pass, which phase A
+//               runs in lock step (us1 < 0: not run, the cell starts from the initial guess)
+//   in flight   the lane holds the invariants in registers; U2/dth/dq hold the Brent snapshot, c1 the packed Brent state
+//   finished    U2, dth, dq ← u★, θ★, q★;  c1 ← iteration count (as an integer)
+// ρ_a and c_p,m — needed again by phase C — are parked in the ρτx / ρτy OUTPUT arrays by phase A (same thread, same
+// element; the lines are still in L2 when phase C overwrites them with the stresses), not in shared memory: 16 B per
+// cell less, i.e. more cells per lane for the same footprint.
 template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
-  FT U2[TILE], dth[TILE], dq[TILE], Tv[TILE], qv[TILE];   // task: invariants of the cell's iteration
+  FT U2[TILE], dth[TILE], dq[TILE], c1[TILE], c2[TILE];
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
-  FT us[TILE], ts[TILE], qs[TILE];                        // iterate / result
-#if COFLUX_TILE_CARRY
-  FT rho[TILE], cp[TILE];                                 // carried to phase C
-#endif
-  // lean loop: Tv/qv hold cb1/cb2 (b★ = cb1·θ★ + cb2·q★) instead; plus 1/ν.  (The Brent snapshot of a cell in
-  // flight lives in that cell's own us/ts/qs/it slots, which nobody reads until the cell is written back.)
-  FT inu[(LEAN && VARNU) ? TILE : 1];
-  int it[TILE];
+  FT inu[(LEAN && VARNU) ? TILE : 1];                     // 1/ν (lean pass)
+  FT us1[LEAN ? TILE : 1], chi1[LEAN ? TILE : 1];         // state after the lock-step first pass (lean pass)
   unsigned short queue[TILE];
-  int n_front, n_back, head;
+  int n_front, n_back, head[2];     // head[0]: next unstable cell (front of the queue), head[1]: next stable cell (back)
+};
+template <typename FT> struct SlotInt;      // integer view of a slot
+template <> struct SlotInt<double> {
+  static __device__ __forceinline__ int get(const double& s) { return (int)__double_as_longlong(s); }
+  static __device__ __forceinline__ void set(double& s, int v) { s = __longlong_as_double((long long)v); }
+};
+template <> struct SlotInt<float> {
+  static __device__ __forceinline__ int get(const float& s) { return __float_as_int(s); }
+  static __device__ __forceinline__ void set(float& s, int v) { s = __int_as_float(v); }
 };
 template <typename FT, int SPEC> struct TileTraits {
+  static constexpr bool F64 = (sizeof(FT) == 8);
   static constexpr bool VARNU = (SPEC != 1);   // `:default` uses a constant air viscosity
-  static constexpr bool LEAN = (COFLUX_LEAN != 0) && (SPEC != 0) && (std::is_same<FT, double>::value || (COFLUX_LEAN_F32 != 0));
-  static constexpr bool TABS = LEAN && std::is_same<FT, double>::value;   // log / exp tables in shared memory
-  // resident CTAs per SM / cells per CTA, A/B-measured per precision and parameter set (profiles/README.md):
-  // Float64 `:default` and generic 6 × 384 (80 registers); Float64 `:corrected` 7 × 256 (72 registers: its pass carries
-  // no ψ(ℓ/L) terms); Float32 8 × 384 (64 registers)
-  static constexpr int MIN_BLOCKS = (sizeof(FT) == 8) ? ((SPEC == 2) ? COFLUX_TILE_MIN_BLOCKS + 1 : COFLUX_TILE_MIN_BLOCKS) : COFLUX_TILE_MIN_BLOCKS_F32;
-  static constexpr int TILE = (sizeof(FT) == 8 && SPEC == 2) ? 256 : COFLUX_TILE_CELLS;
+  static constexpr bool LEAN = (COFLUX_LEAN != 0) && (SPEC != 0) && (F64 || (COFLUX_LEAN_F32 != 0));
+  static constexpr bool TABS = LEAN && F64;    // log / exp tables in shared memory
+  static constexpr int NT = F64 ? ((SPEC == 1) ? COFLUX_TILE_NT64 : COFLUX_TILE_NT64_S2) : COFLUX_TILE_NT32;
+  static constexpr int TILE = F64 ? ((SPEC == 1) ? COFLUX_TILE_CELLS64 : COFLUX_TILE_CELLS64_S2) : COFLUX_TILE_CELLS32;
+  static constexpr int MIN_BLOCKS = F64 ? ((SPEC == 1) ? COFLUX_TILE_MIN_BLOCKS64 : COFLUX_TILE_MIN_BLOCKS64_S2) : COFLUX_TILE_MIN_BLOCKS32;
+  static constexpr int PSI_BYTES = LEAN ? COFLUX_PSI_SM_ROWS * 16 * (int)sizeof(FT) : 16;
+  static_assert(TILE <= 65535, "queue entries are 16-bit");
 };
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
-__global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+__global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr bool VARNU = TileTraits<FT, SPEC>::VARNU;
-  constexpr bool LEAN = TileTraits<FT, SPEC>::LEAN;
-  constexpr bool TABS = TileTraits<FT, SPEC>::TABS;
+  using TT = TileTraits<FT, SPEC>;
+  constexpr bool VARNU = TT::VARNU;
+  constexpr bool LEAN = TT::LEAN;
+  constexpr bool TABS = TT::TABS;
+  constexpr int NT = TT::NT;
   using MP = std::conditional_t<TABS, MLeanD, M<FT>>;      // math policy of the phase-A thermodynamics
+  using SI = SlotInt<FT>;
   TileSmem<FT, TILE, VARNU, LEAN>& sm = *reinterpret_cast<TileSmem<FT, TILE, VARNU, LEAN>*>(smem_raw);
-  // log / exp tables of the lean Float64 functions: STATIC shared arrays, so that their addresses are compile-time
-  // shared-window offsets (through the dynamic block every lookup paid a generic→shared address conversion)
+  // log / exp tables of the lean Float64 functions and the hot ψ rows: STATIC shared arrays, so that their addresses are
+  // compile-time shared-window offsets (through the dynamic block every lookup paid a generic→shared address conversion)
   __shared__ __align__(16) double s_lgt[TABS ? 256 : 2];
   __shared__ double s_ext[TABS ? 64 : 2];
+  __shared__ __align__(128) unsigned char s_psi[TT::PSI_BYTES];
   const DevParams<FT>& P = a.P;
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
   const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
-  if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head = 0; }
+  if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head[0] = 0; sm.head[1] = 0; }
   if (TABS) {
-    for (int k = tid; k < 256; k += 128) s_lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
+    for (int k = tid; k < 256; k += NT) s_lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
     if (tid < 64) s_ext[tid] = COFLUX_EXP_TABLE[tid];
   }
+  if constexpr (LEAN) {
+    if constexpr (sizeof(FT) == 8) {     // 8 pieces of 16 B per row, piece p at position p ^ (r & 7)
+      const double2* src = reinterpret_cast<const double2*>(&COFLUX_PSI_TABLE_F64[COFLUX_PSI_SM_ROW0][0][0]);
+      double2* dst = reinterpret_cast<double2*>(s_psi);
+      for (int k = tid; k < COFLUX_PSI_SM_ROWS * 8; k += NT) { const int r = k >> 3, p = k & 7; dst[(r << 3) + (p ^ (r & 7))] = __ldg(src + k); }
+    } else {                             // 4 pieces per row, piece p at position p ^ ((r >> 1) & 3)
+      const float4* src = reinterpret_cast<const float4*>(&COFLUX_PSI_TABLE_F32[COFLUX_PSI_SM_ROW0][0][0]);
+      float4* dst = reinterpret_cast<float4*>(s_psi);
+      for (int k = tid; k < COFLUX_PSI_SM_ROWS * 4; k += NT) { const int r = k >> 2, p = k & 3; dst[(r << 2) + (p ^ ((r >> 1) & 3))] = __ldg(src + k); }
+    }
+  }
   __syncthreads();
-  const LeanTabs tb{s_lgt, s_ext};
+  const LeanTabs tb{s_lgt, s_ext, (unsigned)__cvta_generic_to_shared(s_psi)};
   const FastConsts<FT>& K = P.K;
   const FT delta = c.eps - FT(1);
   const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
 
   // ------------------------------------------------------------------ phase A
-  for (int cidx = tid; cidx < TILE; cidx += 128) {
+  for (int cidx = tid; cidx < TILE; cidx += NT) {
     const long long idx = tile0 + cidx;
-    if (idx >= a.ncell) { sm.it[cidx] = -1; continue; }
+    if (idx >= a.ncell) continue;
     const int jj = (int)(idx / a.nxr);
     const int ii = (int)(idx - (long long)jj * a.nxr);
     const int i = ii - a.ring, j = jj - a.ring;
@@ -590,8 +711,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
       ua = ldgs<FT>(a.xu, i, j); va = ldgs<FT>(a.xv, i, j); Ta = ldgs<FT>(a.xT, i, j); pa = ldgs<FT>(a.xp, i, j);
       qa = ldgs<FT>(a.xq, i, j);
     }
-    FT us = FT(0), ts = FT(0), qs = FT(0);
-    int it = 0;
+    bool queued = false, finished_in_a = false;
     if (is_active(a.mask, i, j)) {
       const FT uo = (ldgs<FT>(a.ou, i, j) + ldgs<FT>(a.ou, i + 1, j)) * FT(0.5);
       const FT vo = (ldgs<FT>(a.ov, i, j) + ldgs<FT>(a.ov, i, j + 1)) * FT(0.5);
@@ -600,74 +720,74 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = ua - uo; dv = va - vo; } else { du = ua; dv = va; }
       const FT U2 = du * du + dv * dv;
-      us = ts = qs = F.init;
-      bool go = fixed ? (F.maxit > 0) : true;
-      FT dtheta, dq, Tv, qv, nu_m;
-      // the first COFLUX_TILE_PRE passes run here, in lock step: they are the start-up transient
-      // (pass 1 is always stable; pass 2 sees u★ ~ 1e-6 and |ζ| up to thousands), so that the refill
-      // loop of phase B only meets settled iterates on the short code path
-      if constexpr (LEAN) {
-        const Thermo<FT> atm = phase_equil_pTq<FT, MP>(c, pa, Ta, qa);
-        const FT s = MP::div(So, FT(1000));
-        const FT x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s);
-        const FT theta_a = Ta + MP::div(P.g * P.h, atm.cp_m);
-        const SurfaceState<FT> S = surface_state<FT, 0, MP>(P, F, atm, pa, theta_a, x, Ts);
-        dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
-#if COFLUX_TILE_CARRY
-        sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
-#endif
-        LeanCell<FT> lc;
-        lc.U2 = U2; lc.dth = dtheta; lc.dq = dq;
-        { const FT v = fm::fma_(F.ugmin, F.ugmin, U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
-        { const FT gTv = P.g * fm::rcp(Tv); lc.cb1 = gTv * (FT(1) + delta * qv); lc.cb2 = gTv * (delta * Tv); }
-        lc.bnu = F.mr.beta_s * nu_m; lc.inv_nu = fm::rcp(nu_m);
-#pragma unroll 1
-        for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
-          const FT u0 = us, t0 = ts, q0 = qs;
-          if (!iterate_lean<FT, SPEC>(P, F, K, tb, lc, us, ts, qs)) {
-            const D3<FT> r = lean_cold_pass<FT, SPEC>(&P, U2, dtheta, dq, lc.cb1, lc.cb2, nu_m, u0, t0, q0);
-            us = r.u; ts = r.t; qs = r.q;
+      const Thermo<FT> atm = phase_equil_pTq<FT, MP>(c, pa, Ta, qa);
+      const FT s = MP::div(So, FT(1000));
+      const FT x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s);
+      const FT theta_a = Ta + MP::div(P.g * P.h, atm.cp_m);
+      const SurfaceState<FT> S = surface_state<FT, 0, MP>(P, F, atm, pa, theta_a, x, Ts);
+      stg<FT>(a.rtx, i, j, atm.rho); stg<FT>(a.rty, i, j, atm.cp_m);     // parked for phase C (see TileSmem)
+      if (fixed ? (F.maxit > 0) : true) {
+        queued = true;
+        FT c1, c2;
+        if constexpr (LEAN) {    // b★ = c1·θ★ + c2·q★
+          const FT gTv = P.g * fm::rcp(S.T_v);
+          c1 = gTv * (FT(1) + delta * S.q_vap); c2 = gTv * (delta * S.T_v);
+          const FT inv_nu = VARNU ? fm::rcp(S.nu_m) : K.inv_nu;
+          if (VARNU) sm.inu[cidx] = inv_nu;
+          // first pass, in lock step (every lane busy, one code path)
+          FT us = F.init, ts = F.init, qs = F.init, chi = FT(0);
+          bool pre = COFLUX_TILE_PRE1 && F.init > FT(0) && (c1 + c2) > FT(0);
+          if (pre) {
+            LeanCell<FT> lc;
+            lc.U2 = U2; lc.dth = S.dtheta; lc.dq = S.dq; lc.cb1 = c1; lc.cb2 = c2;
+            { const FT v = fm::fma_(F.ugmin, F.ugmin, U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
+            lc.bnu = VARNU ? F.mr.beta_s * S.nu_m : K.bnu; lc.inv_nu = inv_nu;
+            pre = iterate_lean<FT, SPEC, true>(P, F, K, tb, lc, us, ts, qs, &chi);
           }
-          ++it;
-          go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
+          if (pre && !keep_going<FT>(F, 1, us, ts, qs, F.init, F.init, F.init)) {     // done after one pass
+            queued = false;
+            sm.U2[cidx] = us; sm.dth[cidx] = ts; sm.dq[cidx] = qs; SI::set(sm.c1[cidx], 1);
+          }
+          sm.us1[cidx] = pre ? us : FT(-1); sm.chi1[cidx] = chi;
+        } else { c1 = S.T_v; c2 = S.q_vap; }
+        if (queued) {
+          sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.c1[cidx] = c1; sm.c2[cidx] = c2;
+          if (VARNU) sm.nu[cidx] = S.nu_m;
+          // stability class of every later pass: sign of the buoyancy scale ∝ Δθ·a1 + a2·Δq (χ_θ = χ_q > 0)
+          const bool unstable = LEAN ? ((S.dtheta * c1 + c2 * S.dq) < FT(0)) : ((S.dtheta * (FT(1) + delta * S.q_vap) + (delta * S.T_v) * S.dq) < FT(0));
+          if (unstable) sm.queue[atomicAdd(&sm.n_front, 1)] = (unsigned short)cidx;
+          else sm.queue[TILE - 1 - atomicAdd(&sm.n_back, 1)] = (unsigned short)cidx;
         }
-        if (VARNU && go) sm.inu[cidx] = lc.inv_nu;
-        Tv = lc.cb1; qv = lc.cb2;      // what the lean loop of phase B wants in sm.Tv / sm.qv
-      } else {
-        const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
-        const FT s = So / FT(1000);
-        const FT x = (FT(1) - s) / (FT(1) - s + P.wmf_alpha * s);
-        const FT theta_a = Ta + P.g * P.h / atm.cp_m;
-        const SurfaceState<FT> S = surface_state<FT, 0>(P, F, atm, pa, theta_a, x, Ts);
-        dtheta = S.dtheta; dq = S.dq; Tv = S.T_v; qv = S.q_vap; nu_m = S.nu_m;
-#if COFLUX_TILE_CARRY
-        sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
-#endif
-        const FT gTv = P.g / Tv, a1 = FT(1) + delta * qv, a2 = delta * Tv;
-#pragma unroll 1
-        for (int k = 0; k < COFLUX_TILE_PRE && go; ++k) {
-          const FT u0 = us, t0 = ts, q0 = qs;
-          iterate_fast<FT, SPEC>(P, F, K, U2, dtheta, dq, gTv, a1, a2, nu_m, us, ts, qs);
-          ++it;
-          go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
-        }
-      }
-      if (go) {
-        sm.U2[cidx] = U2; sm.dth[cidx] = dtheta; sm.dq[cidx] = dq; sm.Tv[cidx] = Tv; sm.qv[cidx] = qv;
-        if (VARNU) sm.nu[cidx] = nu_m;
-        // stability class of every later pass: sign of the buoyancy scale ∝ Δθ·a1 + a2·Δq (χ_θ = χ_q > 0)
-        const bool unstable = LEAN ? ((dtheta * Tv + qv * dq) < FT(0)) : ((dtheta * (FT(1) + delta * qv) + (delta * Tv) * dq) < FT(0));
-        if (unstable) sm.queue[atomicAdd(&sm.n_front, 1)] = (unsigned short)cidx;
-        else sm.queue[TILE - 1 - atomicAdd(&sm.n_back, 1)] = (unsigned short)cidx;
+        finished_in_a = !queued;
       }
     }
-    sm.us[cidx] = us; sm.ts[cidx] = ts; sm.qs[cidx] = qs; sm.it[cidx] = it;
+    if (!queued && !finished_in_a) {      // finished on the spot: land, or a zero-pass solve
+      const FT r0 = is_active(a.mask, i, j) ? F.init : FT(0);
+      sm.U2[cidx] = r0; sm.dth[cidx] = r0; sm.dq[cidx] = r0; SI::set(sm.c1[cidx], 0);
+    }
   }
   __syncthreads();
 
-  const int n_front = sm.n_front, n_total = sm.n_front + sm.n_back;
+  const int n_front = sm.n_front, n_back = sm.n_back;
 
-  // ------------------------------------------------------------------ phase B: lane refill
+  // ------------------------------------------------------------------ phase B: lane refill, class-pure warps
+  // The two stability classes run different code (unstable: cube root + ψ table; stable: closed forms).  With ONE queue
+  // (unstable cells first) the lanes of every warp drift into the stable cells one by one, and for the last third of
+  // the phase every warp executes BOTH blocks per pass (ncu, round 2: the shared tail of the pass ran 1.49× per loop
+  // trip).  So each warp serves ONE class: warps [0, W_u) pop unstable cells from the front of the queue, the others
+  // stable cells from its back, W_u proportional to the classes' expected work (stable cells need ≈ 15 % more passes).
+  // A warp whose class has run dry AND whose lanes have all finished moves over to help with the other class.
+  constexpr int NW = NT / 32;
+  int cls;                                       // 0 unstable, 1 stable
+  {
+    const float wu = 13.9f * (float)n_front, ws = 15.9f * (float)n_back;
+    int W_u = (wu + ws > 0.f) ? (int)((float)NW * wu / (wu + ws) + 0.5f) : NW;
+    if (n_front > 0 && W_u < 1) W_u = 1;
+    if (n_back > 0 && W_u > NW - 1) W_u = NW - 1;
+    if (n_front == 0) W_u = 0;
+    cls = ((tid >> 5) < W_u) ? 0 : 1;
+  }
+  bool moved = false;
   // Brent cycle detection: (su, st, sq) is a snapshot of the iterate taken at pass `snap_it`; it is
   // refreshed after 1, 2, 4, 8 … passes.  When the iterate returns EXACTLY to the snapshot the orbit
   // is periodic with period λ = it − snap_it; the reference keeps iterating until maxiter, i.e. it
@@ -680,25 +800,27 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
     FT nu = F.mr.visc.nu, us = 0, ts = 0, qs = 0;
     if (!VARNU) { lc.bnu = K.bnu; lc.inv_nu = K.inv_nu; }
     auto pop = [&]() {
-      const int pos = atomicAdd(&sm.head, 1);
+      const int pos = atomicAdd(&sm.head[cls], 1);
       slot = -1;
-      if (pos < n_total) {
-        slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
-        lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.Tv[slot]; lc.cb2 = sm.qv[slot];
+      if (pos < (cls ? n_back : n_front)) {
+        slot = cls ? sm.queue[TILE - 1 - pos] : sm.queue[pos];
+        lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.c1[slot]; lc.cb2 = sm.c2[slot];
         { const FT v = fm::fma_(F.ugmin, F.ugmin, lc.U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
         if (VARNU) { nu = sm.nu[slot]; lc.inv_nu = sm.inu[slot]; lc.bnu = F.mr.beta_s * nu; }
-        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
+        us = sm.us1[slot];
+        if (us >= FT(0)) { const FT chi = sm.chi1[slot]; ts = chi * lc.dth; qs = chi * lc.dq; it = 1; }
+        else { us = ts = qs = F.init; it = 0; }
       }
     };
     // rare tail of a cell's iteration: the Brent bookkeeping lives in the cell's own shared-memory slots
-    // (us/ts/qs: snapshot; it: snap_it | window << 8 | (stop_at + 1) << 16), not in registers
+    // (U2/dth/dq: snapshot; c1: snap_it | window << 8 | (stop_at + 1) << 16), not in registers
     auto brent = [&](bool go) -> bool {
       if (it == BRENT_FROM) {
-        sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs;
-        sm.it[slot] = it | (1 << 8);
+        sm.U2[slot] = us; sm.dth[slot] = ts; sm.dq[slot] = qs;
+        SI::set(sm.c1[slot], it | (1 << 8));
         return go;
       }
-      const int packed = sm.it[slot];
+      const int packed = SI::get(sm.c1[slot]);
       const int snap_it = packed & 0xff, window = (packed >> 8) & 0xff, stop_at = (packed >> 16) - 1;
       if (stop_at >= 0) {                         // finishing a detected cycle
         if (it < stop_at) return true;
@@ -706,22 +828,28 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
         return false;
       }
       if (!go) return false;
-      if (same_bits<FT>(us, sm.us[slot]) && same_bits<FT>(ts, sm.ts[slot]) && same_bits<FT>(qs, sm.qs[slot])) {
+      if (same_bits<FT>(us, sm.U2[slot]) && same_bits<FT>(ts, sm.dth[slot]) && same_bits<FT>(qs, sm.dq[slot])) {
         const int lambda = it - snap_it;
         const int stop = it + (F.maxit - it) % lambda;
-        sm.it[slot] = packed | ((stop + 1) << 16);
+        SI::set(sm.c1[slot], packed | ((stop + 1) << 16));
         if (it < stop) return true;
         it = F.maxit;
         return false;
       }
       if (it - snap_it == window) {
-        sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs;
-        sm.it[slot] = it | ((window * 2) << 8);
+        sm.U2[slot] = us; sm.dth[slot] = ts; sm.dq[slot] = qs;
+        SI::set(sm.c1[slot], it | ((window * 2) << 8));
       }
       return true;
     };
     pop();
-    while (__any_sync(0xffffffffu, slot >= 0)) {
+    for (;;) {
+      if (!__any_sync(0xffffffffu, slot >= 0)) {       // the whole warp is idle: help with the other class, once
+        if (moved) break;
+        moved = true; cls ^= 1;
+        pop();
+        continue;
+      }
       if (slot >= 0) {
         const FT u0 = us, t0 = ts, q0 = qs;
         if (__builtin_expect(!iterate_lean<FT, SPEC>(P, F, K, tb, lc, us, ts, qs), 0)) {
@@ -732,7 +860,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
         bool go = keep_going<FT>(F, it, us, ts, qs, u0, t0, q0);
         if (__builtin_expect(it >= BRENT_FROM && !fixed && F.maxit < 250, 0)) go = brent(go);   // (8-bit fields)
         if (!go) {
-          sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
+          sm.U2[slot] = us; sm.dth[slot] = ts; sm.dq[slot] = qs; SI::set(sm.c1[slot], it);
           pop();
         }
       }
@@ -743,19 +871,25 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
     FT su = 0, st = 0, sq = 0;
     int snap_it = 0, window = 1, stop_at = 0;
     auto pop = [&]() {
-      int pos = atomicAdd(&sm.head, 1);
+      const int pos = atomicAdd(&sm.head[cls], 1);
       slot = -1;
-      if (pos < n_total) {
-        slot = (pos < n_front) ? sm.queue[pos] : sm.queue[TILE - 1 - (pos - n_front)];
+      if (pos < (cls ? n_back : n_front)) {
+        slot = cls ? sm.queue[TILE - 1 - pos] : sm.queue[pos];
         U2 = sm.U2[slot]; dth = sm.dth[slot]; dq = sm.dq[slot];
-        { const FT Tv = sm.Tv[slot], qv = sm.qv[slot]; gTv = P.g / Tv; a1 = FT(1) + delta * qv; a2 = delta * Tv; }
+        { const FT Tv = sm.c1[slot], qv = sm.c2[slot]; gTv = P.g / Tv; a1 = FT(1) + delta * qv; a2 = delta * Tv; }
         nu = VARNU ? sm.nu[slot] : F.mr.visc.nu;
-        us = sm.us[slot]; ts = sm.ts[slot]; qs = sm.qs[slot]; it = sm.it[slot];
+        us = ts = qs = F.init; it = 0;
         su = us; st = ts; sq = qs; snap_it = it; window = 1; stop_at = -1;
       }
     };
     pop();
-    while (__any_sync(0xffffffffu, slot >= 0)) {
+    for (;;) {
+      if (!__any_sync(0xffffffffu, slot >= 0)) {       // the whole warp is idle: help with the other class, once
+        if (moved) break;
+        moved = true; cls ^= 1;
+        pop();
+        continue;
+      }
       if (slot >= 0) {
         const FT u0 = us, t0 = ts, q0 = qs;
         iterate_fast<FT, SPEC>(P, F, K, U2, dth, dq, gTv, a1, a2, nu, us, ts, qs);
@@ -778,7 +912,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
           }
         }
         if (!go) {
-          sm.us[slot] = us; sm.ts[slot] = ts; sm.qs[slot] = qs; sm.it[slot] = it;
+          sm.U2[slot] = us; sm.dth[slot] = ts; sm.dq[slot] = qs; SI::set(sm.c1[slot], it);
           pop();
         }
       }
@@ -787,7 +921,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
   __syncthreads();
 
   // ------------------------------------------------------------------ phase C
-  for (int cidx = tid; cidx < TILE; cidx += 128) {
+  for (int cidx = tid; cidx < TILE; cidx += NT) {
     const long long idx = tile0 + cidx;
     if (idx >= a.ncell) continue;
     const int jj = (int)(idx / a.nxr);
@@ -796,7 +930,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
     const FT Tunits = ldg<FT>(a.oT, i, j);
     const bool act = is_active(a.mask, i, j);
     FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0);
-    const FT us = sm.us[cidx], ts = sm.ts[cidx], qs = sm.qs[cidx];
+    const FT us = sm.U2[cidx], ts = sm.dth[cidx], qs = sm.dq[cidx];
     if (act) {
       // the exchange state was written by this very thread in phase A (or is an input): plain loads
       const FT ua = reinterpret_cast<const FT*>(a.xu.p)[(int64_t)i * a.xu.si + (int64_t)j * a.xu.sj];
@@ -807,14 +941,8 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
         du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
         dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
       } else { du = ua; dv = va; }
-#if COFLUX_TILE_CARRY
-      const FT rho = sm.rho[cidx], cp = sm.cp[cidx];
-#else
-      const FT pa = reinterpret_cast<const FT*>(a.xp.p)[(int64_t)i * a.xp.si + (int64_t)j * a.xp.sj];
-      const FT qa = reinterpret_cast<const FT*>(a.xq.p)[(int64_t)i * a.xq.si + (int64_t)j * a.xq.sj];
-      const Thermo<FT> atm = phase_equil_pTq(c, pa, Ta, qa);
-      const FT rho = atm.rho, cp = atm.cp_m;
-#endif
+      const FT rho = reinterpret_cast<const FT*>(a.rtx.p)[(int64_t)i * a.rtx.si + (int64_t)j * a.rtx.sj];
+      const FT cp = reinterpret_cast<const FT*>(a.rty.p)[(int64_t)i * a.rty.si + (int64_t)j * a.rty.sj];
       FT taux, tauy;
       if constexpr (LEAN) {
         const FT d2 = du * du + dv * dv;
@@ -835,7 +963,7 @@ __global__ void __launch_bounds__(128, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_ti
     stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
     stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tunits);
     stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
-    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? sm.it[cidx] : 0;
+    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? SI::get(sm.c1[cidx]) : 0;
     if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
     if (ASSEMBLE) {
       if (i >= 0 && i < a.Nx && j >= 0 && j < a.Ny) {

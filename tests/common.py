@@ -40,6 +40,11 @@ def make_case(Nx, Ny, Nz, bits=64, latitude=(-60.0, 60.0), flux_configuration="d
     grid = cj.LatitudeLongitudeGrid((Nx, Ny, Nz), latitude=latitude, halo=halo, dtype=np_dtype(bits))
     host = cj.SurfaceFluxData.synthetic(grid, ring=ring, **synth_kw)
     cfg = cj.default_config(Nx, Ny, Nz, bits, flux_configuration, velocity)
+    if flux_configuration == "default" and velocity == "wind":
+        # build_coupled_model ignores velocity_formulation for `:default` (omip_simulation.jl:127-133); a user gets wind
+        # velocities there through ComponentInterfaces(...; atmosphere_ocean_velocity_difference = WindVelocity())
+        cfg.atmosphere_ocean.velocity_formulation = _abi.VELOCITY_WIND
+        cfg.atmosphere_sea_ice.velocity_formulation = _abi.VELOCITY_WIND
     cfg.grid.ring = ring
     return grid, host, cfg
 

@@ -64,7 +64,16 @@ def test_flux_configurations_follow_omip_simulation():
     with pytest.raises(cj.CofluxError, match="Unknown flux_configuration: shear_aware. Options: default, corrected, ncar"):
         cj.default_config(8, 8, 2, flux_configuration="shear_aware")                                           # :159-160
     with pytest.raises(ValueError, match="Unknown velocity_formulation"):
-        cj.default_config(8, 8, 2, velocity_formulation="absolute")
+        cj.default_config(8, 8, 2, flux_configuration="corrected", velocity_formulation="absolute")
+    # `:default` returns before velocity_formulation is looked at (omip_simulation.jl:127-133): never validated, never applied
+    d = cj.default_config(8, 8, 2, flux_configuration="default", velocity_formulation="wind")
+    assert d.atmosphere_ocean.velocity_formulation == _abi.VELOCITY_RELATIVE
+    assert cj.default_config(8, 8, 2, velocity_formulation="absolute").atmosphere_sea_ice.velocity_formulation == _abi.VELOCITY_RELATIVE
+    lib = cj.load_library()
+    import ctypes
+    assert lib.coflux_apply_flux_configuration(ctypes.byref(d), b"default", 7) == 0      # the C entry agrees
+    assert d.atmosphere_ocean.velocity_formulation == _abi.VELOCITY_RELATIVE
+    assert lib.coflux_apply_flux_configuration(ctypes.byref(d), b"ncar", 7) == _abi.ERR_INVALID_ARGUMENT
 
 
 def test_python_parameter_objects_reproduce_the_presets():

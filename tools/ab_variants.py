@@ -11,11 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "t256_b4": [],
-    "t384_b4": ["COFLUX_ICE_TILE_CELLS=384"],
-    "t512_b3": ["COFLUX_ICE_TILE_CELLS=512", "COFLUX_ICE_MIN_BLOCKS=3"],
-    "t256_b5": ["COFLUX_ICE_MIN_BLOCKS=5"],
-    "t256_b6": ["COFLUX_ICE_MIN_BLOCKS=6"],
+    "base_256x3_768": [],
+    "pre0": ["COFLUX_TILE_PRE1=0"],
+    "d384x2_1152": ["COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=1152", "COFLUX_TILE_MIN_BLOCKS64=2"],
+    "d384x2_1536": ["COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=1536", "COFLUX_TILE_MIN_BLOCKS64=2"],
+    "s2_256x3_512": ["COFLUX_TILE_NT64_S2=256", "COFLUX_TILE_CELLS64_S2=512", "COFLUX_TILE_MIN_BLOCKS64_S2=3"],
+    "f32_384x3_1536": ["COFLUX_TILE_NT32=384", "COFLUX_TILE_CELLS32=1536", "COFLUX_TILE_MIN_BLOCKS32=3"],
 }
 
 
