@@ -10,7 +10,7 @@ from ._abi import CofluxError, load_library, default_config
 from .fields import Field, FieldTimeSeries, LatitudeLongitudeGrid, fractional_indices
 from .state import SurfaceFluxData
 from .engine import Engine
-from .forcing import InMemoryWindow
+from .forcing import InMemoryWindow, DeviceForcingWindow
 from .models import *  # noqa: F401,F403  (reference-facing names)
 
 load_library()   # fail loudly at import when lib/libcoflux.so has not been built

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COFLUX_LIB") or os.path.join(_HERE, "lib", "libcoflux.so")   # COFLUX_LIB: tuning variants
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, F64 = 32, 64
 
 # status codes
@@ -30,6 +30,7 @@ TEMPERATURE_CELSIUS, TEMPERATURE_KELVIN = 0, 1
 ICE_OCEAN_ICE_BATH, ICE_OCEAN_THREE_EQUATION = 0, 1
 FRICTION_VELOCITY_CONSTANT, FRICTION_VELOCITY_MOMENTUM_BASED = 0, 1
 TIME_LINEAR, TIME_CYCLICAL, TIME_CLAMP = 0, 1, 2
+SEA_ICE_ALBEDO_PRESCRIBED, SEA_ICE_ALBEDO_CCSM3 = 0, 1
 SEAM_HANDLE_BYTES = 128
 
 i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
@@ -88,9 +89,17 @@ class OceanProperties(C.Structure):
                 ("constituent_mass_fraction", f64 * 4)]
 
 
+class Ccsm3Albedo(C.Structure):
+    _fields_ = [(n, f64) for n in (
+        "ice_visible", "ice_near_infrared", "snow_visible", "snow_near_infrared", "thickness_scale",
+        "melt_temperature_range", "ice_melt_change", "snow_visible_melt_change", "snow_near_infrared_melt_change",
+        "snow_patchiness", "ocean_albedo", "visible_fraction", "melting_temperature")]
+
+
 class RadiationProperties(C.Structure):
     _fields_ = [("stefan_boltzmann_constant", f64), ("ocean_albedo", f64), ("ocean_emissivity", f64),
-                ("sea_ice_emissivity", f64), ("sea_ice_albedo", f64), ("shortwave_penetrates", i32), ("reserved", i32)]
+                ("sea_ice_emissivity", f64), ("sea_ice_albedo", f64), ("shortwave_penetrates", i32),
+                ("sea_ice_albedo_kind", i32), ("ccsm3", Ccsm3Albedo)]
 
 
 class IceOceanParams(C.Structure):
@@ -114,7 +123,13 @@ class Config(C.Structure):
 class AtmosSeries(C.Structure):
     _fields_ = [(n, Array) for n in ("u", "v", "T", "q", "p", "Qs", "Ql", "rain", "snow")] + [
         ("times", C.POINTER(f64)), ("Nt", i32), ("time_indexing", i32), ("cycle_period", f64),
-        ("fi", Array), ("fj", Array), ("cos_theta", Array), ("sin_theta", Array)]
+        ("fi", Array), ("fj", Array), ("cos_theta", Array), ("sin_theta", Array),
+        ("ring_start", i32), ("ring_capacity", i32)]
+
+
+class LandSeries(C.Structure):
+    _fields_ = [("rivers", Array), ("icebergs", Array), ("times", C.POINTER(f64)), ("Nt", i32), ("time_indexing", i32),
+                ("cycle_period", f64), ("fi", Array), ("fj", Array), ("ring_start", i32), ("ring_capacity", i32)]
 
 
 class ExchangeState(C.Structure):
@@ -149,9 +164,19 @@ class NetOceanFluxes(C.Structure):
                                      "downwelling_shortwave", "penetrating_shortwave")]
 
 
+class NetSeaIceFluxes(C.Structure):
+    _fields_ = [(n, Array) for n in ("top_heat", "bottom_heat", "top_u", "top_v")]
+
+
+class FluxAverages(C.Structure):
+    _fields_ = [(n, Array) for n in ("tau_x", "tau_y", "JT", "JS", "Qc", "Qv", "JT_atmosphere_ocean", "JT_ice_ocean",
+                                     "JS_ice_ocean", "JT_frazil")] + [("previous_interval", f64), ("dt", f64)]
+
+
 class UpdateInputs(C.Structure):
     _fields_ = [("atmosphere", C.POINTER(AtmosSeries)), ("ocean", C.POINTER(OceanSurface)),
-                ("sea_ice", C.POINTER(SeaIceState)), ("ice_ocean", C.POINTER(IceOceanFluxes))]
+                ("sea_ice", C.POINTER(SeaIceState)), ("ice_ocean", C.POINTER(IceOceanFluxes)),
+                ("land", C.POINTER(LandSeries))]
 
 
 class UpdateOutputs(C.Structure):
@@ -182,7 +207,9 @@ STRUCTS = {"array": Array, "air_viscosity": AirViscosity, "momentum_roughness": 
            "ocean_surface": OceanSurface, "interface_fluxes": InterfaceFluxes, "sea_ice_state": SeaIceState,
            "ocean_columns": OceanColumns, "ice_ocean_fluxes": IceOceanFluxes, "net_ocean_fluxes": NetOceanFluxes,
            "update_inputs": UpdateInputs, "update_outputs": UpdateOutputs, "host_step": HostStep,
-           "salinity_normalization": SalinityNormalization, "closure_forcing": ClosureForcing}
+           "salinity_normalization": SalinityNormalization, "closure_forcing": ClosureForcing,
+           "land_series": LandSeries, "ccsm3_albedo": Ccsm3Albedo, "net_sea_ice_fluxes": NetSeaIceFluxes,
+           "flux_averages": FluxAverages}
 
 # every symbol include/coflux.h declares
 EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "coflux_sizeof", "coflux_default_config",
@@ -191,7 +218,11 @@ EXPORTS = ("coflux_abi_version", "coflux_last_error", "coflux_build_info", "cofl
            "coflux_sea_ice_ocean_fluxes", "coflux_assemble_net_ocean_fluxes", "coflux_update_state",
            "coflux_update_state_host", "coflux_launch_count", "coflux_profile_enable", "coflux_profile_read", "coflux_seam_export", "coflux_seam_attach",
            "coflux_seam_detach", "coflux_salinity_flux_sums", "coflux_subtract_mean_flux", "coflux_normalize_salinity_flux",
-           "coflux_closure_surface_forcing", "coflux_attach_closure_forcing")
+           "coflux_closure_surface_forcing", "coflux_attach_closure_forcing",
+           "coflux_interpolate_land", "coflux_assemble_net_sea_ice_fluxes", "coflux_attach_flux_averages",
+           "coflux_accumulate_flux_averages", "coflux_forcing_window_create", "coflux_forcing_window_destroy",
+           "coflux_forcing_window_upload", "coflux_forcing_window_field", "coflux_forcing_window_wait",
+           "coflux_forcing_window_release", "coflux_forcing_window_stats")
 
 
 class CofluxError(RuntimeError):
@@ -245,6 +276,26 @@ def load_library(path=None):
     lib.coflux_normalize_salinity_flux.argtypes = [vp, P(SalinityNormalization), vp]
     lib.coflux_closure_surface_forcing.argtypes = [vp, P(NetOceanFluxes), P(ClosureForcing), vp]
     lib.coflux_attach_closure_forcing.argtypes = [vp, P(ClosureForcing)]
+    lib.coflux_interpolate_land.argtypes = [vp, P(LandSeries), f64, P(ExchangeState), vp]
+    lib.coflux_assemble_net_sea_ice_fluxes.argtypes = [vp, P(ExchangeState), P(OceanSurface), P(SeaIceState), P(InterfaceFluxes),
+                                                       P(IceOceanFluxes), P(NetSeaIceFluxes), vp]
+    lib.coflux_attach_flux_averages.argtypes = [vp, P(FluxAverages)]
+    lib.coflux_accumulate_flux_averages.argtypes = [vp, P(NetOceanFluxes), P(InterfaceFluxes), P(SeaIceState), P(IceOceanFluxes),
+                                                    P(FluxAverages), vp]
+    lib.coflux_forcing_window_create.argtypes = [P(vp), vp, i32, i64, i32]
+    lib.coflux_forcing_window_destroy.argtypes = [vp]
+    lib.coflux_forcing_window_upload.argtypes = [vp, i64, P(vp)]
+    lib.coflux_forcing_window_field.argtypes = [vp, i32, P(vp)]
+    lib.coflux_forcing_window_wait.argtypes = [vp, i64, i64, vp]
+    lib.coflux_forcing_window_release.argtypes = [vp, i64, i64, vp]
+    lib.coflux_forcing_window_stats.argtypes = [vp, P(i64), P(i64)]
+    # layout check: a binding whose struct mirrors drifted from the header must not run (it would corrupt memory)
+    if lib.coflux_abi_version() != ABI_VERSION:
+        raise ImportError(f"{p}: library ABI version {lib.coflux_abi_version()} != binding {ABI_VERSION}; rebuild (python __graft_entry__.py)")
+    for sname, cls in STRUCTS.items():
+        n = lib.coflux_sizeof(sname.encode())
+        if n != C.sizeof(cls):
+            raise ImportError(f"{p}: sizeof(coflux_{sname}) is {n} in the library but {C.sizeof(cls)} in the ctypes mirror; rebuild the library")
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("coflux_abi_version", "coflux_sizeof"):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SRC = os.path.join(HERE, "csrc", "coflux_abi.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "coflux_kernels.cuh"), os.path.join(HERE, "csrc", "coflux_solve_tile.cuh"), os.path.join(HERE, "csrc", "coflux_psi_table.h"), os.path.join(HERE, "csrc", "coflux_fastmath.cuh"), os.path.join(HERE, "csrc", "coflux_math_tables.h"), os.path.join(HERE, "csrc", "coflux_device.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "coflux_kernels.cuh"), os.path.join(HERE, "csrc", "coflux_solve_tile.cuh"), os.path.join(HERE, "csrc", "coflux_solve_stream.cuh"), os.path.join(HERE, "csrc", "coflux_psi_table.h"), os.path.join(HERE, "csrc", "coflux_fastmath.cuh"), os.path.join(HERE, "csrc", "coflux_math_tables.h"), os.path.join(HERE, "csrc", "coflux_device.cuh"),
         os.path.join(ROOT, "include", "coflux.h")]
 OUT = os.path.join(HERE, "lib", "libcoflux.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -12,7 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
-#include "coflux_solve_tile.cuh"
+#include <vector>
+#include "coflux_solve_stream.cuh"
 #include <cstdlib>
 #include <unistd.h>
 
@@ -51,6 +52,7 @@ extern "C" int coflux_sizeof(const char* name) {
   SZ(atmosphere_properties); SZ(ocean_properties); SZ(radiation_properties); SZ(ice_ocean_params); SZ(grid_desc);
   SZ(config); SZ(atmos_series); SZ(exchange_state); SZ(ocean_surface); SZ(interface_fluxes); SZ(sea_ice_state);
   SZ(ocean_columns); SZ(ice_ocean_fluxes); SZ(net_ocean_fluxes); SZ(update_inputs); SZ(update_outputs); SZ(host_step); SZ(salinity_normalization); SZ(closure_forcing);
+  SZ(land_series); SZ(ccsm3_albedo); SZ(net_sea_ice_fluxes); SZ(flux_averages);
 #undef SZ
   return -1;
 }
@@ -101,6 +103,9 @@ static const int SALT_BLOCKS = 148 * 8;   // CTAs of the salinity-flux reduction
 struct coflux_ctx {
   bool closure_on = false;               // coflux_attach_closure_forcing: by-products emitted by the stress kernel
   coflux_closure_forcing closure;
+  bool avg_on = false;                   // coflux_attach_flux_averages: running averages updated by the fused kernels
+  coflux_flux_averages avg;
+  int sm_count = 0;
   double* salt_ws = nullptr;             // [2 * SALT_BLOCKS] CTA partials + [2] totals of the salinity-flux reduction
   coflux_config cfg;
   Profile prof;
@@ -229,6 +234,12 @@ extern "C" int coflux_default_config(coflux_config* cfg, int32_t Nx, int32_t Ny,
   r.ocean_albedo = 0.06; r.ocean_emissivity = 1.0;   // atmosphere.jl:43 (OMIP-2 ocean surface)
   r.sea_ice_emissivity = 1.0; r.sea_ice_albedo = 0.7;
   r.shortwave_penetrates = 1;
+  r.sea_ice_albedo_kind = COFLUX_SEA_ICE_ALBEDO_PRESCRIBED;
+  coflux_ccsm3_albedo& a = r.ccsm3;      // CCSM3 / CICE "ccsm3" constants (Briegleb et al. 2004)
+  a.ice_visible = 0.78; a.ice_near_infrared = 0.36; a.snow_visible = 0.98; a.snow_near_infrared = 0.70;
+  a.thickness_scale = 0.3; a.melt_temperature_range = 1.5; a.ice_melt_change = 0.075;
+  a.snow_visible_melt_change = 0.10; a.snow_near_infrared_melt_change = 0.15; a.snow_patchiness = 0.02;
+  a.ocean_albedo = 0.06; a.visible_fraction = 0.52; a.melting_temperature = 273.15;
   return COFLUX_OK;
 }
 
@@ -397,6 +408,16 @@ static int validate_config(const coflux_config* c) {
   const coflux_radiation_properties& r = c->radiation;
   const double rv[5] = {r.stefan_boltzmann_constant, r.ocean_albedo, r.ocean_emissivity, r.sea_ice_emissivity, r.sea_ice_albedo};
   if (!finite_all(rv, 5)) return fail(COFLUX_ERR_INVALID_ARGUMENT, "non-finite radiation property");
+  if (r.sea_ice_albedo_kind != COFLUX_SEA_ICE_ALBEDO_PRESCRIBED && r.sea_ice_albedo_kind != COFLUX_SEA_ICE_ALBEDO_CCSM3)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "unknown sea_ice_albedo_kind %d", r.sea_ice_albedo_kind);
+  if (r.sea_ice_albedo_kind == COFLUX_SEA_ICE_ALBEDO_CCSM3) {
+    const coflux_ccsm3_albedo& a = r.ccsm3;
+    const double cv[13] = {a.ice_visible, a.ice_near_infrared, a.snow_visible, a.snow_near_infrared, a.thickness_scale,
+                           a.melt_temperature_range, a.ice_melt_change, a.snow_visible_melt_change, a.snow_near_infrared_melt_change,
+                           a.snow_patchiness, a.ocean_albedo, a.visible_fraction, a.melting_temperature};
+    if (!finite_all(cv, 13) || !(a.thickness_scale > 0) || !(a.melt_temperature_range > 0) || !(a.snow_patchiness > 0))
+      return fail(COFLUX_ERR_INVALID_ARGUMENT, "CCSM3 albedo parameters must be finite (thickness_scale, melt_temperature_range, snow_patchiness > 0)");
+  }
   return COFLUX_OK;
 }
 
@@ -455,6 +476,15 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
   P.T_offset = (c.ocean.temperature_units == COFLUX_TEMPERATURE_CELSIUS) ? (FT)273.15 : (FT)0;
   P.sigma = (FT)c.radiation.stefan_boltzmann_constant; P.alb_o = (FT)c.radiation.ocean_albedo; P.emis_o = (FT)c.radiation.ocean_emissivity;
   P.emis_i = (FT)c.radiation.sea_ice_emissivity; P.alb_i = (FT)c.radiation.sea_ice_albedo; P.sw_pen = c.radiation.shortwave_penetrates;
+  P.ice_albedo_kind = c.radiation.sea_ice_albedo_kind;
+  {
+    const coflux_ccsm3_albedo& a = c.radiation.ccsm3;
+    P.ccsm3.ice_v = (FT)a.ice_visible; P.ccsm3.ice_n = (FT)a.ice_near_infrared; P.ccsm3.snow_v = (FT)a.snow_visible;
+    P.ccsm3.snow_n = (FT)a.snow_near_infrared; P.ccsm3.hmax = (FT)a.thickness_scale; P.ccsm3.dT = (FT)a.melt_temperature_range;
+    P.ccsm3.d_ice = (FT)a.ice_melt_change; P.ccsm3.d_snow_v = (FT)a.snow_visible_melt_change;
+    P.ccsm3.d_snow_n = (FT)a.snow_near_infrared_melt_change; P.ccsm3.hpatch = (FT)a.snow_patchiness;
+    P.ccsm3.alb_o = (FT)a.ocean_albedo; P.ccsm3.fvis = (FT)a.visible_fraction; P.ccsm3.Tmelt = (FT)a.melting_temperature;
+  }
   P.ao = to_dev<FT>(c.atmosphere_ocean);
   P.ai = to_dev<FT>(c.atmosphere_sea_ice);
   {
@@ -508,6 +538,7 @@ extern "C" int coflux_create(coflux_ctx** out, const coflux_config* cfg) {
   c->device = cfg->device;
   c->P64 = make_dev_params<double>(*cfg);
   c->P32 = make_dev_params<float>(*cfg);
+  c->sm_count = prop.multiProcessorCount;
   *out = c;
   return COFLUX_OK;
 }
@@ -633,9 +664,11 @@ static inline DArr view2d_opt(const coflux_array* a, int k, size_t esize) {
   if (!a) return DArr{nullptr, 0, 0};
   return view2d(*a, k, esize);
 }
-static inline DSeries view_series(const coflux_array& a, int n1, int n2, size_t esize) {
+// ring_capacity > 0: logical level n lives in time slot (ring_start + n) mod ring_capacity (coflux_forcing_window)
+static inline DSeries view_series(const coflux_array& a, int n1, int n2, size_t esize, int ring_start = 0, int ring_capacity = 0) {
   DSeries s{nullptr, nullptr, 0, 0};
   if (!a.ptr) return s;
+  if (ring_capacity > 0) { n1 = (ring_start + n1) % ring_capacity; n2 = (ring_start + n2) % ring_capacity; }
   const int64_t off = (int64_t)a.off_i * a.stride_i + (int64_t)a.off_j * a.stride_j + (int64_t)a.off_k * a.stride_k;
   s.p1 = static_cast<char*>(a.ptr) + (off + (int64_t)n1 * a.stride_n) * (int64_t)esize;
   s.p2 = static_cast<char*>(a.ptr) + (off + (int64_t)n2 * a.stride_n) * (int64_t)esize;
@@ -700,9 +733,12 @@ static int fill_interp(const coflux_ctx* c, const coflux_atmos_series* in, doubl
     const coflux_array* xs[8] = {&out->u, &out->v, &out->T, &out->p, &out->q, &out->Qs, &out->Ql, &out->Mp};
     for (const coflux_array* p : xs) HALO(*p, ring, ring, "exchange state");
   }
-  a.su = view_series(in->u, n1, n2, es); a.sv = view_series(in->v, n1, n2, es); a.sT = view_series(in->T, n1, n2, es);
-  a.sq = view_series(in->q, n1, n2, es); a.sp = view_series(in->p, n1, n2, es); a.sQs = view_series(in->Qs, n1, n2, es);
-  a.sQl = view_series(in->Ql, n1, n2, es); a.srain = view_series(in->rain, n1, n2, es); a.ssnow = view_series(in->snow, n1, n2, es);
+  REQUIRE(in->ring_capacity >= 0 && in->ring_start >= 0 && (in->ring_capacity == 0 || in->Nt <= in->ring_capacity),
+          "atmosphere series: bad ring_start / ring_capacity (Nt must not exceed the ring capacity)");
+  const int rs = in->ring_start, rc_ = in->ring_capacity;
+  a.su = view_series(in->u, n1, n2, es, rs, rc_); a.sv = view_series(in->v, n1, n2, es, rs, rc_); a.sT = view_series(in->T, n1, n2, es, rs, rc_);
+  a.sq = view_series(in->q, n1, n2, es, rs, rc_); a.sp = view_series(in->p, n1, n2, es, rs, rc_); a.sQs = view_series(in->Qs, n1, n2, es, rs, rc_);
+  a.sQl = view_series(in->Ql, n1, n2, es, rs, rc_); a.srain = view_series(in->rain, n1, n2, es, rs, rc_); a.ssnow = view_series(in->snow, n1, n2, es, rs, rc_);
   a.fi = view2d(in->fi, 0, es); a.fj = view2d(in->fj, 0, es);
   a.cs = view2d(in->cos_theta, 0, es); a.sn = view2d(in->sin_theta, 0, es);
   a.nfrac = (FT)frac;
@@ -719,6 +755,35 @@ template <typename FT> static int fill_exchange_in(const coflux_exchange_state* 
   a.xq = view2d(x->q, 0, es); a.xQs = view2d(x->Qs, 0, es); a.xQl = view2d(x->Ql, 0, es); a.xMp = view2d(x->Mp, 0, es);
   return COFLUX_OK;
 }
+// land freshwater series (rivers + icebergs): own source grid, own time axis
+template <typename FT> static int fill_land(const coflux_ctx* c, const coflux_land_series* in, double time, FluxArgs<FT>& a) {
+  if (!in) return COFLUX_OK;
+  REQUIRE(in->rivers.ptr || in->icebergs.ptr, "land series: rivers and icebergs are both absent");
+  REQUIRE(in->fi.ptr && in->fj.ptr, "land series: fractional indices fi, fj are required");
+  REQUIRE(in->ring_capacity >= 0 && in->ring_start >= 0 && (in->ring_capacity == 0 || in->Nt <= in->ring_capacity),
+          "land series: bad ring_start / ring_capacity");
+  int32_t n1, n2; double frac;
+  int rc = coflux_time_indices(in->times, in->Nt, in->time_indexing, in->cycle_period, time, &n1, &n2, &frac);
+  if (rc) return rc;
+  const size_t es = sizeof(FT);
+  const int ring = c->cfg.grid.ring;
+  HALO(in->fi, ring, ring, "land fi"); HALO(in->fj, ring, ring, "land fj");
+  a.sriv = view_series(in->rivers, n1, n2, es, in->ring_start, in->ring_capacity);
+  a.sicb = view_series(in->icebergs, n1, n2, es, in->ring_start, in->ring_capacity);
+  a.lfi = view2d(in->fi, 0, es); a.lfj = view2d(in->fj, 0, es);
+  a.lnfrac = (FT)frac;
+  return COFLUX_OK;
+}
+template <typename FT> static void fill_avg(const coflux_ctx* c, AvgArgs<FT>& g) {
+  if (!c->avg_on) { g.on = 0; return; }
+  const size_t es = sizeof(FT);
+  const coflux_flux_averages& v = c->avg;
+  g.on = 1;
+  g.JT = view2d(v.JT, 0, es); g.JS = view2d(v.JS, 0, es); g.Qc = view2d(v.Qc, 0, es); g.Qv = view2d(v.Qv, 0, es);
+  g.JTao = view2d(v.JT_atmosphere_ocean, 0, es); g.JTio = view2d(v.JT_ice_ocean, 0, es); g.JSio = view2d(v.JS_ice_ocean, 0, es);
+  g.T = (FT)v.previous_interval; g.dt = (FT)v.dt;
+}
+
 template <typename FT> static int fill_ocean(const coflux_ctx* c, const coflux_ocean_surface* o, FluxArgs<FT>& a) {
   REQUIRE(o, "NULL ocean surface");
   REQUIRE(o->u.ptr && o->v.ptr && o->T.ptr && o->S.ptr, "ocean u, v, T, S are required");
@@ -817,8 +882,47 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   kern<<<grid_for(a.ncell - a.cell0, TILE), TT::NT, smem, st>>>(a);
   return COFLUX_OK;
 }
+// COFLUX_KERNEL=stream selects the persistent warp-specialised kernel (coflux_solve_stream.cuh: one CTA per SM for the
+// whole launch) for the OMIP parameter sets.  Measured on B200 (profiles/README.md, round 2): bit-identical results, but
+// 6.4 ms against 3.3 ms at 1/12° Float64 — with 24 register-limited warps per SM the 7 service warps cannot feed the
+// solver lanes (19 of 32 active) and the two instruction streams thrash the instruction cache (26 % no_inst stalls).
+// The tile kernel stays the production path.
+static bool use_stream_kernel() {
+  static const bool f = [] { const char* e = std::getenv("COFLUX_KERNEL"); return e && !strcmp(e, "stream"); }();
+  return f;
+}
+template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_stream_spec(const FluxArgs<FT>& a, cudaStream_t st) {
+  using TT = StreamTraits<FT, SPEC>;
+  auto kern = flux_stream_kernel<FT, INTERP, ASSEMBLE, SPEC>;
+  const size_t smem = sizeof(StreamSmem<FT, TT::NB, TT::VARNU>);
+  static unsigned long long configured = 0;
+  static int sm_count[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!(configured >> (dev & 63) & 1ull)) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    configured |= 1ull << (dev & 63);
+  }
+  const long long nchunks = (a.ncell - a.cell0 + 31) / 32;
+  const long long per_cta = 16;                                  // do not spread a small launch thinner than 16 chunks per CTA
+  long long grid = (nchunks + per_cta - 1) / per_cta;
+  if (grid > sm_count[dev & 63]) grid = sm_count[dev & 63];
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, TT::NT, smem, st>>>(a);
+  return COFLUX_OK;
+}
 template <typename FT, bool INTERP, bool ASSEMBLE> static int launch_tile(const coflux_ctx* c, const FluxArgs<FT>& a, cudaStream_t st) {
-  switch (tile_spec<FT>(c)) {
+  const int spec = tile_spec<FT>(c);
+  constexpr bool lean = (COFLUX_LEAN != 0) && (sizeof(FT) == 8 || (COFLUX_LEAN_F32 != 0));
+  if constexpr (lean) {
+    if (use_stream_kernel() && dev_params<FT>(c).ao.maxit < 250) {
+      if (spec == 1) return launch_stream_spec<FT, INTERP, ASSEMBLE, 1>(a, st);
+      if (spec == 2) return launch_stream_spec<FT, INTERP, ASSEMBLE, 2>(a, st);
+    }
+  }
+  switch (spec) {
     case 1: return launch_tile_spec<FT, INTERP, ASSEMBLE, 1>(a, st);
     case 2: return launch_tile_spec<FT, INTERP, ASSEMBLE, 2>(a, st);
     default: return launch_tile_spec<FT, INTERP, ASSEMBLE, 0>(a, st);
@@ -899,7 +1003,7 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   a.oS = DArr{nullptr, 0, 0};
   a.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
   a.ih = view2d(ice->thickness, 0, es); a.iS = view2d(ice->salinity, 0, es); a.ialb = view2d(ice->albedo, 0, es);
-  a.iconc = view2d(ice->concentration, 0, es);
+  a.iconc = view2d(ice->concentration, 0, es); a.ihs = view2d(ice->snow_thickness, 0, es);
   rc = check_interface_halos<FT>(c, f);
   if (rc) return rc;
   fill_interface_out<FT>(f, a);
@@ -953,6 +1057,7 @@ static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* 
   a.Qf = view2d(f->frazil_heat, 0, es); a.Qio = view2d(f->interface_heat, 0, es); a.Js = view2d(f->salt, 0, es);
   a.tx = view2d(f->x_momentum, 0, es); a.ty = view2d(f->y_momentum, 0, es);
   a.dt = (FT)dt;
+  if (c->avg_on) { a.avg_JTf = view2d(c->avg.JT_frazil, 0, es); a.avg_T = (FT)c->avg.previous_interval; a.avg_dt = (FT)c->avg.dt; }
   a.P = dev_params<FT>(c);
   ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, COFLUX_IO_BLOCK), COFLUX_IO_BLOCK, 0, st>>>(a);
   return check_launch(c, 1);
@@ -1066,8 +1171,15 @@ static int build_update_args(coflux_ctx* c, const coflux_update_inputs* in, cofl
   a.JT = view2d(n->T, 0, es); a.JS = view2d(n->S, 0, es); a.Qu = view2d(n->upwelling_longwave, 0, es);
   a.Qal = view2d(n->downwelling_longwave, 0, es); a.Qts = view2d(n->downwelling_shortwave, 0, es);
   a.J0 = view2d(n->penetrating_shortwave, 0, es);
+  rc = fill_land<FT>(c, in->land, time, a);
+  if (rc) return rc;
+  fill_avg<FT>(c, a.avg);
   memset(&s, 0, sizeof(s));
   fill_stress<FT>(c, in->ocean, out->atmosphere_ocean, ice, io, n, s);
+  if (c->avg_on) {
+    s.avg_tx = view2d(c->avg.tau_x, 0, es); s.avg_ty = view2d(c->avg.tau_y, 0, es);
+    s.avg_T = (FT)c->avg.previous_interval; s.avg_dt = (FT)c->avg.dt;
+  }
   return COFLUX_OK;
 }
 // flux kernel over rows jj ∈ [jj_lo, jj_hi) of the ring-extended surface
@@ -1263,6 +1375,221 @@ extern "C" int coflux_update_state_host(coflux_ctx* c, const coflux_atmos_series
   CUDA_TRY(cudaSetDevice(c->device));
   return c->cfg.dtype == COFLUX_F64 ? do_update_host<double>(c, atm, step, time, h2d_bytes, d2h_bytes)
                                     : do_update_host<float>(c, atm, step, time, h2d_bytes, d2h_bytes);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// land freshwater, stand-alone (JRA55PrescribedLand: friver + licalvf → exchange Mp)
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_land(coflux_ctx* c, const coflux_land_series* in, double time, coflux_exchange_state* x, cudaStream_t st) {
+  FluxArgs<FT> a;
+  zero_args(a);
+  fill_geometry(c, a);
+  REQUIRE(x->Mp.ptr, "exchange Mp is required");
+  HALO(x->Mp, c->cfg.grid.ring, c->cfg.grid.ring, "exchange Mp");
+  a.xMp = view2d(x->Mp, 0, sizeof(FT));
+  int rc = fill_land<FT>(c, in, time, a);
+  if (rc) return rc;
+  land_kernel<FT><<<grid_for(a.ncell, 256), 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_interpolate_land(coflux_ctx* c, const coflux_land_series* in, double time, coflux_exchange_state* x, void* stream) {
+  REQUIRE(c && in && x, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_land<double>(c, in, time, x, st) : do_land<float>(c, in, time, x, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_net_sea_ice_fluxes! (§8f row 1)
+// ---------------------------------------------------------------------------------------------
+template <typename FT>
+static int do_net_ice(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o, const coflux_sea_ice_state* ice,
+                      const coflux_interface_fluxes* ai, const coflux_ice_ocean_fluxes* io, coflux_net_sea_ice_fluxes* out, cudaStream_t st) {
+  REQUIRE(x->Qs.ptr && x->Ql.ptr, "exchange state Qs, Ql are required");
+  REQUIRE(ice->top_temperature.ptr && ice->concentration.ptr, "sea ice top_temperature and concentration are required");
+  REQUIRE(ai->sensible_heat.ptr && ai->latent_heat.ptr, "atmosphere-sea-ice sensible and latent heat fluxes are required");
+  REQUIRE(out->top_heat.ptr && out->bottom_heat.ptr, "top_heat and bottom_heat outputs are required");
+  REQUIRE((!out->top_u.ptr || ai->x_momentum.ptr) && (!out->top_v.ptr || ai->y_momentum.ptr), "top stresses need the atmosphere-sea-ice momentum fluxes");
+  const DevParams<FT>& P = dev_params<FT>(c);
+  REQUIRE(P.ice_albedo_kind != COFLUX_SEA_ICE_ALBEDO_CCSM3 || ice->thickness.ptr, "the CCSM3 albedo needs the ice thickness");
+  if (out->top_u.ptr) HALO(ai->x_momentum, 1, 0, "atmosphere-sea-ice x_momentum");
+  if (out->top_v.ptr) HALO(ai->y_momentum, 0, 1, "atmosphere-sea-ice y_momentum");
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = sizeof(FT);
+  NetIceArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.Nx = g.Nx; a.Ny = g.Ny; a.wrap_x = (g.ring == 0 && g.periodic_x) ? 1 : 0;
+  a.Qs = view2d(x->Qs, 0, es); a.Ql = view2d(x->Ql, 0, es);
+  a.Ttop = view2d(ice->top_temperature, 0, es); a.conc = view2d(ice->concentration, 0, es); a.ih = view2d(ice->thickness, 0, es);
+  a.ihs = view2d(ice->snow_thickness, 0, es); a.ialb = view2d(ice->albedo, 0, es);
+  a.Qc = view2d(ai->sensible_heat, 0, es); a.Qv = view2d(ai->latent_heat, 0, es);
+  a.rtx = view2d(ai->x_momentum, 0, es); a.rty = view2d(ai->y_momentum, 0, es);
+  a.Qf = io ? view2d(io->frazil_heat, 0, es) : DArr{nullptr, 0, 0};
+  a.Qi = io ? view2d(io->interface_heat, 0, es) : DArr{nullptr, 0, 0};
+  a.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
+  a.top = view2d(out->top_heat, 0, es); a.bottom = view2d(out->bottom_heat, 0, es);
+  a.top_u = view2d(out->top_u, 0, es); a.top_v = view2d(out->top_v, 0, es);
+  a.P = P;
+  net_sea_ice_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_assemble_net_sea_ice_fluxes(coflux_ctx* c, const coflux_exchange_state* x, const coflux_ocean_surface* o,
+                                                  const coflux_sea_ice_state* ice, const coflux_interface_fluxes* ai,
+                                                  const coflux_ice_ocean_fluxes* io, coflux_net_sea_ice_fluxes* out, void* stream) {
+  REQUIRE(c && x && ice && ai && out, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_net_ice<double>(c, x, o, ice, ai, io, out, st) : do_net_ice<float>(c, x, o, ice, ai, io, out, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// time-averaged flux diagnostics (§8f row 4; omip_diagnostics.jl:77-89, 125-158)
+// ---------------------------------------------------------------------------------------------
+static int check_averages(const coflux_flux_averages* v) {
+  REQUIRE(std::isfinite(v->previous_interval) && std::isfinite(v->dt) && v->previous_interval >= 0 && v->dt > 0,
+          "flux averages: previous_interval must be >= 0 and dt > 0");
+  return COFLUX_OK;
+}
+extern "C" int coflux_attach_flux_averages(coflux_ctx* c, const coflux_flux_averages* v) {
+  REQUIRE(c, "NULL context");
+  if (!v) { c->avg_on = false; return COFLUX_OK; }
+  int rc = check_averages(v);
+  if (rc) return rc;
+  c->avg = *v;
+  c->avg_on = true;
+  return COFLUX_OK;
+}
+template <typename FT>
+static int do_averages(coflux_ctx* c, const coflux_net_ocean_fluxes* net, const coflux_interface_fluxes* ao, const coflux_sea_ice_state* ice,
+                       const coflux_ice_ocean_fluxes* io, const coflux_flux_averages* v, cudaStream_t st) {
+  const coflux_grid_desc& g = c->cfg.grid;
+  const size_t es = sizeof(FT);
+  FluxAvgArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.Nx = g.Nx; a.Ny = g.Ny;
+  a.tx = view2d(net->u, 0, es); a.ty = view2d(net->v, 0, es); a.JT = view2d(net->T, 0, es); a.JS = view2d(net->S, 0, es);
+  if (ao) { a.Qc = view2d(ao->sensible_heat, 0, es); a.Qv = view2d(ao->latent_heat, 0, es); }
+  if (ice) a.conc = view2d(ice->concentration, 0, es);
+  if (io) { a.Qio = view2d(io->interface_heat, 0, es); a.salt_io = view2d(io->salt, 0, es); a.Qf = view2d(io->frazil_heat, 0, es); }
+  a.a_tx = view2d(v->tau_x, 0, es); a.a_ty = view2d(v->tau_y, 0, es); a.a_JT = view2d(v->JT, 0, es); a.a_JS = view2d(v->JS, 0, es);
+  a.a_Qc = view2d(v->Qc, 0, es); a.a_Qv = view2d(v->Qv, 0, es); a.a_JTao = view2d(v->JT_atmosphere_ocean, 0, es);
+  a.a_JTio = view2d(v->JT_ice_ocean, 0, es); a.a_JSio = view2d(v->JS_ice_ocean, 0, es); a.a_JTf = view2d(v->JT_frazil, 0, es);
+  a.T = (FT)v->previous_interval; a.dt = (FT)v->dt;
+  a.rho0 = dev_params<FT>(c).rho0; a.c0 = dev_params<FT>(c).c0;
+  flux_average_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, 256), 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+extern "C" int coflux_accumulate_flux_averages(coflux_ctx* c, const coflux_net_ocean_fluxes* net, const coflux_interface_fluxes* ao,
+                                               const coflux_sea_ice_state* ice, const coflux_ice_ocean_fluxes* io,
+                                               const coflux_flux_averages* v, void* stream) {
+  REQUIRE(c && net && v, "NULL argument");
+  int rc = check_averages(v);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return c->cfg.dtype == COFLUX_F64 ? do_averages<double>(c, net, ao, ice, io, v, st) : do_averages<float>(c, net, ao, ice, io, v, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device forcing window (§8f row 2; time_indices_in_memory + prefetch, atmosphere.jl:22-27)
+// ---------------------------------------------------------------------------------------------
+struct coflux_forcing_window {
+  int device = 0, n_fields = 0, capacity = 0;
+  int64_t plane_elements = 0;
+  size_t esize = 8;
+  std::vector<char*> field;                 // per field: capacity × plane_elements elements
+  std::vector<cudaEvent_t> uploaded;        // per slot: the upload of the level it holds has landed
+  std::vector<cudaEvent_t> released;        // per slot: last reader enqueued so far has finished
+  std::vector<char> has_release;
+  std::vector<int64_t> level;               // per slot: logical level held (−1: none)
+  cudaStream_t copy = nullptr;
+  int64_t bytes = 0, levels = 0;
+};
+extern "C" int coflux_forcing_window_destroy(coflux_forcing_window* w) {
+  if (!w) return COFLUX_OK;
+  cudaSetDevice(w->device);
+  if (w->copy) { cudaStreamSynchronize(w->copy); cudaStreamDestroy(w->copy); }
+  for (char* p : w->field) if (p) cudaFree(p);
+  for (cudaEvent_t e : w->uploaded) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : w->released) if (e) cudaEventDestroy(e);
+  delete w;
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_create(coflux_forcing_window** out, coflux_ctx* c, int32_t n_fields, int64_t plane_elements, int32_t capacity) {
+  REQUIRE(out && c, "NULL argument");
+  *out = nullptr;
+  REQUIRE(n_fields >= 1 && n_fields <= 64 && plane_elements >= 1 && capacity >= 2, "forcing window: need 1..64 fields, a non-empty plane and capacity >= 2 levels");
+  CUDA_TRY(cudaSetDevice(c->device));
+  coflux_forcing_window* w = new (std::nothrow) coflux_forcing_window();
+  if (!w) return fail(COFLUX_ERR_ALLOC, "out of host memory");
+  w->device = c->device; w->n_fields = n_fields; w->capacity = capacity; w->plane_elements = plane_elements;
+  w->esize = (c->cfg.dtype == COFLUX_F64) ? 8 : 4;
+  w->field.assign(n_fields, nullptr);
+  w->uploaded.assign(capacity, nullptr); w->released.assign(capacity, nullptr);
+  w->has_release.assign(capacity, 0); w->level.assign(capacity, -1);
+  const size_t bytes = (size_t)capacity * (size_t)plane_elements * w->esize;
+  for (int f = 0; f < n_fields; ++f) {
+    if (cudaMalloc(&w->field[f], bytes) != cudaSuccess) { cudaGetLastError(); coflux_forcing_window_destroy(w); return fail(COFLUX_ERR_ALLOC, "forcing window: cudaMalloc of %zu bytes failed", bytes); }
+  }
+  bool ok = cudaStreamCreateWithFlags(&w->copy, cudaStreamNonBlocking) == cudaSuccess;
+  for (int s = 0; s < capacity && ok; ++s)
+    ok = cudaEventCreateWithFlags(&w->uploaded[s], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&w->released[s], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); coflux_forcing_window_destroy(w); return fail(COFLUX_ERR_CUDA, "forcing window: stream / event creation failed"); }
+  *out = w;
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_upload(coflux_forcing_window* w, int64_t level, const void* const* host_planes) {
+  REQUIRE(w && host_planes && level >= 0, "forcing window upload: bad argument");
+  CUDA_TRY(cudaSetDevice(w->device));
+  const int slot = (int)(level % w->capacity);
+  // the slot's previous level may still be read by work enqueued on a compute stream: wait for its last reader ON THE
+  // COPY STREAM (the host does not block)
+  if (w->has_release[slot]) CUDA_TRY(cudaStreamWaitEvent(w->copy, w->released[slot], 0));
+  const size_t plane = (size_t)w->plane_elements * w->esize;
+  for (int f = 0; f < w->n_fields; ++f) {
+    REQUIRE(host_planes[f], "forcing window upload: NULL host plane");
+    CUDA_TRY(cudaMemcpyAsync(w->field[f] + (size_t)slot * plane, host_planes[f], plane, cudaMemcpyHostToDevice, w->copy));
+  }
+  CUDA_TRY(cudaEventRecord(w->uploaded[slot], w->copy));
+  w->level[slot] = level;
+  w->has_release[slot] = 0;
+  w->bytes += (int64_t)(plane * w->n_fields); w->levels += 1;
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_field(coflux_forcing_window* w, int32_t f, void** ptr) {
+  REQUIRE(w && ptr && f >= 0 && f < w->n_fields, "forcing window field: bad argument");
+  *ptr = w->field[f];
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_wait(coflux_forcing_window* w, int64_t first, int64_t last, void* stream) {
+  REQUIRE(w && first >= 0 && last >= first && last - first < w->capacity, "forcing window wait: bad level range");
+  CUDA_TRY(cudaSetDevice(w->device));
+  for (int64_t l = first; l <= last; ++l) {
+    const int slot = (int)(l % w->capacity);
+    if (w->level[slot] != l) return fail(COFLUX_ERR_INVALID_ARGUMENT, "forcing window: level %lld is not in memory (slot %d holds level %lld)", (long long)l, slot, (long long)w->level[slot]);
+    CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), w->uploaded[slot], 0));
+  }
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_release(coflux_forcing_window* w, int64_t first, int64_t last, void* stream) {
+  REQUIRE(w && first >= 0 && last >= first && last - first < w->capacity, "forcing window release: bad level range");
+  CUDA_TRY(cudaSetDevice(w->device));
+  for (int64_t l = first; l <= last; ++l) {
+    const int slot = (int)(l % w->capacity);
+    if (w->level[slot] != l) continue;
+    CUDA_TRY(cudaEventRecord(w->released[slot], static_cast<cudaStream_t>(stream)));
+    w->has_release[slot] = 1;
+  }
+  return COFLUX_OK;
+}
+extern "C" int coflux_forcing_window_stats(coflux_forcing_window* w, int64_t* bytes, int64_t* levels) {
+  REQUIRE(w, "NULL window");
+  if (bytes) *bytes = w->bytes;
+  if (levels) *levels = w->levels;
+  return COFLUX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

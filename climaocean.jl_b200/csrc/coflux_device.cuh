@@ -141,16 +141,38 @@ template <typename FT> struct FastConsts {
   // reciprocals / products hoisted for the lean Float64 pass (coflux_solve_tile.cuh::iterate_lean)
   FT alpha_g, inv_g, bnu, inv_nu;   // bnu, inv_nu: constant-viscosity case
 };
+// CCSM3 sea-ice albedo (coflux_ccsm3_albedo; atmosphere.jl:31-44 `SeaIceAlbedo(hi, hs, Ts)`)
+template <typename FT> struct Ccsm3P {
+  FT ice_v, ice_n, snow_v, snow_n, hmax, dT, d_ice, d_snow_v, d_snow_n, hpatch, alb_o, fvis, Tmelt;
+};
 template <typename FT> struct DevParams {
   ThermoC<FT> th;
   FastConsts<FT> K;                // for the atmosphere–ocean parameters
   FT h, hbl, g;
   FT rho0, c0, rhof, Smin, wmf_alpha, T_offset;  // T_offset: 273.15 if ocean T in °C else 0
   FT sigma, alb_o, emis_o, emis_i, alb_i;
-  int sw_pen;
+  int sw_pen, ice_albedo_kind;
+  Ccsm3P<FT> ccsm3;
   FluxP<FT> ao, ai;
   IceOceanP<FT> io;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Sea-ice albedo seen by the radiation terms of rows a7 / f1: a prescribed plane or constant, or the CCSM3 form evaluated
+// from the live ice thickness, snow thickness and top temperature (include/coflux.h: coflux_ccsm3_albedo)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> __device__ __forceinline__ FT ccsm3_albedo(const Ccsm3P<FT>& c, FT hi, FT hs, FT TsK) {
+  const FT fh = M<FT>::min(M<FT>::atan(FT(4) * hi) / M<FT>::atan(FT(4) * c.hmax), FT(1));
+  const FT fT = M<FT>::min(M<FT>::max(FT(1) - (c.Tmelt - TsK) / c.dT, FT(0)), FT(1));
+  const FT aiv = c.ice_v * fh + c.alb_o * (FT(1) - fh) - c.d_ice * fT;
+  const FT ain = c.ice_n * fh + c.alb_o * (FT(1) - fh) - c.d_ice * fT;
+  const FT asv = c.snow_v - c.d_snow_v * fT;
+  const FT asn = c.snow_n - c.d_snow_n * fT;
+  const FT fs = hs / (hs + c.hpatch);
+  const FT av = (FT(1) - fs) * aiv + fs * asv;
+  const FT an = (FT(1) - fs) * ain + fs * asn;
+  return c.fvis * av + (FT(1) - c.fvis) * an;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Thermodynamics (A1, A2)

@@ -66,6 +66,19 @@ __device__ __forceinline__ bool is_active(const DArr& m, int i, int j) {
   return __ldg(reinterpret_cast<const uint8_t*>(m.p) + ((int64_t)i * m.si + (int64_t)j * m.sj)) != 0;
 }
 
+// Running time averages (Oceananigans WindowedTimeAverage, the schedule of omip_diagnostics.jl:152-158):
+//   result ← (result·T + field·Δt) / (T + Δt),  T = time already accumulated in the window
+template <typename FT> struct AvgArgs {
+  int on;
+  DArr JT, JS, Qc, Qv, JTao, JTio, JSio;
+  FT T, dt;
+};
+template <typename FT> __device__ __forceinline__ void avg_update(const DArr& d, int i, int j, FT x, FT T, FT dt) {
+  if (!d.p) return;
+  FT* p = reinterpret_cast<FT*>(d.p) + ((int64_t)i * d.si + (int64_t)j * d.sj);
+  *p = (*p * T + x * dt) / (T + dt);
+}
+
 template <typename FT> struct FluxArgs {
   int nxr, nyr, ring, Nx, Ny;
   long long cell0, ncell;   // linear cell range [cell0, ncell) of the ring-extended surface handled by this launch
@@ -85,6 +98,12 @@ template <typename FT> struct FluxArgs {
   DArr JT, JS, Qu, Qal, Qts, J0;
   // seam push (multi-GPU, ring == 0): last column of ρτx stored to the east neighbour
   char* seam_east;     // peer pointer, Ny elements (or nullptr)
+  // land freshwater (JRA55PrescribedLand: rivers + icebergs, atmosphere.jl:46) on its own source grid / time axis
+  DSeries sriv, sicb;
+  DArr lfi, lfj;
+  FT lnfrac;
+  DArr ihs;            // snow thickness on sea ice (CCSM3 albedo), optional
+  AvgArgs<FT> avg;     // running time averages of the flux fields (omip_diagnostics.jl:125-158), optional
   DevParams<FT> P;
 };
 
@@ -102,11 +121,38 @@ __device__ __forceinline__ FT interp_series(const DSeries& s, int i0, int j0, in
   return p2 * nfrac + p1 * (FT(1) - nfrac);
 }
 
+// bilinear stencil of one fractional index pair (A8)
+template <typename FT> struct Bilin { int i0, j0, i1, j1; FT w00, w01, w10, w11; };
+template <typename FT> __device__ __forceinline__ Bilin<FT> bilin(FT fi, FT fj) {
+  Bilin<FT> b;
+  b.i0 = (int)M<FT>::trunc(fi); b.j0 = (int)M<FT>::trunc(fj);
+  b.i1 = b.i0 + ((fi > FT(0)) - (fi < FT(0))); b.j1 = b.j0 + ((fj > FT(0)) - (fj < FT(0)));
+  const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
+  b.w00 = (FT(1) - xi) * (FT(1) - eta); b.w01 = (FT(1) - xi) * eta; b.w10 = xi * (FT(1) - eta); b.w11 = xi * eta;
+  return b;
+}
+// rivers + icebergs interpolated to ocean cell (i, j): the land part of the exchange freshwater flux (0 without land)
+template <typename FT> __device__ __forceinline__ FT land_freshwater(const FluxArgs<FT>& a, int i, int j) {
+  if (!a.lfi.p) return FT(0);
+  const Bilin<FT> b = bilin<FT>(ldgs<FT>(a.lfi, i, j), ldgs<FT>(a.lfj, i, j));
+  FT Mr = FT(0), Mi = FT(0);
+  if (a.sriv.p1) Mr = interp_series<FT>(a.sriv, b.i0, b.j0, b.i1, b.j1, b.w00, b.w01, b.w10, b.w11, a.lnfrac);
+  if (a.sicb.p1) Mi = interp_series<FT>(a.sicb, b.i0, b.j0, b.i1, b.j1, b.w00, b.w01, b.w10, b.w11, a.lnfrac);
+  return Mr + Mi;
+}
+// sea-ice albedo of cell (i, j): prescribed plane / constant, or CCSM3 from the live h_i, h_s, T_s (atmosphere.jl:31-44)
+template <typename FT> __device__ __forceinline__ FT sea_ice_albedo(const DevParams<FT>& P, const DArr& ialb, const DArr& ih, const DArr& ihs,
+                                                                    int i, int j, FT TsK) {
+  if (P.ice_albedo_kind == COFLUX_SEA_ICE_ALBEDO_CCSM3)
+    return ccsm3_albedo<FT>(P.ccsm3, ldg<FT>(ih, i, j), ihs.p ? ldg<FT>(ihs, i, j) : FT(0), TsK);
+  return ialb.p ? ldg<FT>(ialb, i, j) : P.alb_i;
+}
+
 // tracer / radiative part of the net ocean flux assembly for one interior cell (A9)
 template <typename FT>
 __device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool act, FT conc, FT So, FT TsK, FT Qs, FT Ql,
                                                  FT Mp, FT Qc, FT Qv, FT Mv, FT Qio, FT salt_io, FT& JT, FT& JS, FT& Qu,
-                                                 FT& Qal, FT& Qts, FT& J0) {
+                                                 FT& Qal, FT& Qts, FT& J0, FT* parts = nullptr /* JTao, JTio, JSio */) {
   const FT rho0inv = FT(1) / P.rho0, rhofinv = FT(1) / P.rhof;
   Qu = P.emis_o * P.sigma * TsK * TsK * TsK * TsK;
   Qal = -P.emis_o * Ql;
@@ -118,10 +164,21 @@ __device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool ac
   const FT JTao = SQ * rho0inv / P.c0;
   FT JSao = -So * SF;
   if (So < P.Smin && JSao > FT(0)) JSao = FT(0);
-  JT = (FT(1) - conc) * JTao + Qio * rho0inv / P.c0;
-  JS = (FT(1) - conc) * JSao + salt_io * conc;
+  const FT JTao_w = (FT(1) - conc) * JTao, JTio = Qio * rho0inv / P.c0, JSio = salt_io * conc;
+  JT = JTao_w + JTio;
+  JS = (FT(1) - conc) * JSao + JSio;
   J0 = (FT(1) - conc) * Qts * rho0inv / P.c0;
   if (!act) { JT = JS = J0 = FT(0); Qu = Qal = Qts = FT(0); }
+  if (parts) { parts[0] = act ? JTao_w : FT(0); parts[1] = act ? JTio : FT(0); parts[2] = act ? JSio : FT(0); }
+}
+
+// epilogue of the fused kernels: running averages of the tracer / turbulent fluxes of one interior cell
+template <typename FT>
+__device__ __forceinline__ void avg_epilogue(const AvgArgs<FT>& g, int i, int j, FT JT, FT JS, FT Qc, FT Qv, const FT* parts) {
+  avg_update<FT>(g.JT, i, j, JT, g.T, g.dt); avg_update<FT>(g.JS, i, j, JS, g.T, g.dt);
+  avg_update<FT>(g.Qc, i, j, Qc, g.T, g.dt); avg_update<FT>(g.Qv, i, j, Qv, g.T, g.dt);
+  avg_update<FT>(g.JTao, i, j, parts[0], g.T, g.dt); avg_update<FT>(g.JTio, i, j, parts[1], g.T, g.dt);
+  avg_update<FT>(g.JSio, i, j, parts[2], g.T, g.dt);
 }
 
 template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE>
@@ -149,6 +206,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
     Mp = FT(0);
     if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
     if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    if (a.lfi.p) Mp += land_freshwater<FT>(a, i, j);
     if (a.cs.p && a.sn.p) {
       const FT cs = ldg<FT>(a.cs, i, j), sn = ldg<FT>(a.sn, i, j);
       const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
@@ -175,7 +233,7 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
   if (SURF == 1) {
     in.h_ice = ldg<FT>(a.ih, i, j);
     in.S_ice = ldg<FT>(a.iS, i, j);
-    in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+    in.albedo = sea_ice_albedo<FT>(P, a.ialb, a.ih, a.ihs, i, j, in.Ts0);
     const FT conc = ldg<FT>(a.iconc, i, j);
     act = act && (conc > FT(0)) && (in.h_ice > FT(0));
   } else {
@@ -212,11 +270,12 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
       const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
       const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
       const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
-      FT JT, JS, Qu, Qal, Qts, J0;
+      FT JT, JS, Qu, Qal, Qts, J0, parts[3];
       assemble_tracers<FT>(P, is_active(a.mask, i, j), conc, in.So, Tsout + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio,
-                           JT, JS, Qu, Qal, Qts, J0);
+                           JT, JS, Qu, Qal, Qts, J0, parts);
       stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
       stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
+      if (a.avg.on) avg_epilogue<FT>(a.avg, i, j, JT, JS, Qc, Qv, parts);
     }
   }
 }
@@ -295,7 +354,7 @@ __global__ void __launch_bounds__(128) flux_refill_kernel(const __grid_constant_
       if (SURF == 1) {
         in.h_ice = ldg<FT>(a.ih, i, j);
         in.S_ice = ldg<FT>(a.iS, i, j);
-        in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+        in.albedo = sea_ice_albedo<FT>(P, a.ialb, a.ih, a.ihs, i, j, in.Ts0);
         const FT conc = ldg<FT>(a.iconc, i, j);
         act = act && (conc > FT(0)) && (in.h_ice > FT(0));
       } else {
@@ -377,7 +436,7 @@ __global__ void __launch_bounds__(128, COFLUX_ICE_MIN_BLOCKS) ice_tile_kernel(co
     in.So = FT(0);
     in.h_ice = ldg<FT>(a.ih, i, j);
     in.S_ice = ldg<FT>(a.iS, i, j);
-    in.albedo = a.ialb.p ? ldg<FT>(a.ialb, i, j) : P.alb_i;
+    in.albedo = sea_ice_albedo<FT>(P, a.ialb, a.ih, a.ihs, i, j, in.Ts0);
     const FT conc = ldg<FT>(a.iconc, i, j);
     const bool act = is_active(a.mask, i, j) && (conc > FT(0)) && (in.h_ice > FT(0));
     FT us = FT(0), ts = FT(0), qs = FT(0), Ts = in.Ts0;
@@ -516,6 +575,8 @@ template <typename FT> struct StressArgs {
   const char* seam_west;   // ρτx of the west neighbour's last column (Ny elements), or nullptr
   FT rho0;
   ClosureArgs<FT> closure;
+  DArr avg_tx, avg_ty;     // running time averages of τx, τy (optional)
+  FT avg_T, avg_dt;
 };
 template <typename FT>
 __device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, int j, FT& tx, FT& ty) {
@@ -549,6 +610,8 @@ template <typename FT> __global__ void __launch_bounds__(256) stress_kernel(cons
   stg<FT>(a.taux, i, j, tx);
   stg<FT>(a.tauy, i, j, ty);
   if (a.closure.on) closure_forcing<FT>(a.closure, i, j, tx, ty);
+  avg_update<FT>(a.avg_tx, i, j, tx, a.avg_T, a.avg_dt);
+  avg_update<FT>(a.avg_ty, i, j, ty, a.avg_T, a.avg_dt);
 }
 // stand-alone closure front end: τx, τy read back from the net fluxes
 template <typename FT> struct ClosureKernelArgs {
@@ -599,6 +662,8 @@ template <typename FT> struct IceOceanArgs {
   DArr ou, ov;          // ocean u, v at k = Nz-1
   DArr iu, iv, ih, ihm, iconc, iS;
   DArr Qf, Qio, Js, tx, ty;
+  DArr avg_JTf;         // running time average of the frazil temperature flux Q_f / (ρ₀ c₀) (optional)
+  FT avg_T, avg_dt;
   FT dt;
   DevParams<FT> P;
 };
@@ -708,9 +773,92 @@ template <typename FT> __global__ void __launch_bounds__(COFLUX_IO_BLOCK) ice_oc
   const FT hm = reinterpret_cast<const FT*>(a.ihm.p)[(int64_t)i * a.ihm.si + (int64_t)j * a.ihm.sj];
   const FT Js = (h - hm) / a.dt * (Si - SN);
   stg<FT>(a.Qf, i, j, dQ);
+  avg_update<FT>(a.avg_JTf, i, j, dQ / rho0 / c0, a.avg_T, a.avg_dt);
   stg<FT>(a.Qio, i, j, Qio);
   stg<FT>(a.Js, i, j, Js);
   stg<FT>(a.ihm, i, j, h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// land freshwater, stand-alone: exchange Mp += rivers + icebergs (the fused kernels do this in their phase A)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> __global__ void __launch_bounds__(256) land_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  const long long idx = a.cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.ncell) return;
+  const int jj = (int)(idx / a.nxr);
+  const int ii = (int)(idx - (long long)jj * a.nxr);
+  const int i = ii - a.ring, j = jj - a.ring;
+  FT* p = reinterpret_cast<FT*>(a.xMp.p) + ((int64_t)i * a.xMp.si + (int64_t)j * a.xMp.sj);
+  *p += land_freshwater<FT>(a, i, j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compute_net_sea_ice_fluxes!: heat into the ice from above and below; the atmosphere–ice stress at the
+// velocity points of the ice model.  Pure streaming: ≈ 12 words read, 2–4 written per cell.
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct NetIceArgs {
+  int Nx, Ny, wrap_x;
+  DArr Qs, Ql;                    // exchange state
+  DArr Ttop, conc, ih, ihs, ialb; // sea ice
+  DArr Qc, Qv, rtx, rty;          // atmosphere–sea-ice interface fluxes
+  DArr Qf, Qi;                    // sea-ice–ocean fluxes
+  DArr mask;
+  DArr top, bottom, top_u, top_v;
+  DevParams<FT> P;
+};
+template <typename FT> __global__ void __launch_bounds__(256) net_sea_ice_kernel(const __grid_constant__ NetIceArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.Nx * a.Ny) return;
+  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  const DevParams<FT>& P = a.P;
+  const bool act = is_active(a.mask, i, j);
+  const FT TsK = ldg<FT>(a.Ttop, i, j) + P.T_offset;
+  const FT conc = ldg<FT>(a.conc, i, j);
+  const FT alpha = sea_ice_albedo<FT>(P, a.ialb, a.ih, a.ihs, i, j, TsK);
+  const FT Qu = P.emis_i * P.sigma * TsK * TsK * TsK * TsK;
+  const FT Qd = -(FT(1) - alpha) * ldg<FT>(a.Qs, i, j) - P.emis_i * ldg<FT>(a.Ql, i, j);
+  const FT SQt = (conc > FT(0)) ? (Qd + Qu + ldg<FT>(a.Qc, i, j) + ldg<FT>(a.Qv, i, j)) : FT(0);
+  const FT SQb = (a.Qf.p ? ldg<FT>(a.Qf, i, j) : FT(0)) + (a.Qi.p ? ldg<FT>(a.Qi, i, j) : FT(0));
+  stg<FT>(a.top, i, j, act ? SQt : FT(0));
+  stg<FT>(a.bottom, i, j, act ? SQb : FT(0));
+  if (a.top_u.p) {
+    const int iw = (a.wrap_x && i == 0) ? a.Nx - 1 : i - 1;
+    const FT v = (ldg<FT>(a.rtx, iw, j) + ldg<FT>(a.rtx, i, j)) * FT(0.5);
+    stg<FT>(a.top_u, i, j, (act && is_active(a.mask, iw, j)) ? v : FT(0));
+  }
+  if (a.top_v.p) {
+    const FT v = (ldg<FT>(a.rty, i, j - 1) + ldg<FT>(a.rty, i, j)) * FT(0.5);
+    stg<FT>(a.top_v, i, j, (act && is_active(a.mask, i, j - 1)) ? v : FT(0));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// time-averaged flux diagnostics, stand-alone (reads the flux fields back; the fused path accumulates in its epilogues)
+// ---------------------------------------------------------------------------------------------
+template <typename FT> struct FluxAvgArgs {
+  int Nx, Ny;
+  DArr tx, ty, JT, JS, Qc, Qv, conc, Qio, salt_io, Qf;
+  DArr a_tx, a_ty, a_JT, a_JS, a_Qc, a_Qv, a_JTao, a_JTio, a_JSio, a_JTf;
+  FT T, dt, rho0, c0;
+};
+template <typename FT> __global__ void __launch_bounds__(256) flux_average_kernel(const __grid_constant__ FluxAvgArgs<FT> a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.Nx * a.Ny) return;
+  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  if (a.tx.p) avg_update<FT>(a.a_tx, i, j, ldg<FT>(a.tx, i, j), a.T, a.dt);
+  if (a.ty.p) avg_update<FT>(a.a_ty, i, j, ldg<FT>(a.ty, i, j), a.T, a.dt);
+  const FT JT = a.JT.p ? ldg<FT>(a.JT, i, j) : FT(0);
+  if (a.JT.p) avg_update<FT>(a.a_JT, i, j, JT, a.T, a.dt);
+  if (a.JS.p) avg_update<FT>(a.a_JS, i, j, ldg<FT>(a.JS, i, j), a.T, a.dt);
+  if (a.Qc.p) avg_update<FT>(a.a_Qc, i, j, ldg<FT>(a.Qc, i, j), a.T, a.dt);
+  if (a.Qv.p) avg_update<FT>(a.a_Qv, i, j, ldg<FT>(a.Qv, i, j), a.T, a.dt);
+  const FT rho0inv = FT(1) / a.rho0;
+  const FT JTio = a.Qio.p ? ldg<FT>(a.Qio, i, j) * rho0inv / a.c0 : FT(0);
+  avg_update<FT>(a.a_JTio, i, j, JTio, a.T, a.dt);
+  if (a.JT.p) avg_update<FT>(a.a_JTao, i, j, JT - JTio, a.T, a.dt);
+  const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
+  avg_update<FT>(a.a_JSio, i, j, a.salt_io.p ? ldg<FT>(a.salt_io, i, j) * conc : FT(0), a.T, a.dt);
+  if (a.Qf.p) avg_update<FT>(a.a_JTf, i, j, ldg<FT>(a.Qf, i, j) / a.rho0 / a.c0, a.T, a.dt);
 }
 
 // ---------------------------------------------------------------------------------------------

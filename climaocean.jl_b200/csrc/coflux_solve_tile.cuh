@@ -700,6 +700,7 @@ __global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>
       FT Mp = FT(0);
       if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
       if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+          if (a.lfi.p) Mp += land_freshwater<FT>(a, i, j);
       if (a.cs.p && a.sn.p) {
         const FT cs = ldgs<FT>(a.cs, i, j), sn = ldgs<FT>(a.sn, i, j);
         const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
@@ -974,10 +975,11 @@ __global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>
         const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
         const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
         const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
-        FT JT, JS, Qu, Qal, Qts, J0;
-        assemble_tracers<FT>(P, act, conc, So, Tunits + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio, JT, JS, Qu, Qal, Qts, J0);
+        FT JT, JS, Qu, Qal, Qts, J0, parts[3];
+        assemble_tracers<FT>(P, act, conc, So, Tunits + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio, JT, JS, Qu, Qal, Qts, J0, parts);
         stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
         stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
+            if (a.avg.on) avg_epilogue<FT>(a.avg, i, j, JT, JS, Qc, Qv, parts);
       }
     }
   }

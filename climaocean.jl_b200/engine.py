@@ -89,6 +89,26 @@ class Engine:
         _abi.check(self.lib.coflux_update_state(self._ctx, C.byref(inputs), C.byref(outputs), float(time),
                                                 _stream_handle(stream)), self.lib)
 
+    def interpolate_land(self, land, time, exchange, stream=None):
+        """Exchange Mp += rivers + icebergs (JRA55PrescribedLand, atmosphere.jl:46)."""
+        _abi.check(self.lib.coflux_interpolate_land(self._ctx, C.byref(land), float(time), C.byref(exchange), _stream_handle(stream)), self.lib)
+
+    def compute_net_sea_ice_fluxes(self, exchange, ocean, ice, ai, io, out, stream=None):
+        _abi.check(self.lib.coflux_assemble_net_sea_ice_fluxes(
+            self._ctx, C.byref(exchange), C.byref(ocean) if ocean is not None else None, C.byref(ice), C.byref(ai),
+            C.byref(io) if io is not None else None, C.byref(out), _stream_handle(stream)), self.lib)
+
+    # --- time-averaged flux diagnostics (omip_diagnostics.jl:125-158) ---
+    def attach_flux_averages(self, averages):
+        """Every following update_state / compute_sea_ice_ocean_fluxes updates the running averages; None detaches."""
+        self._avg_keep = averages
+        _abi.check(self.lib.coflux_attach_flux_averages(self._ctx, C.byref(averages) if averages is not None else None), self.lib)
+
+    def accumulate_flux_averages(self, net, ao, ice, io, averages, stream=None):
+        _abi.check(self.lib.coflux_accumulate_flux_averages(
+            self._ctx, C.byref(net), C.byref(ao) if ao is not None else None, C.byref(ice) if ice is not None else None,
+            C.byref(io) if io is not None else None, C.byref(averages), _stream_handle(stream)), self.lib)
+
     # --- closure surface-forcing front ends (KPP/kpp_surface_forcing.jl, NEMOTKE/nemo_tke_surface_forcing.jl) ---
     def closure_surface_forcing(self, net, forcing, stream=None):
         _abi.check(self.lib.coflux_closure_surface_forcing(self._ctx, C.byref(net), C.byref(forcing), _stream_handle(stream)), self.lib)

@@ -324,6 +324,26 @@ class PrescribedAtmosphere:
         self.boundary_layer_height = boundary_layer_height
 
 
+class PrescribedLand:
+    """JRA55PrescribedLand (atmosphere.jl:46): river runoff + iceberg calving series living in `data.land`; their sum is
+    added to the exchange freshwater flux (enters J^S like rain and snow)."""
+
+    def __init__(self, data):
+        if data.land is None:
+            raise ValueError("PrescribedLand needs land freshwater series (SurfaceFluxData.land)")
+        self.data = data
+        self.times = data.land_times
+
+
+class SeaIceAlbedo:
+    """SeaIceAlbedo(hi, hs, Ts) — CCSM3 thickness / snow / temperature dependent albedo evaluated from the LIVE sea-ice
+    fields (atmosphere.jl:31-44).  Keyword arguments override the CCSM3 constants (coflux_ccsm3_albedo)."""
+
+    def __init__(self, ice_thickness=None, snow_thickness=None, surface_temperature=None, **params):
+        self.ice_thickness, self.snow_thickness, self.surface_temperature = ice_thickness, snow_thickness, surface_temperature
+        self.params = params
+
+
 class SurfaceRadiationProperties:
     def __init__(self, albedo, emissivity):
         self.albedo, self.emissivity = albedo, emissivity
@@ -375,8 +395,16 @@ class ComponentInterfaces:
         cfg.radiation.stefan_boltzmann_constant = radiation.stefan_boltzmann_constant
         cfg.radiation.ocean_albedo = radiation.ocean_surface.albedo
         cfg.radiation.ocean_emissivity = radiation.ocean_surface.emissivity
-        cfg.radiation.sea_ice_albedo = radiation.sea_ice_surface.albedo
+        if isinstance(radiation.sea_ice_surface.albedo, SeaIceAlbedo):       # atmosphere.jl:39-44
+            cfg.radiation.sea_ice_albedo_kind = _abi.SEA_ICE_ALBEDO_CCSM3
+            for k, v in radiation.sea_ice_surface.albedo.params.items():
+                setattr(cfg.radiation.ccsm3, k, float(v))
+        else:
+            cfg.radiation.sea_ice_albedo = radiation.sea_ice_surface.albedo
         cfg.radiation.sea_ice_emissivity = radiation.sea_ice_surface.emissivity
+        if land is not None and not isinstance(land, PrescribedLand):
+            raise NotImplementedError("land must be a PrescribedLand (river runoff + iceberg calving series) or None")
+        self.land = land
         cfg.ocean.minimum_salinity = float(ocean_minimum_salinity)
         cfg.atmosphere.surface_layer_height = atmosphere.surface_layer_height
         cfg.atmosphere.boundary_layer_height = atmosphere.boundary_layer_height
@@ -390,6 +418,8 @@ class ComponentInterfaces:
             "latent_heat", "sensible_heat", "water_vapor", "x_momentum", "y_momentum")}),
             temperature=data.ao["interface_temperature"])
         if self.has_sea_ice:
+            self.net_fluxes.sea_ice = _Named(top=_Named(heat=data.net_ice["top_heat"], u=data.net_ice["top_u"], v=data.net_ice["top_v"]),
+                                             bottom=_Named(heat=data.net_ice["bottom_heat"]))
             self.sea_ice_ocean_interface = _Named(fluxes=_Named(**data.io))
             self.atmosphere_sea_ice_interface = _Named(fluxes=_Named(**{k: data.ai[k] for k in (
                 "latent_heat", "sensible_heat", "water_vapor", "x_momentum", "y_momentum")}),
@@ -452,17 +482,20 @@ def update_state(model):
     itf = model.interfaces
     d, eng, t = itf.data, itf.engine, model.clock.time
     if not itf.has_sea_ice:
-        inp, out = d.update_bundles()
+        inp, out = d.update_bundles(with_land=itf.land is not None)
         eng.update_state(inp, out, t, model.stream)
         return
     series, xch, ocean = d.atmos_series(), d.exchange_state(), d.ocean_surface()
     ice, io = d.sea_ice_state(), d.ice_ocean_fluxes()
     ao, ai, net = d.interface_fluxes("ao"), d.interface_fluxes("ai"), d.net_ocean_fluxes()
     eng.interpolate_atmosphere_state(series, t, xch, model.stream)
+    if itf.land is not None:
+        eng.interpolate_land(d.land_series(), t, xch, model.stream)
     eng.compute_atmosphere_ocean_fluxes(xch, ocean, ao, model.stream)
     eng.compute_atmosphere_sea_ice_fluxes(xch, ocean, ice, ai, model.stream)
     eng.compute_sea_ice_ocean_fluxes(d.ocean_columns(), ice, model.last_dt, io, model.stream)
     eng.compute_net_ocean_fluxes(xch, ocean, ao, ice, io, net, model.stream)
+    eng.compute_net_sea_ice_fluxes(xch, ocean, ice, ai, io, d.net_sea_ice_fluxes(), model.stream)
 
 
 def time_step(model, dt):

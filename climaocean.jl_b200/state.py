@@ -17,7 +17,10 @@ IFACE_NAMES = ("latent_heat", "sensible_heat", "water_vapor", "x_momentum", "y_m
 NET_NAMES = ("u", "v", "T", "S", "upwelling_longwave", "downwelling_longwave", "downwelling_shortwave",
              "penetrating_shortwave")
 IO_NAMES = ("frazil_heat", "interface_heat", "salt", "x_momentum", "y_momentum")
-ICE_NAMES = ("thickness", "previous_thickness", "concentration", "salinity", "u", "v", "top_temperature")
+ICE_NAMES = ("thickness", "previous_thickness", "concentration", "salinity", "u", "v", "top_temperature", "snow_thickness")
+NET_ICE_NAMES = ("top_heat", "bottom_heat", "top_u", "top_v")
+AVG_NAMES = ("tau_x", "tau_y", "JT", "JS", "Qc", "Qv", "JT_atmosphere_ocean", "JT_ice_ocean", "JS_ice_ocean", "JT_frazil")
+LAND_NAMES = ("rivers", "icebergs")
 
 
 class SurfaceFluxData:
@@ -40,12 +43,20 @@ class SurfaceFluxData:
         self.io = {}
         self.net = {}
         self.iterations = None
+        self.land = None         # dict name -> FieldTimeSeries (rivers, icebergs) or None
+        self.land_times = None
+        self.land_time_indexing = _abi.TIME_LINEAR
+        self.lfi = self.lfj = None
+        self.rotation = None     # (cos θ, sin θ) Fields of a curvilinear grid, or None
+        self.net_ice = {}
+        self.averages = {}
+        self.ring_start = self.ring_capacity = 0      # device ring buffer of the atmosphere series (forcing.DeviceForcingWindow)
         self._keep = []
 
     # ------------------------------------------------------------------------------------------
     @classmethod
     def synthetic(cls, grid, device=None, with_ice=False, land_fraction=0.0, frazil=False, Nt=8, atmos_size=(640, 320),
-                  atmos_halo=3, ring=1):
+                  atmos_halo=3, ring=1, with_land=False, land_size=(360, 180), land_Nt=4):
         """Inputs per SURVEY §8d on the host; call .to(device) for the CUDA copy."""
         self = cls(grid, None)
         dt = grid.dtype
@@ -66,6 +77,13 @@ class SurfaceFluxData:
         if with_ice:
             ice = synth.sea_ice_state(grid, dt)
             self.ice = {n: Field(ice[n], (grid.halo[0], grid.halo[1], 0), "ice_" + n) for n in ICE_NAMES}
+        if with_land:
+            lh = 2
+            lser, ltimes = synth.land_series(land_size[0], land_size[1], land_Nt, lh, dt)
+            self.land_times = ltimes
+            self.land = {n: FieldTimeSeries(lser[n], (lh, lh, 0), ltimes, n) for n in LAND_NAMES}
+            LFI, LFJ = fractional_indices(grid, land_size[0], land_size[1], ring=ring)
+            self.lfi, self.lfj = Field(LFI, (ring, ring, 0), "land_fi"), Field(LFJ, (ring, ring, 0), "land_fj")
         self.allocate_outputs()
         return self
 
@@ -81,6 +99,14 @@ class SurfaceFluxData:
         if self.ice is not None:
             self.ai = {n: mk("ai_" + n) for n in IFACE_NAMES}
             self.io = {n: mk("io_" + n) for n in IO_NAMES}
+            self.net_ice = {n: mk("net_ice_" + n) for n in NET_ICE_NAMES}
+
+    def allocate_averages(self):
+        """Zeroed running-average Fields (omip_diagnostics.jl:125-158), one per averaged flux."""
+        g = self.grid
+        self.averages = {n: Field.zeros((g.Nx, g.Ny, 1), (g.halo[0], g.halo[1], 0), self.dtype, self.device, "avg_" + n)
+                         for n in AVG_NAMES}
+        return self.averages
 
     def to(self, device):
         o = SurfaceFluxData(self.grid, device)
@@ -92,6 +118,12 @@ class SurfaceFluxData:
         o.area = self.area.to(device) if self.area is not None else None
         o.mask = self.mask.to(device) if self.mask is not None else None
         o.ice = {n: f.to(device) for n, f in self.ice.items()} if self.ice is not None else None
+        if self.land is not None:
+            o.land = {n: f.to(device) for n, f in self.land.items()}
+            o.land_times, o.land_time_indexing = self.land_times, self.land_time_indexing
+            o.lfi, o.lfj = self.lfi.to(device), self.lfj.to(device)
+        if self.rotation is not None:
+            o.rotation = tuple(f.to(device) for f in self.rotation)
         o.allocate_outputs()
         if getattr(self, "eos", None):
             o.eos = {k: f.to(device) for k, f in self.eos.items()}
@@ -145,7 +177,26 @@ class SurfaceFluxData:
         s.time_indexing = self.time_indexing
         s.cycle_period = 0.0
         s.fi, s.fj = arr(self.fi), arr(self.fj)
-        s.cos_theta, s.sin_theta = arr(None), arr(None)
+        if self.rotation is not None:
+            s.cos_theta, s.sin_theta = arr(self.rotation[0]), arr(self.rotation[1])
+        else:
+            s.cos_theta, s.sin_theta = arr(None), arr(None)
+        s.ring_start, s.ring_capacity = int(self.ring_start), int(self.ring_capacity)
+        return s
+
+    def land_series(self):
+        """coflux_land_series (JRA55PrescribedLand: friver + licalvf, atmosphere.jl:46), or None without land."""
+        if self.land is None:
+            return None
+        s = _abi.LandSeries()
+        s.rivers, s.icebergs = arr(self.land.get("rivers")), arr(self.land.get("icebergs"))
+        self._land_times_c = (C.c_double * len(self.land_times))(*self.land_times)
+        s.times = C.cast(self._land_times_c, C.POINTER(C.c_double))
+        s.Nt = len(self.land_times)
+        s.time_indexing = self.land_time_indexing
+        s.cycle_period = 0.0
+        s.fi, s.fj = arr(self.lfi), arr(self.lfj)
+        s.ring_start = s.ring_capacity = 0
         return s
 
     def exchange_state(self):
@@ -172,8 +223,23 @@ class SurfaceFluxData:
     def sea_ice_state(self):
         s = _abi.SeaIceState()
         for n in ICE_NAMES:
-            setattr(s, n, arr(self.ice[n]))
-        s.snow_thickness, s.albedo = arr(None), arr(None)
+            setattr(s, n, arr(self.ice.get(n)))
+        s.albedo = arr(self.ice.get("albedo"))
+        return s
+
+    def net_sea_ice_fluxes(self, with_stress=True):
+        s = _abi.NetSeaIceFluxes()
+        s.top_heat, s.bottom_heat = arr(self.net_ice["top_heat"]), arr(self.net_ice["bottom_heat"])
+        s.top_u = arr(self.net_ice["top_u"]) if with_stress else arr(None)
+        s.top_v = arr(self.net_ice["top_v"]) if with_stress else arr(None)
+        return s
+
+    def flux_averages(self, previous_interval, dt, names=AVG_NAMES):
+        """coflux_flux_averages over self.averages (allocate_averages() first)."""
+        s = _abi.FluxAverages()
+        for n in AVG_NAMES:
+            setattr(s, n, arr(self.averages[n]) if n in names else arr(None))
+        s.previous_interval, s.dt = float(previous_interval), float(dt)
         return s
 
     def ocean_columns(self):
@@ -242,12 +308,16 @@ class SurfaceFluxData:
         self._keep_norm = (s, additional)
         return s
 
-    def update_bundles(self, with_ice_terms=False):
+    def update_bundles(self, with_ice_terms=False, with_land=True):
         """(UpdateInputs, UpdateOutputs) for coflux_update_state; keeps the sub-structs alive."""
         a, o = self.atmos_series(), self.ocean_surface()
         x, f, n = self.exchange_state(), self.interface_fluxes("ao"), self.net_ocean_fluxes()
-        inp = _abi.UpdateInputs(C.pointer(a), C.pointer(o), None, None)
+        inp = _abi.UpdateInputs(C.pointer(a), C.pointer(o), None, None, None)
         keep = [a, o, x, f, n]
+        land = self.land_series() if with_land else None
+        if land is not None:
+            inp.land = C.pointer(land)
+            keep.append(land)
         if with_ice_terms and self.ice is not None:
             ice, io = self.sea_ice_state(), self.ice_ocean_fluxes()
             inp.sea_ice, inp.ice_ocean = C.pointer(ice), C.pointer(io)
@@ -259,7 +329,8 @@ class SurfaceFluxData:
     def outputs(self):
         """name -> numpy interior (Ny, Nx) of every output field (copied to host)."""
         res = {}
-        for grp, d in (("exchange", self.exchange), ("ao", self.ao), ("ai", self.ai), ("io", self.io), ("net", self.net)):
+        for grp, d in (("exchange", self.exchange), ("ao", self.ao), ("ai", self.ai), ("io", self.io), ("net", self.net),
+                       ("net_ice", self.net_ice), ("avg", self.averages)):
             for n, f in d.items():
                 a = f.numpy()
                 Hx, Hy, _ = f.halo

@@ -52,6 +52,9 @@ def pattern(field_id, lo, hi, ig, jg, Nxg, Nyg, level=0, random_weight=0.5):
 F_OCEAN_U, F_OCEAN_V, F_OCEAN_T, F_OCEAN_S = 1, 2, 3, 4
 F_ATM = {"u": 10, "v": 11, "T": 12, "q": 13, "p": 14, "Qs": 15, "Ql": 16, "rain": 17, "snow": 18}
 F_ICE_CONC, F_ICE_H, F_ICE_S, F_ICE_U, F_ICE_V, F_ICE_T, F_ICE_HPREV, F_MASK = 30, 31, 32, 33, 34, 35, 36, 40
+F_ICE_SNOW = 37
+F_LAND = {"rivers": 20, "icebergs": 21}
+LAND_RANGES = {"rivers": (-3e-4, 1.5e-4), "icebergs": (-6e-4, 1e-4)}    # clipped at 0: runoff / calving are non-zero in patches only
 
 ATM_RANGES = {"u": (-25.0, 25.0), "v": (-25.0, 25.0), "T": (250.0, 305.0), "q": (1e-4, 2e-2), "p": (9.6e4, 1.04e5),
               "Qs": (0.0, 1000.0), "Ql": (100.0, 450.0), "rain": (0.0, 3e-4), "snow": (0.0, 3e-4)}
@@ -102,6 +105,22 @@ def atmosphere_series(Nxa=640, Nya=320, Nt=8, halo=3, dtype=np.float64, dt_hours
     return out, times
 
 
+def land_series(Nxl=360, Nyl=180, Nt=4, halo=2, dtype=np.float64, dt_hours=24.0):
+    """JRA55-do-like land freshwater forcing (friver, licalvf: jra55_data_staging.jl:8) on its own regular source grid and
+    (daily) time axis.  Parents (Nt, 1, Nyl+2H, Nxl+2H), kg m⁻² s⁻¹, zero over most of the globe."""
+    ig = np.arange(-halo, Nxl + halo)
+    jg = np.arange(-halo, Nyl + halo)
+    times = np.arange(Nt, dtype=np.float64) * dt_hours * 3600.0
+    out = {}
+    for name, fid in F_LAND.items():
+        lo, hi = LAND_RANGES[name]
+        a = np.empty((Nt, 1, jg.size, ig.size), dtype=np.float64)
+        for n in range(Nt):
+            a[n, 0] = np.maximum(pattern(fid, lo, hi, ig, jg, Nxl, Nyl, level=n), 0.0)
+        out[name] = a.astype(dtype)
+    return out, times
+
+
 def sea_ice_state(grid, dtype=None):
     """ℵ ∈ {0, (0,1), 1}, h ∈ [0,3] m (0 where ℵ = 0), S_i, ice velocities, top temperature (°C)."""
     dtype = dtype or grid.dtype
@@ -117,7 +136,8 @@ def sea_ice_state(grid, dtype=None):
     out = {"concentration": conc, "thickness": h, "previous_thickness": hprev,
            "salinity": pattern(F_ICE_S, 2.0, 8.0, ig, jg, Nxg, grid.Ny),
            "u": pattern(F_ICE_U, -0.3, 0.3, ig, jg, Nxg, grid.Ny), "v": pattern(F_ICE_V, -0.3, 0.3, ig, jg, Nxg, grid.Ny),
-           "top_temperature": pattern(F_ICE_T, -30.0, -0.5, ig, jg, Nxg, grid.Ny)}
+           "top_temperature": pattern(F_ICE_T, -30.0, -0.5, ig, jg, Nxg, grid.Ny),
+           "snow_thickness": np.where(conc > 0.0, np.maximum(pattern(F_ICE_SNOW, -0.2, 0.5, ig, jg, Nxg, grid.Ny), 0.0), 0.0)}
     return {k: v[None].astype(dtype) for k, v in out.items()}
 
 

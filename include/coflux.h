@@ -22,6 +22,13 @@
  *   coflux_update_state_host          <- same, HOST buffers (end-to-end measurement entry)
  *   coflux_create / coflux_destroy    <- ComponentInterfaces(...) construction (row a10;
  *                                        omip_simulation.jl:128-158)
+ *   coflux_interpolate_land           <- the land / auxiliary-freshwater part of interpolate_atmosphere_state!
+ *                                        (JRA55PrescribedLand: friver + licalvf, atmosphere.jl:46, jra55_data_staging.jl:8)
+ *   coflux_assemble_net_sea_ice_fluxes <- compute_net_sea_ice_fluxes!        
+ *   coflux_forcing_window_*           <- FieldTimeSeries InMemory window with prefetch (time_indices_in_memory,
+ *                                        prefetch = true: atmosphere.jl:22-27; §8f row 2)
+ *   coflux_attach_flux_averages       <- AveragedTimeInterval output of the flux fields (omip_diagnostics.jl:77-89,
+ *                                        125-158; §8f row 4)
  *
  * Conventions
  *   - every function returns 0 (COFLUX_OK) or a negative coflux_status; nothing throws or aborts;
@@ -47,7 +54,7 @@
 extern "C" {
 #endif
 
-#define COFLUX_ABI_VERSION 1
+#define COFLUX_ABI_VERSION 2   /* 2: land freshwater series, forcing ring, CCSM3 sea-ice albedo, net sea-ice fluxes, flux averages */
 
 typedef enum {
   COFLUX_OK = 0,
@@ -180,13 +187,37 @@ typedef struct coflux_ocean_properties {
   double  constituent_mass_fraction[4];
 } coflux_ocean_properties;
 
+typedef enum { COFLUX_SEA_ICE_ALBEDO_PRESCRIBED = 0,  /* coflux_sea_ice_state.albedo plane, else the constant sea_ice_albedo */
+               COFLUX_SEA_ICE_ALBEDO_CCSM3 = 1        /* SeaIceAlbedo(h_i, h_s, T_s) from the LIVE sea-ice fields (atmosphere.jl:31-44) */
+} coflux_sea_ice_albedo_kind;
+/* CCSM3 sea-ice albedo (Briegleb et al. 2004, the "ccsm3" shortwave option of CICE): thickness, snow-depth and surface
+ * temperature dependent, two spectral bands combined with a fixed visible fraction.
+ *   f_h = min(atan(4 h_i) / atan(4 h_max), 1)             thin ice fades into the ocean albedo
+ *   f_T = clamp(1 − (T_melt − T_s)/ΔT_melt, 0, 1)          0 below T_melt − ΔT_melt, 1 at the melting point
+ *   α_ice,b  = α_ice,b⁰ f_h + α_ocean (1 − f_h) − Δα_ice f_T          (b = visible, near infrared)
+ *   α_snow,b = α_snow,b⁰ − Δα_snow,b f_T
+ *   f_s = h_s / (h_s + h_patch);   α_b = (1 − f_s) α_ice,b + f_s α_snow,b;   α = f_vis α_vis + (1 − f_vis) α_nir            */
+typedef struct coflux_ccsm3_albedo {
+  double ice_visible, ice_near_infrared;            /* 0.78, 0.36                                            */
+  double snow_visible, snow_near_infrared;          /* 0.98, 0.70                                            */
+  double thickness_scale;                           /* h_max = 0.3 m                                         */
+  double melt_temperature_range;                    /* ΔT_melt = 1.5 K                                       */
+  double ice_melt_change;                           /* Δα_ice = 0.075                                        */
+  double snow_visible_melt_change, snow_near_infrared_melt_change;   /* 0.10, 0.15                          */
+  double snow_patchiness;                           /* h_patch = 0.02 m                                      */
+  double ocean_albedo;                              /* 0.06                                                  */
+  double visible_fraction;                          /* f_vis = 0.52                                          */
+  double melting_temperature;                       /* T_melt = 273.15 K                                     */
+} coflux_ccsm3_albedo;
+
 typedef struct coflux_radiation_properties {  /* SurfaceRadiationProperties (atmosphere.jl:42-46)     */
   double stefan_boltzmann_constant;
   double ocean_albedo, ocean_emissivity;
   double sea_ice_emissivity;
-  double sea_ice_albedo;         /* used when coflux_sea_ice_state.albedo is absent                  */
+  double sea_ice_albedo;         /* PRESCRIBED kind: used when coflux_sea_ice_state.albedo is absent  */
   int32_t shortwave_penetrates;  /* 1: transmitted SW goes to the penetrating-radiation surface flux */
-  int32_t reserved;
+  int32_t sea_ice_albedo_kind;   /* coflux_sea_ice_albedo_kind                                       */
+  coflux_ccsm3_albedo ccsm3;
 } coflux_radiation_properties;
 
 typedef enum { COFLUX_ICE_OCEAN_ICE_BATH = 0,        /* bulk: ρ₀c₀ u_m★ (T − T_m) ℵ                   */
@@ -260,9 +291,26 @@ typedef struct coflux_atmos_series {
   double  cycle_period;              /* CYCLICAL: period; <=0 → times[Nt-1]-times[0]+Δt              */
   /* fractional zero-based source indices of every ocean cell of the ring-extended surface:        */
   coflux_array fi, fj;               /* (Nx+2ring.., Ny+2ring..) dtype; see coflux_grid_desc.ring    */
-  /* optional rotation of (u,v) into the grid frame (curvilinear grids): u' = c·u − s·v ...          */
+  /* optional rotation of (u,v) into the grid frame (curvilinear grids): u' = c·u + s·v, v' = −s·u + c·v */
   coflux_array cos_theta, sin_theta;
+  /* device ring buffer (coflux_forcing_window): logical level n of `times` is stored at time slot
+   * (ring_start + n) mod ring_capacity of every series array.  ring_capacity == 0: plain layout (slot n).    */
+  int32_t ring_start, ring_capacity;
 } coflux_atmos_series;
+
+/* PrescribedLand — JRA55PrescribedLand (atmosphere.jl:46): river runoff `friver` and iceberg calving `licalvf`
+ * (jra55_data_staging.jl:8), freshwater mass fluxes [kg m⁻² s⁻¹] on their OWN source grid and time axis.  They are
+ * interpolated like the atmosphere (bilinear × linear in time) and ADDED to the exchange freshwater flux Mp, so that they
+ * enter the net salinity flux like rain and snow.                                                              */
+typedef struct coflux_land_series {
+  coflux_array rivers, icebergs;     /* friver, licalvf; either may be absent                                */
+  const double* times;               /* host, length Nt                                                      */
+  int32_t Nt;
+  int32_t time_indexing;             /* coflux_time_indexing                                                 */
+  double  cycle_period;
+  coflux_array fi, fj;               /* fractional source indices of every ocean cell (ring-extended surface) */
+  int32_t ring_start, ring_capacity; /* as in coflux_atmos_series                                            */
+} coflux_land_series;
 
 /* The 2-D "exchange" atmosphere state on the ocean grid (outputs of a3, inputs of a4/a9).         */
 typedef struct coflux_exchange_state {
@@ -292,7 +340,7 @@ typedef struct coflux_sea_ice_state {
   coflux_array u, v;                            /* ice velocities at (F,C) / (C,F)                   */
   coflux_array top_temperature;                 /* T_top (in/out of the skin-temperature solve)      */
   coflux_array snow_thickness;                  /* optional                                          */
-  coflux_array albedo;                          /* optional 2-D albedo; else radiation default       */
+  coflux_array albedo;                          /* optional 2-D albedo (PRESCRIBED kind); else radiation default */
 } coflux_sea_ice_state;
 
 /* Ocean columns for the frazil sweep: T is READ AND CONDITIONALLY WRITTEN.                         */
@@ -315,11 +363,21 @@ typedef struct coflux_net_ocean_fluxes {
   coflux_array penetrating_shortwave;
 } coflux_net_ocean_fluxes;
 
+/* interfaces.net_fluxes.sea_ice.{top, bottom} — what compute_net_sea_ice_fluxes! hands to the sea-ice model
+ * (SURVEY §3.2): the heat flux into the ice from above (radiation + turbulent, where ice is present) and from below
+ * (frazil + interface heat), W m⁻², positive upward; optionally the atmosphere–ice stress moved to the velocity
+ * points of the ice model (N m⁻²).                                                                              */
+typedef struct coflux_net_sea_ice_fluxes {
+  coflux_array top_heat, bottom_heat;
+  coflux_array top_u, top_v;                     /* optional: ρτx at (Face,Center), ρτy at (Center,Face)          */
+} coflux_net_sea_ice_fluxes;
+
 typedef struct coflux_update_inputs {
   const coflux_atmos_series*  atmosphere;
   const coflux_ocean_surface* ocean;
   const coflux_sea_ice_state* sea_ice;           /* NULL: ocean-only model                           */
   const coflux_ice_ocean_fluxes* ice_ocean;      /* NULL: no ice–ocean contribution in the assembly  */
+  const coflux_land_series*   land;              /* NULL: no land freshwater                         */
 } coflux_update_inputs;
 
 typedef struct coflux_update_outputs {
@@ -350,6 +408,10 @@ int coflux_time_indices(const double* times, int32_t Nt, int32_t time_indexing, 
 int coflux_interpolate_atmosphere(coflux_ctx*, const coflux_atmos_series* in, double time,
                                   coflux_exchange_state* out, void* cu_stream);
 
+/* Exchange Mp += interpolated (rivers + icebergs).  Run AFTER coflux_interpolate_atmosphere (which sets Mp); the fused
+ * coflux_update_state does both when inputs->land is given.                                                       */
+int coflux_interpolate_land(coflux_ctx*, const coflux_land_series* in, double time, coflux_exchange_state* inout, void* cu_stream);
+
 int coflux_atmosphere_ocean_fluxes(coflux_ctx*, const coflux_exchange_state* atmos,
                                    const coflux_ocean_surface* ocean,
                                    coflux_interface_fluxes* out, void* cu_stream);
@@ -369,6 +431,12 @@ int coflux_assemble_net_ocean_fluxes(coflux_ctx*, const coflux_exchange_state* a
                                      const coflux_sea_ice_state* ice /* may be NULL */,
                                      const coflux_ice_ocean_fluxes* ice_ocean /* may be NULL */,
                                      coflux_net_ocean_fluxes* out, void* cu_stream);
+
+/* compute_net_sea_ice_fluxes!: top = (Q_d + Q_u + Q_c + Q_v)·[ℵ > 0], bottom = Q_frazil + Q_interface, land cells 0.
+ * Q_u = ε σ T_s⁴ with the ice top temperature, Q_d = −(1 − α) Q_s − ε Q_ℓ with the sea-ice albedo (prescribed or CCSM3). */
+int coflux_assemble_net_sea_ice_fluxes(coflux_ctx*, const coflux_exchange_state* atmos, const coflux_ocean_surface* ocean /* mask; may be NULL */,
+                                       const coflux_sea_ice_state* ice, const coflux_interface_fluxes* atmosphere_sea_ice,
+                                       const coflux_ice_ocean_fluxes* ice_ocean, coflux_net_sea_ice_fluxes* out, void* cu_stream);
 
 /* Fused interpolate + similarity solve + net-ocean assembly (2 launches: flux kernel, then the
  * centre→face stress kernel).  Writes every contract output exactly once.                          */
@@ -443,6 +511,53 @@ typedef struct coflux_closure_forcing {
 int coflux_closure_surface_forcing(coflux_ctx*, const coflux_net_ocean_fluxes* net, const coflux_closure_forcing*, void* cu_stream);
 int coflux_attach_closure_forcing(coflux_ctx*, const coflux_closure_forcing* forcing_or_null);
 
+/* ------------------------------------------------------------------------------------------------
+ * Time-averaged flux diagnostics — SURVEY §8f row 4, second half.  The reference writes the flux fields through
+ * `JLD2Writer(...; schedule = AveragedTimeInterval(...))` (omip_diagnostics.jl:125-158), i.e. Oceananigans'
+ * WindowedTimeAverage: at every iteration inside the window  result ← (result·T + field·Δt) / (T + Δt), T the time
+ * already accumulated.  Attached to a context, the running averages are updated by coflux_update_state itself — in the
+ * epilogue of the flux kernel (tracer fluxes, turbulent heat fluxes) and of the stress kernel (τx, τy), while the values
+ * are in registers: no flux field is read back.  Any array may be absent.
+ *   tau_x tau_y JT JS Qc Qv          tauuo tauvo hfds wfo hfss hfls   (omip_diagnostics.jl:77-82, 125-130)
+ *   JT_atmosphere_ocean               JTao = (1 − ℵ) ΣQ / (ρ₀ c₀)
+ *   JT_ice_ocean, JS_ice_ocean        JTio = Q_io / (ρ₀ c₀),  JSio = ℵ · J^S_io
+ *   JT_frazil                         JTf  = Q_frazil / (ρ₀ c₀)  (accumulated by coflux_sea_ice_ocean_fluxes)
+ * (JTn, JSn of omip_diagnostics.jl:85-88 are JT, JS.)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct coflux_flux_averages {
+  coflux_array tau_x, tau_y, JT, JS, Qc, Qv;
+  coflux_array JT_atmosphere_ocean, JT_ice_ocean, JS_ice_ocean, JT_frazil;
+  double previous_interval;      /* T: seconds already accumulated in the current window (0 starts a new window) */
+  double dt;                     /* Δt of this collection                                                     */
+} coflux_flux_averages;
+/* every following coflux_update_state / coflux_sea_ice_ocean_fluxes accumulates; call again with the new
+ * (previous_interval, dt) before each step; NULL detaches                                                       */
+int coflux_attach_flux_averages(coflux_ctx*, const coflux_flux_averages* averages_or_null);
+/* stand-alone form: one launch, reads the flux fields back                                                       */
+int coflux_accumulate_flux_averages(coflux_ctx*, const coflux_net_ocean_fluxes* net, const coflux_interface_fluxes* atmosphere_ocean,
+                                    const coflux_sea_ice_state* ice /* may be NULL */, const coflux_ice_ocean_fluxes* ice_ocean /* may be NULL */,
+                                    const coflux_flux_averages* averages, void* cu_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device forcing window — SURVEY §8f row 2.  The reference keeps `time_indices_in_memory` levels of every JRA55
+ * series on the device and prefetches the next ones (`prefetch = true`, atmosphere.jl:22-27; launch.sh:86-87).  Here:
+ * a ring of `capacity` time slots per field in device memory.  coflux_forcing_window_upload copies ONE time level of
+ * all fields from (pinned) host memory into the slot  level mod capacity  on the window's own copy stream and returns
+ * at once; coflux_forcing_window_wait orders a compute stream behind the uploads of the levels it is about to read
+ * (event wait, no host sync); coflux_forcing_window_release records that the work enqueued on a compute stream so far
+ * is the last reader of the given levels, so a later upload into one of their slots waits for it (on the copy stream).  The series descriptors
+ * handed to the kernels point into the ring with (ring_start, ring_capacity).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct coflux_forcing_window coflux_forcing_window;
+int coflux_forcing_window_create(coflux_forcing_window** w, coflux_ctx* ctx, int32_t n_fields, int64_t plane_elements, int32_t capacity);
+int coflux_forcing_window_destroy(coflux_forcing_window* w);
+int coflux_forcing_window_upload(coflux_forcing_window* w, int64_t level, const void* const* host_planes /* n_fields */);
+int coflux_forcing_window_field(coflux_forcing_window* w, int32_t field, void** device_ptr /* capacity × plane_elements elements */);
+int coflux_forcing_window_wait(coflux_forcing_window* w, int64_t first_level, int64_t last_level, void* cu_stream);
+int coflux_forcing_window_release(coflux_forcing_window* w, int64_t first_level, int64_t last_level, void* cu_stream);
+/* bytes uploaded so far, and the number of uploads that had to wait for a reader (diagnostics)                 */
+int coflux_forcing_window_stats(coflux_forcing_window* w, int64_t* bytes_uploaded, int64_t* levels_uploaded);
+
 /* Diagnostics */
 int coflux_launch_count(coflux_ctx*, int64_t* launches);   /* kernels launched through this context  */
 /* Per-kernel device timing of coflux_update_state: when enabled, CUDA events are recorded on the
@@ -463,6 +578,9 @@ int coflux_profile_read(coflux_ctx*, double* flux_kernel_ms, double* stress_kern
  * the host (torch.distributed / MPI all-gather), every rank calls coflux_seam_attach with its west
  * and east neighbours' handles (periodic ring); afterwards all ranks must call coflux_update_state
  * the same number of times.  With world == 1 a context may attach to itself (periodic single slab).
+ * Ordering required of the host: a barrier between the LAST coflux_update_state of the ring and any
+ * coflux_seam_detach / coflux_destroy (a neighbour may still be storing into this context's buffer); none is needed
+ * between attach and the first update (attach does not reset the flag words).
  * ---------------------------------------------------------------------------------------------- */
 #define COFLUX_SEAM_HANDLE_BYTES 128
 int coflux_seam_export(coflux_ctx*, void* handle_out /* COFLUX_SEAM_HANDLE_BYTES */);

@@ -446,6 +446,9 @@ static inline int SUF(active)(const coflux_array* mask, int i, int j) {
   return ((const uint8_t*)mask->ptr)[SUF(idx)(mask, i, j, 0, 0)] != 0;
 }
 
+/* device ring buffer of a series (coflux_forcing_window): logical level n lives in time slot (start + n) mod capacity */
+static int SUF(ring_slot)(int n, int start, int capacity) { return capacity > 0 ? (start + n) % capacity : n; }
+
 /* A8: bilinear (space) × linear (time) interpolation of one series */
 static FT SUF(interp_series)(const coflux_array* a, FT fi, FT fj, int n1, int n2, FT nfrac) {
   int i0 = (int)TRUNC(fi), j0 = (int)TRUNC(fj);
@@ -467,6 +470,8 @@ int SUF(oracle_interpolate_atmosphere)(const coflux_config* cfg, const coflux_at
   if (rc) return rc;
   const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny, r = cfg->grid.ring;
   FT nf = (FT)frac;
+  n1 = SUF(ring_slot)(n1, in->ring_start, in->ring_capacity);
+  n2 = SUF(ring_slot)(n2, in->ring_start, in->ring_capacity);
 #pragma omp parallel for schedule(static)
   for (int j = -r; j < Ny + r; ++j)
     for (int i = -r; i < Nx + r; ++i) {
@@ -491,6 +496,50 @@ int SUF(oracle_interpolate_atmosphere)(const coflux_config* cfg, const coflux_at
       SUF(st)(&out->Ql, i, j, 0, Ql); SUF(st)(&out->Mp, i, j, 0, Mp);
     }
   return 0;
+}
+
+/* Land freshwater (JRA55PrescribedLand, /root/reference/src/OMIPConfigurations/atmosphere.jl:46; variables friver, licalvf:
+ * jra55_data_staging.jl:8): river runoff and iceberg calving, interpolated like the atmosphere on their own source grid
+ * and time axis and ADDED to the exchange freshwater flux:  Mp ← Mp + (M_rivers + M_icebergs). */
+int SUF(oracle_interpolate_land)(const coflux_config* cfg, const coflux_land_series* in, double time, coflux_exchange_state* x) {
+  int n1, n2; double frac;
+  int rc = oracle_time_indices(in->times, in->Nt, in->time_indexing, in->cycle_period, time, &n1, &n2, &frac);
+  if (rc) return rc;
+  const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny, r = cfg->grid.ring;
+  FT nf = (FT)frac;
+  n1 = SUF(ring_slot)(n1, in->ring_start, in->ring_capacity);
+  n2 = SUF(ring_slot)(n2, in->ring_start, in->ring_capacity);
+#pragma omp parallel for schedule(static)
+  for (int j = -r; j < Ny + r; ++j)
+    for (int i = -r; i < Nx + r; ++i) {
+      FT fi = SUF(ld)(&in->fi, i, j, 0, 0), fj = SUF(ld)(&in->fj, i, j, 0, 0);
+      FT Mr = in->rivers.ptr ? SUF(interp_series)(&in->rivers, fi, fj, n1, n2, nf) : (FT)0;
+      FT Mi = in->icebergs.ptr ? SUF(interp_series)(&in->icebergs, fi, fj, n1, n2, nf) : (FT)0;
+      SUF(st)(&x->Mp, i, j, 0, SUF(ld)(&x->Mp, i, j, 0, 0) + (Mr + Mi));
+    }
+  return 0;
+}
+
+/* CCSM3 sea-ice albedo (Briegleb et al. 2004; the "ccsm3" shortwave option of CICE), include/coflux.h coflux_ccsm3_albedo;
+ * reference call site: SeaIceAlbedo(hi, hs, Ts), /root/reference/src/OMIPConfigurations/atmosphere.jl:31-44 */
+static FT SUF(ccsm3_albedo)(const coflux_ccsm3_albedo* a, FT hi, FT hs, FT TsK) {
+  FT fh = FMIN(ATAN((FT)4 * hi) / ATAN((FT)4 * (FT)a->thickness_scale), (FT)1);
+  FT fT = FMIN(FMAX((FT)1 - ((FT)a->melting_temperature - TsK) / (FT)a->melt_temperature_range, (FT)0), (FT)1);
+  FT aiv = (FT)a->ice_visible * fh + (FT)a->ocean_albedo * ((FT)1 - fh) - (FT)a->ice_melt_change * fT;
+  FT ain = (FT)a->ice_near_infrared * fh + (FT)a->ocean_albedo * ((FT)1 - fh) - (FT)a->ice_melt_change * fT;
+  FT asv = (FT)a->snow_visible - (FT)a->snow_visible_melt_change * fT;
+  FT asn = (FT)a->snow_near_infrared - (FT)a->snow_near_infrared_melt_change * fT;
+  FT fs = hs / (hs + (FT)a->snow_patchiness);
+  FT av = ((FT)1 - fs) * aiv + fs * asv;
+  FT an = ((FT)1 - fs) * ain + fs * asn;
+  return (FT)a->visible_fraction * av + ((FT)1 - (FT)a->visible_fraction) * an;
+}
+static FT SUF(sea_ice_albedo)(const coflux_config* cfg, const coflux_sea_ice_state* ice, int i, int j, FT TsK) {
+  if (cfg->radiation.sea_ice_albedo_kind == COFLUX_SEA_ICE_ALBEDO_CCSM3) {
+    FT hs = ice->snow_thickness.ptr ? SUF(ld)(&ice->snow_thickness, i, j, 0, 0) : (FT)0;
+    return SUF(ccsm3_albedo)(&cfg->radiation.ccsm3, SUF(ld)(&ice->thickness, i, j, 0, 0), hs, TsK);
+  }
+  return ice->albedo.ptr ? SUF(ld)(&ice->albedo, i, j, 0, 0) : (FT)cfg->radiation.sea_ice_albedo;
 }
 
 static FT SUF(to_kelvin)(const coflux_ocean_properties* o, FT T) {
@@ -568,7 +617,7 @@ int SUF(oracle_atmosphere_sea_ice_fluxes)(const coflux_config* cfg, const coflux
       in.So = (FT)0;
       in.h_ice = SUF(ld)(&ice->thickness, i, j, 0, 0);
       in.S_ice = SUF(ld)(&ice->salinity, i, j, 0, 0);
-      in.albedo = ice->albedo.ptr ? SUF(ld)(&ice->albedo, i, j, 0, 0) : (FT)cfg->radiation.sea_ice_albedo;
+      in.albedo = SUF(sea_ice_albedo)(cfg, ice, i, j, in.To);
       FT conc = SUF(ld)(&ice->concentration, i, j, 0, 0);
       FT Qv = 0, Qc = 0, Fv = 0, rtx = 0, rty = 0, Tsout = Ttop_units, us = 0, ts = 0, qs = 0; int its = 0;
       if (SUF(active)(&ocean->mask, i, j) && conc > (FT)0 && in.h_ice > (FT)0) {
@@ -754,10 +803,87 @@ int SUF(oracle_update_state)(const coflux_config* cfg, const coflux_update_input
                              double time) {
   int rc = SUF(oracle_interpolate_atmosphere)(cfg, in->atmosphere, time, out->exchange);
   if (rc) return rc;
+  if (in->land) { rc = SUF(oracle_interpolate_land)(cfg, in->land, time, out->exchange); if (rc) return rc; }
   rc = SUF(oracle_atmosphere_ocean_fluxes)(cfg, out->exchange, in->ocean, out->atmosphere_ocean);
   if (rc) return rc;
   return SUF(oracle_assemble_net_ocean_fluxes)(cfg, out->exchange, in->ocean, out->atmosphere_ocean, in->sea_ice,
                                                in->ice_ocean, out->net_ocean);
+}
+
+/* compute_net_sea_ice_fluxes!: what the sea-ice model receives.
+ *   top    = (Q_d + Q_u + Q_c + Q_v)·[ℵ > 0],  Q_u = ε σ T_s⁴ (ice top temperature), Q_d = −(1 − α) Q_s − ε Q_ℓ
+ *   bottom = Q_frazil + Q_interface
+ * land cells 0; optional: atmosphere–ice stress ρτ averaged to the velocity points. */
+int SUF(oracle_assemble_net_sea_ice_fluxes)(const coflux_config* cfg, const coflux_exchange_state* atmos, const coflux_ocean_surface* ocean,
+                                            const coflux_sea_ice_state* ice, const coflux_interface_fluxes* ai,
+                                            const coflux_ice_ocean_fluxes* io, coflux_net_sea_ice_fluxes* out) {
+  const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny, r = cfg->grid.ring;
+  const coflux_radiation_properties* R = &cfg->radiation;
+  FT sigma = (FT)R->stefan_boltzmann_constant, emis = (FT)R->sea_ice_emissivity;
+  const int px = (r == 0 && cfg->grid.periodic_x);
+  coflux_array nomask; nomask.ptr = 0;
+  const coflux_array* mask = ocean ? &ocean->mask : &nomask;
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j < Ny; ++j)
+    for (int i = 0; i < Nx; ++i) {
+      int act = SUF(active)(mask, i, j);
+      FT TsK = SUF(to_kelvin)(&cfg->ocean, SUF(ld)(&ice->top_temperature, i, j, 0, 0));
+      FT conc = SUF(ld)(&ice->concentration, i, j, 0, 0);
+      FT alpha = SUF(sea_ice_albedo)(cfg, ice, i, j, TsK);
+      FT Qu = emis * sigma * TsK * TsK * TsK * TsK;
+      FT Qd = -((FT)1 - alpha) * SUF(ld)(&atmos->Qs, i, j, 0, 0) - emis * SUF(ld)(&atmos->Ql, i, j, 0, 0);
+      FT SQt = (conc > (FT)0) ? (Qd + Qu + SUF(ld)(&ai->sensible_heat, i, j, 0, 0) + SUF(ld)(&ai->latent_heat, i, j, 0, 0)) : (FT)0;
+      FT Qf = (io && io->frazil_heat.ptr) ? SUF(ld)(&io->frazil_heat, i, j, 0, 0) : (FT)0;
+      FT Qi = (io && io->interface_heat.ptr) ? SUF(ld)(&io->interface_heat, i, j, 0, 0) : (FT)0;
+      SUF(st)(&out->top_heat, i, j, 0, act ? SQt : (FT)0);
+      SUF(st)(&out->bottom_heat, i, j, 0, act ? (Qf + Qi) : (FT)0);
+      if (out->top_u.ptr) {
+        int iw = (px && i == 0) ? Nx - 1 : i - 1;
+        FT v = (SUF(ld)(&ai->x_momentum, iw, j, 0, 0) + SUF(ld)(&ai->x_momentum, i, j, 0, 0)) * (FT)0.5;
+        SUF(st)(&out->top_u, i, j, 0, (act && SUF(active)(mask, iw, j)) ? v : (FT)0);
+      }
+      if (out->top_v.ptr) {
+        FT v = (SUF(ld)(&ai->y_momentum, i, j - 1, 0, 0) + SUF(ld)(&ai->y_momentum, i, j, 0, 0)) * (FT)0.5;
+        SUF(st)(&out->top_v, i, j, 0, (act && SUF(active)(mask, i, j - 1)) ? v : (FT)0);
+      }
+    }
+  return 0;
+}
+
+/* Time-averaged flux diagnostics (§8f row 4): the reference writes the flux fields under
+ * `schedule = AveragedTimeInterval(...)` (/root/reference/src/OMIPConfigurations/omip_diagnostics.jl:152-158), i.e. Oceananigans'
+ * WindowedTimeAverage, which accumulates  result ← (result·T + field·Δt) / (T + Δt)  at every iteration inside the window
+ * (T: time already accumulated).  Fields: omip_diagnostics.jl:77-89, 125-148. */
+static void SUF(avg_update)(const coflux_array* a, int i, int j, FT x, FT T, FT dt) {
+  if (!a->ptr) return;
+  FT* p = (FT*)a->ptr + SUF(idx)(a, i, j, 0, 0);
+  *p = (*p * T + x * dt) / (T + dt);
+}
+int SUF(oracle_accumulate_flux_averages)(const coflux_config* cfg, const coflux_net_ocean_fluxes* net, const coflux_interface_fluxes* ao,
+                                         const coflux_sea_ice_state* ice, const coflux_ice_ocean_fluxes* io, const coflux_flux_averages* v) {
+  const int Nx = cfg->grid.Nx, Ny = cfg->grid.Ny;
+  FT T = (FT)v->previous_interval, dt = (FT)v->dt;
+  FT rho0 = (FT)cfg->ocean.reference_density, c0 = (FT)cfg->ocean.heat_capacity;
+  FT rho0inv = (FT)1 / rho0;
+  for (int j = 0; j < Ny; ++j)
+    for (int i = 0; i < Nx; ++i) {
+      SUF(avg_update)(&v->tau_x, i, j, SUF(ld)(&net->u, i, j, 0, 0), T, dt);
+      SUF(avg_update)(&v->tau_y, i, j, SUF(ld)(&net->v, i, j, 0, 0), T, dt);
+      FT JT = SUF(ld)(&net->T, i, j, 0, 0);
+      SUF(avg_update)(&v->JT, i, j, JT, T, dt);
+      SUF(avg_update)(&v->JS, i, j, SUF(ld)(&net->S, i, j, 0, 0), T, dt);
+      if (ao) {
+        SUF(avg_update)(&v->Qc, i, j, SUF(ld)(&ao->sensible_heat, i, j, 0, 0), T, dt);
+        SUF(avg_update)(&v->Qv, i, j, SUF(ld)(&ao->latent_heat, i, j, 0, 0), T, dt);
+      }
+      FT JTio = (io && io->interface_heat.ptr) ? SUF(ld)(&io->interface_heat, i, j, 0, 0) * rho0inv / c0 : (FT)0;
+      SUF(avg_update)(&v->JT_ice_ocean, i, j, JTio, T, dt);
+      SUF(avg_update)(&v->JT_atmosphere_ocean, i, j, JT - JTio, T, dt);
+      FT conc = (ice && ice->concentration.ptr) ? SUF(ld)(&ice->concentration, i, j, 0, 0) : (FT)0;
+      SUF(avg_update)(&v->JS_ice_ocean, i, j, (io && io->salt.ptr) ? SUF(ld)(&io->salt, i, j, 0, 0) * conc : (FT)0, T, dt);
+      if (io && io->frazil_heat.ptr) SUF(avg_update)(&v->JT_frazil, i, j, SUF(ld)(&io->frazil_heat, i, j, 0, 0) / rho0 / c0, T, dt);
+    }
+  return 0;
 }
 
 /* scalar probes for unit tests */

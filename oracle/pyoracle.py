@@ -84,6 +84,24 @@ def normalize_salinity_flux(cfg, norm, mean=None):
     return sums[0], sums[1]
 
 
+def interpolate_land(cfg, land, time, exchange):
+    f = fn("oracle_interpolate_land", cfg)
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    assert f(C.byref(cfg), C.byref(land), float(time), C.byref(exchange)) == 0
+
+
+def assemble_net_sea_ice_fluxes(cfg, exchange, ocean, ice, ai, io, out):
+    f = fn("oracle_assemble_net_sea_ice_fluxes", cfg)
+    assert f(C.byref(cfg), C.byref(exchange), C.byref(ocean) if ocean is not None else None, C.byref(ice), C.byref(ai),
+             C.byref(io) if io is not None else None, C.byref(out)) == 0
+
+
+def accumulate_flux_averages(cfg, net, ao, ice, io, averages):
+    f = fn("oracle_accumulate_flux_averages", cfg)
+    assert f(C.byref(cfg), C.byref(net), C.byref(ao) if ao is not None else None, C.byref(ice) if ice is not None else None,
+             C.byref(io) if io is not None else None, C.byref(averages)) == 0
+
+
 def set_threads(n):
     """Limit / set OpenMP threads of the oracle through libgomp's omp_set_num_threads."""
     gomp = C.CDLL("libgomp.so.1")
