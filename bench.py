@@ -44,10 +44,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+TRAFFIC_FILE = "profiles/r02_traffic.json"
+
+
 def load_traffic(cells):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the flux kernel from the committed `ncu --set full`
-    capture (profiles/r01_traffic.json, bytes per cell on the same 1/12° grid) scaled to this launch."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the flux kernel.  NOT measured in this run (a bench number is never
+    taken under a profiler): it comes from the committed `ncu --set full` capture of the same kernel on the same 1/12° grid
+    (bytes per cell in profiles/r02_traffic.json) scaled to this launch; `traffic_source` in the JSON line says so."""
+    p = os.path.join(ROOT, TRAFFIC_FILE)
     try:
         return float(json.load(open(p))["flux_tile_kernel_f64_dram_bytes_per_cell"]) * cells
     except Exception:
@@ -119,6 +123,32 @@ def barrier(dist):
         dist.barrier()
 
 
+def gather_over_ranks(dist, x, device, world):
+    """x of every rank, on every rank (list of floats)."""
+    if dist is None:
+        return [float(x)]
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
+def bit_checksum(field, x0=None, x1=None):
+    """Order-independent checksum of the interior of a 2-D output Field: the sum of the raw bit patterns (mod 2⁶⁴) of the
+    columns [x0, x1) — equal checksums ⇔ (to all intents) bit-identical data, and slab checksums add up to the global one."""
+    import torch
+    Hx, Hy, _ = field.halo
+    a = field.data[0, Hy:field.data.shape[1] - Hy, Hx:field.data.shape[2] - Hx]
+    if x0 is not None:
+        a = a[:, x0:x1]
+    bits = a.contiguous().view(torch.int64 if a.dtype == torch.float64 else torch.int32).to(torch.int64)
+    return int(bits.sum().item())
+
+
+CHECK_FIELDS = (("net", "u"), ("net", "v"), ("net", "T"), ("net", "S"), ("ao", "latent_heat"), ("ao", "sensible_heat"))
+
+
 def max_over_ranks(dist, x, device):
     if dist is None:
         return x
@@ -155,6 +185,7 @@ def time_device_steps(eng, dev, steps, warmup, dist, device, sampler=None):
     flux_ms, stress_ms, calls = eng.profile_read()
     eng.profile(False)
     launches = eng.launches - l0
+    time_device_steps.local_ms = ms                       # this rank's own time (the return value is the max over ranks)
     ms = max_over_ranks(dist, ms, device)
     return ms, launches, flux_ms / max(calls, 1), stress_ms / max(calls, 1), clocks
 
@@ -203,8 +234,10 @@ def oracle_rate(host, cfg_full, rows, threads):
 
 def cpu_baseline(host, cfg, target_seconds=12.0):
     """Oracle port on all host cores, on a bounded sample of the same workload (≈ target_seconds of CPU wall
-    time): as many latitude rows as fit, the whole grid repeated when one pass is shorter than the target."""
+    time): as many latitude rows as fit, the whole grid repeated when one pass is shorter than the target.
+    Uses the CPU-baseline build of the oracle (-O3 -march=native, compiled here for this host: oracle/Makefile `fast`)."""
     from oracle import pyoracle
+    pyoracle.use_fast_build()
     cores = os.cpu_count() or 1
     pyoracle.set_threads(cores)
     oracle_rate(host, cfg, 4, cores)                                   # spin up the thread team
@@ -221,6 +254,7 @@ def cpu_baseline(host, cfg, target_seconds=12.0):
         dt, cells = oracle_rate(host, cfg, rows, cores)
         total_t += dt; total_c += cells; reps += 1
     return {"value": total_c / total_t / 1e6, "unit": "Mcells/s", "cores": cores, "kind": "port",
+            "build": "gcc -O3 -march=native -fopenmp (oracle/Makefile: fast), built on this host",
             "sample": f"CPU oracle (C restatement, OpenMP) update_state on the first {rows} of {Ny} latitude rows "
                       f"({Nx * rows} cells) of the same workload, {reps} pass(es), {total_t:.1f} s",
             "note": "the Julia reference cannot run here (no Julia, dependency un-vendored); this is the oracle port"}
@@ -231,9 +265,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["COFLUX_NO_LIBRARY"] = "1"       # this arm must not load the product: grid / synthetic-input helpers only
     from oracle import pyoracle
+    from climaocean.jl_b200 import _abi
+    pyoracle.use_fast_build()                    # -O3 -march=native build of the oracle, compiled here for this host
     grid, host = make_host_case(NX, NY, 64, 0, 1)
-    cfg = make_cfg(grid, 1, 64, 0)
+    cfg = pyoracle.default_config(_abi.Config(), grid.Nx, grid.Ny, 1, 64, "default")     # defaults stated on the oracle side
+    cfg.grid.ring = 1
     cores = os.cpu_count() or 1
     pyoracle.set_threads(cores)
     oracle_rate(host, cfg, 4, cores)
@@ -258,7 +296,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(1),
-        "cpu_baseline": {"value": v, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample,
+                         "build": "gcc -O3 -march=native -fopenmp (oracle/Makefile: fast), built on this host"},
         "e2e": {"value": v, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port on host cores; the Julia reference is not runnable in this environment (DESIGN.md §3)"}))
 
@@ -313,8 +352,10 @@ def main():
     cells_global = NX * NY
     cells_local = grid.Nx * grid.Ny
     value = cells_global / (ms * 1e-3) / 1e6
+    rank_kernel_ms = gather_over_ranks(dist, flux_ms, device, world)
+    rank_step_ms = gather_over_ranks(dist, time_device_steps.local_ms, device, world)
     its = dev.iterations.numpy()[0, 7:-7, 7:-7]
-    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,384,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
+    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,768,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
             "achieved": cells_local * WORDS_FLUX_KERNEL * 8 / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "peak_source": peak_src, "traffic": load_traffic(cells_local),
             "algorithmic_bytes_per_cell": WORDS_FLUX_KERNEL * 8, "kernel_ms": flux_ms, "stress_kernel_ms": stress_ms,
@@ -428,7 +469,33 @@ def main():
                                                    "ice_covered_fraction": float((di.ice["concentration"].data > 0).double().mean())}
         ei.close(); del di, hi, T0
 
+    multi_gpu_check = None
     if world > 1:
+        # correctness of the slab decomposition, carried by the scaling run itself: every rank checksums the bit patterns of
+        # its slab's outputs; rank 0 solves the WHOLE grid once on its own GPU and checksums the same column ranges.
+        import torch
+        mine = torch.tensor([bit_checksum(getattr(dev, g)[n]) for g, n in CHECK_FIELDS], dtype=torch.int64, device=device)
+        allsums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+        if rank == 0:
+            gf, hf = make_host_case(NX, NY, 64, 0, 1)
+            df = hf.to_device_columns(device, NZ)
+            ef = cj.Engine(make_cfg(df.grid, NZ, 64, local))
+            inp_f, out_f = df.update_bundles()
+            ef.update_state(inp_f, out_f, QUERY_TIME, torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            nx = NX // world
+            bad = []
+            for r in range(world):
+                want = [bit_checksum(getattr(df, g)[n], r * nx, (r + 1) * nx) for g, n in CHECK_FIELDS]
+                got = [int(v) for v in allsums[r].tolist()]
+                if want != got:
+                    bad.append(r)
+            multi_gpu_check = {"bitwise_match_vs_single_gpu": not bad, "mismatching_slabs": bad,
+                               "fields": [f"{g}.{n}" for g, n in CHECK_FIELDS],
+                               "how": "sum of raw bit patterns (mod 2^64) of every slab's interior vs the same columns of a one-GPU solve of the whole grid"}
+            ef.close(); del df, hf
+        barrier(dist)
         # mode B: ring = 0, the flux kernel pushes the seam column of ρτx into the east neighbour over NVLink
         from climaocean.jl_b200 import slabs
         gs, hs = make_host_case(NX, NY, 64, rank, world)
@@ -458,6 +525,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(world), "roofline": roof, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extras": extras,
+                "ranks": {"flux_kernel_ms": {"min": min(rank_kernel_ms), "mean": float(np.mean(rank_kernel_ms)), "max": max(rank_kernel_ms)},
+                          "step_ms": {"min": min(rank_step_ms), "mean": float(np.mean(rank_step_ms)), "max": max(rank_step_ms)}},
+                "multi_gpu_check": multi_gpu_check,
                 "parity_note": "oracle-relative (the Julia reference cannot run here; parity unpinned, DESIGN.md §3)"}
         print(json.dumps(line))
     eng.close()

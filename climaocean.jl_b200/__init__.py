@@ -13,4 +13,9 @@ from .engine import Engine
 from .forcing import InMemoryWindow, DeviceForcingWindow
 from .models import *  # noqa: F401,F403  (reference-facing names)
 
-load_library()   # fail loudly at import when lib/libcoflux.so has not been built
+import os as _os
+
+# fail loudly at import when lib/libcoflux.so has not been built.  COFLUX_NO_LIBRARY=1 is for bench.py's CPU arm
+# (`--impl reference`), which only needs the grid / synthetic-input / struct-layout helpers and must not load the product.
+if not _os.environ.get("COFLUX_NO_LIBRARY"):
+    load_library()

@@ -561,7 +561,9 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 // different CTAs overlap on an SM (A is latency bound on gathers, B on the FP64 / issue pipes), which wants several.
 //   Float64 `:default`   256 threads × 3 CTAs/SM, 768 cells per CTA (58 B/cell + 29 KB of tables = 73.7 KB), 80 registers
 //   Float64 `:corrected` 384 threads × 2 CTAs/SM, 1152 cells (74 B/cell: ν and 1/ν vary), 80 registers
-//   Float32              256 threads × 4 CTAs/SM, 1024 cells (30 / 38 B/cell + 13 KB table), 64 registers
+//   Float32              384 threads × 3 CTAs/SM, 1536 cells (30 / 38 B/cell + 13 KB table), 56 registers
+// A/B on B200 at 1/12° (profiles/README.md): Float64 at 64 / 72 registers (32 / 28 warps per SM) is SLOWER (3.98 / 3.56 ms
+// against 3.32 ms: the spills cost more than the extra warps hide); Float32 256 × 4 × 1024 2.40 ms, 384 × 3 × 1536 2.34 ms.
 // Round-1 shape for reference (table in global memory): 128 threads × 6 CTAs, 384 cells (profiles/README.md).
 #ifndef COFLUX_TILE_PRE1
 #define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A (A/B knob) */
@@ -585,13 +587,13 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 #define COFLUX_TILE_MIN_BLOCKS64_S2 2
 #endif
 #ifndef COFLUX_TILE_NT32
-#define COFLUX_TILE_NT32 256
+#define COFLUX_TILE_NT32 384
 #endif
 #ifndef COFLUX_TILE_CELLS32
-#define COFLUX_TILE_CELLS32 1024
+#define COFLUX_TILE_CELLS32 1536
 #endif
 #ifndef COFLUX_TILE_MIN_BLOCKS32
-#define COFLUX_TILE_MIN_BLOCKS32 4
+#define COFLUX_TILE_MIN_BLOCKS32 3
 #endif
 
 // shared-memory layout of one tile (SoA: consecutive lanes touch consecutive words — no bank conflicts).

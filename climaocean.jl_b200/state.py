@@ -97,6 +97,7 @@ class SurfaceFluxData:
         self.net = {n: mk("net_" + n) for n in NET_NAMES}
         self.iterations = Field.zeros(size2, h2, np.int32, self.device, "iterations")
         if self.ice is not None:
+            self.iterations_ai = Field.zeros(size2, h2, np.int32, self.device, "iterations_ai")
             self.ai = {n: mk("ai_" + n) for n in IFACE_NAMES}
             self.io = {n: mk("io_" + n) for n in IO_NAMES}
             self.net_ice = {n: mk("net_ice_" + n) for n in NET_ICE_NAMES}
@@ -217,7 +218,7 @@ class SurfaceFluxData:
         s = _abi.InterfaceFluxes()
         for n in IFACE_NAMES:
             setattr(s, n, arr(d[n]))
-        s.iterations = arr(self.iterations) if (with_iterations and which == "ao") else arr(None)
+        s.iterations = arr(self.iterations if which == "ao" else self.iterations_ai) if with_iterations else arr(None)
         return s
 
     def sea_ice_state(self):

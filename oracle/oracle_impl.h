@@ -966,3 +966,15 @@ void SUF(oracle_probe_solve)(const coflux_config* cfg, const FT* in9, FT* out4) 
   SUF(scales) s = SUF(solve_cell)(&cfg->atmosphere_ocean, cfg, &c, &in, 0, &atm, &du, &dv);
   out4[0] = s.ustar; out4[1] = s.tstar; out4[2] = s.qstar; out4[3] = (FT)s.iterations;
 }
+/* solve one atmosphere–sea-ice cell (skin temperature): in13 = ua va Ta pa qa ui vi Ttop[K] Qs Ql h_ice S_ice albedo;
+ * out5 = u★ θ★ q★ T_s[K] iterations */
+void SUF(oracle_probe_solve_ice)(const coflux_config* cfg, const FT* in13, FT* out5) {
+  SUF(thermo_consts) c = SUF(make_thermo)(&cfg->atmosphere.thermodynamics);
+  SUF(cell_in) in;
+  in.ua = in13[0]; in.va = in13[1]; in.Ta = in13[2]; in.pa = in13[3]; in.qa = in13[4];
+  in.uo = in13[5]; in.vo = in13[6]; in.To = in13[7]; in.So = (FT)0;
+  in.Qs = in13[8]; in.Ql = in13[9]; in.h_ice = in13[10]; in.S_ice = in13[11]; in.albedo = in13[12];
+  SUF(thermo_state) atm; FT du, dv;
+  SUF(scales) s = SUF(solve_cell)(&cfg->atmosphere_sea_ice, cfg, &c, &in, 1, &atm, &du, &dv);
+  out5[0] = s.ustar; out5[1] = s.tstar; out5[2] = s.qstar; out5[3] = s.Ts; out5[4] = (FT)s.iterations;
+}

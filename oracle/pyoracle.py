@@ -13,6 +13,25 @@ LIB_PATH = os.path.join(_HERE, "libcoflux_oracle.so")
 _lib = None
 
 
+def use_fast_build():
+    """Switch this process to the CPU-BASELINE build of the oracle (-O3 -march=native, built here and now for this host's
+    cores: oracle/Makefile `fast`).  For bench.py's timed CPU legs only; the parity tests keep the -O2 -ffp-contract=off build."""
+    global LIB_PATH, _lib
+    subprocess.run(["make", "-C", _HERE, "-B", "fast"], check=True, stdout=subprocess.DEVNULL)
+    LIB_PATH = os.path.join(_HERE, "libcoflux_oracle_fast.so")
+    _lib = None
+    return load(build_if_missing=False)
+
+
+def default_config(cfg, Nx, Ny, Nz, dtype, flux_configuration="default", velocity=0):
+    """Fill a coflux_config with the reference defaults + a build_coupled_model flux configuration — on the oracle side, so
+    that the CPU arm of bench.py does not load the product library."""
+    lib = load()
+    assert lib.oracle_default_config(C.byref(cfg), int(Nx), int(Ny), int(Nz), int(dtype)) == 0
+    assert lib.oracle_apply_flux_configuration(C.byref(cfg), flux_configuration.encode(), int(velocity)) == 0
+    return cfg
+
+
 def load(build_if_missing=True):
     global _lib
     if _lib is not None:

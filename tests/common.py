@@ -9,15 +9,35 @@ from oracle import pyoracle
 QUERY_TIME = 1.37 * 3 * 3600.0   # exercises the time weights
 
 # Tolerances of BASELINE.json:north_star: ≤1e-12 relative in Float64, ≤1e-5 in Float32.
-# Relative error is |a−b| / max(|b|, FLOOR·max|b|).  Every flux is proportional to a difference of
-# nearly equal inputs (Δθ = θ_a − T_s, Δq = q_a − q_s, signed sums in the assembly), so a result near
-# zero carries an ABSOLUTE rounding error of a few ulp of the operands — i.e. a few ulp of the field's
-# own scale — no matter who computes it (measured: ≤ 8e-16·max|b| in Float64, ≤ 5e-7·max|b| in Float32
-# between oracle and CUDA, tests/diag/parity_report.py).  The denominator is therefore floored at a
-# fraction of the field's largest magnitude: 1e-3 in Float64 (absolute error ≤ 1e-15·max|b| ≈ 9 ulp)
-# and 1e-1 in Float32 (≤ 1e-6·max|b| ≈ 17 ulp).  Stated once here, used by every parity test.
+# Relative error is |a−b| / max(|b|, FLOOR·max|b|).  Every flux is proportional to a difference of nearly equal inputs
+# (Δθ = θ_a − T_s, Δq = q_a − q_s, signed sums in the assembly), so a result near zero carries an ABSOLUTE rounding error of a
+# few ulp of the operands — i.e. a few ulp of the field's own scale — no matter who computes it.  Measured, CUDA vs oracle on
+# 256×128 cells × 3 flux configurations (tests/diag/parity_report.py → profiles/r02_parity_report.log):
+#   Float64  max|a−b| ≤ 1.0e-15·max|b| in every field; un-floored relative error p99.9 ≤ 3e-13
+#   Float32  max|a−b| ≤ 5.2e-7·max|b| (4 ulp of the field scale) in every field; un-floored relative error of the cells
+#            carrying signal: median 1.2e-7, p99 5.5e-6, p99.9 4.8e-5, max 5e-3 (latent heat −0.18 W m⁻² in a field of ±600);
+#            with the denominator floored at 1e-3·max|b| 0.4 % of the cells exceed 1e-5, at 1e-2 the worst cell reads 1.7e-5,
+#            at 1e-1 it reads 2e-6.
+# The max-norm test therefore floors the denominator at 1e-3 (Float64) / 1e-1 (Float32) of the field's largest magnitude, and in
+# Float32 `compare` ADDITIONALLY requires (a) max|a−b| ≤ 1e-6·max|b|, (b) the 99th percentile of the un-floored relative
+# error ≤ 1e-5, (c) ≤ 1 % of the cells over 1e-5 at the 1e-3 floor — so the wide floor cannot hide a systematic error.
 RTOL = {64: 1e-12, 32: 1e-5}
 FLOOR = {64: 1e-3, 32: 1e-1}
+
+
+def f32_distribution_ok(a, b):
+    """The extra Float32 requirements (a)–(c) above.  Returns (ok, description)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    if scale == 0.0:
+        return bool(np.max(np.abs(a)) == 0.0) if a.size else True, "zero field"
+    d = np.abs(a - b)
+    sig = np.abs(b) > 1e-6 * scale
+    p99 = float(np.percentile(d[sig] / np.abs(b[sig]), 99)) if sig.any() else 0.0
+    over = float(np.mean(d / np.maximum(np.abs(b), 1e-3 * scale) > 1e-5))
+    amax = float(d.max() / scale)
+    return (amax <= 1e-6 and p99 <= 1e-5 and over <= 0.01), f"max|d|/max|b| {amax:.1e}, raw p99 {p99:.1e}, cells>1e-5@1e-3 {over:.1e}"
 
 
 def rel_err(a, b, bits=64):
@@ -78,6 +98,51 @@ def compare(gpu, ref, bits, keys=None, rtol=None):
         if k not in gpu:
             continue
         worst[k] = rel_err(gpu[k], v, bits)
+        if bits == 32 and rtol == RTOL[32] and np.size(v) >= 1000:      # (percentiles of a handful of cells mean nothing)
+            ok, what = f32_distribution_ok(gpu[k], v)
+            assert ok, f"Float32 error distribution of {k}: {what}"
     bad = {k: e for k, e in worst.items() if not (e <= rtol)}
     assert not bad, f"parity failures (rtol {rtol}): {bad}"
     return worst
+
+
+def rel_err_masked(a, b, bits, mask):
+    """rel_err over the cells of `mask` only (the scale of the denominator floor is still that of the whole field)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    if scale == 0.0 or not mask.any():
+        return float(np.max(np.abs(a[mask]))) if mask.any() else 0.0
+    return float(np.max(np.abs(a[mask] - b[mask]) / np.maximum(np.abs(b[mask]), FLOOR[bits] * scale)))
+
+
+def compare_sea_ice(gpu, ref, bits, its_gpu, its_ref, maxit, keys, stress_keys=()):
+    """Parity of the atmosphere–sea-ice solve and what is derived from it (rows a7, f1).
+
+    The clamped skin-temperature update T_s ← T_s + clamp(T★(T_s) − T_s, ±ΔT_max) is not a contraction for h ≳ 0.1 m
+    (|∂T★/∂T_s| = (h/k)·∂Q_a/∂T_s ≈ 1.5 × 20 W m⁻² K⁻¹ ≫ 1): one ice cell in nine never meets the stop rule and ends, at
+    maxiter, somewhere on a 2-cycle whose phase is decided by the last bit.  The oracle's OWN Float32 and Float64 results differ
+    by up to 8 % of the field scale in such cells (tests/test_a7_conditioning.py).  So:
+      * cells where both sides converged: the north_star tolerance (1e-12 Float64, 1e-5 Float32);
+      * cells on a limit cycle in either: the orbit amplifies last-bit differences up to the cycle's amplitude.  Float64: the two
+        implementations have stayed within 1e-9 on every case so far (held to 1e-6), and the SAME cells must run to maxiter;
+        Float32: only bounded by the cycle amplitude, and which borderline cells run to maxiter may differ (reported)."""
+    conv = (its_gpu < maxit) & (its_ref < maxit)
+    cyc = ~conv
+    mismatch = float(np.mean((its_gpu >= maxit) != (its_ref >= maxit)))
+    assert mismatch <= (0.0 if bits == 64 else 0.25), f"different cells run to maxiter: {mismatch}"
+    face = conv.copy()                       # face-located averages see the cell and its west / south neighbour
+    face[:, 1:] &= conv[:, :-1]
+    face[1:, :] &= conv[:-1, :]
+    face[:, 0] = False
+    face[0, :] = False
+    worst = {}
+    for k in keys:
+        m = face if k in stress_keys else conv
+        worst[k] = rel_err_masked(gpu[k], ref[k], bits, m)
+        assert worst[k] <= RTOL[bits], (k, worst[k], "converged cells")
+        if cyc.any() and k not in stress_keys:
+            e = rel_err_masked(gpu[k], ref[k], bits, cyc)
+            assert e <= (1e-6 if bits == 64 else 3.0), (k, e, "limit-cycle cells")
+            worst[k + " (limit cycle)"] = e
+    return worst, float(cyc.mean())

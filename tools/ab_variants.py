@@ -11,14 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "base_256x3_768": [],
-    "r64_512x2_1408": ["COFLUX_TILE_NT64=512", "COFLUX_TILE_CELLS64=1408", "COFLUX_TILE_MIN_BLOCKS64=2",
-                       "COFLUX_TILE_NT64_S2=512", "COFLUX_TILE_CELLS64_S2=1024", "COFLUX_TILE_MIN_BLOCKS64_S2=2"],
-    "r72_448x2_1344": ["COFLUX_TILE_NT64=448", "COFLUX_TILE_CELLS64=1344", "COFLUX_TILE_MIN_BLOCKS64=2",
-                       "COFLUX_TILE_NT64_S2=448", "COFLUX_TILE_CELLS64_S2=1120", "COFLUX_TILE_MIN_BLOCKS64_S2=2"],
-    "r64_1024x1_2816": ["COFLUX_TILE_NT64=1024", "COFLUX_TILE_CELLS64=2816", "COFLUX_TILE_MIN_BLOCKS64=1"],
-    "f32_384x3_1536": ["COFLUX_TILE_NT32=384", "COFLUX_TILE_CELLS32=1536", "COFLUX_TILE_MIN_BLOCKS32=3"],
-    "f32_512x3_1536": ["COFLUX_TILE_NT32=512", "COFLUX_TILE_CELLS32=1536", "COFLUX_TILE_MIN_BLOCKS32=3"],
+    "ice_coare": ["COFLUX_ICE_COARE=1"],
 }
 
 
