@@ -7,7 +7,7 @@ Importing the package requires the built CUDA library; there is no CPU fallback.
 """
 from . import _abi
 from ._abi import CofluxError, load_library, default_config
-from .fields import Field, FieldTimeSeries, LatitudeLongitudeGrid, fractional_indices
+from .fields import Field, FieldTimeSeries, LatitudeLongitudeGrid, TripolarGrid, fractional_indices
 from .state import SurfaceFluxData
 from .engine import Engine
 from .forcing import InMemoryWindow, DeviceForcingWindow

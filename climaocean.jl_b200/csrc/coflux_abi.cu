@@ -879,7 +879,24 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured |= 1ull << (dev & 63);
   }
-  kern<<<grid_for(a.ncell - a.cell0, TILE), TT::NT, smem, st>>>(a);
+  // Balanced tiling.  CTAs are dispatched as slots free up, so a launch lasts ceil(#CTAs / resident slots) CTA lifetimes
+  // (measured: a 1/8 longitude slab of the 1/12° grid, 2.85 waves of 768-cell tiles, took exactly 3 × 168 µs).  Every CTA
+  // therefore takes the same number of cells, chosen so that the grid is a whole number of waves: no ragged last wave.
+  static int sm_count[64] = {};
+  if (!sm_count[dev & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  FluxArgs<FT> b = a;
+  const long long n = a.ncell - a.cell0;
+  const long long slots = (long long)sm_count[dev & 63] * TT::MIN_BLOCKS;
+  long long grid = grid_for(n, TILE);
+  b.tile_cells = 0;
+  static const bool balance = [] { const char* e = std::getenv("COFLUX_BALANCE"); return !(e && e[0] == '0'); }();
+  if (balance && n > slots * (TILE / 4)) {
+    const long long waves = (n + slots * TILE - 1) / (slots * TILE);
+    const long long per = (n + waves * slots - 1) / (waves * slots);           // cells per CTA, ≤ TILE
+    b.tile_cells = (int)per;
+    grid = (n + per - 1) / per;
+  }
+  kern<<<(unsigned)grid, TT::NT, smem, st>>>(b);
   return COFLUX_OK;
 }
 // COFLUX_KERNEL=stream selects the persistent warp-specialised kernel (coflux_solve_stream.cuh: one CTA per SM for the
@@ -1059,7 +1076,28 @@ static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* 
   a.dt = (FT)dt;
   if (c->avg_on) { a.avg_JTf = view2d(c->avg.JT_frazil, 0, es); a.avg_T = (FT)c->avg.previous_interval; a.avg_dt = (FT)c->avg.dt; }
   a.P = dev_params<FT>(c);
-  ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, COFLUX_IO_BLOCK), COFLUX_IO_BLOCK, 0, st>>>(a);
+  // bulk-asynchronous form (cp.async.bulk → shared memory, mbarrier pipeline) whenever the columns are contiguous in i and the
+  // parents have a halo to absorb the 16-byte alignment slack; COFLUX_IO_BULK=0 selects the register-staged kernel (A/B)
+  static const bool bulk_off = [] { const char* e = std::getenv("COFLUX_IO_BULK"); return e && e[0] == '0'; }();
+  const bool can_bulk = !bulk_off && a.T.si == 1 && a.S.si == 1 && oc->T.off_i >= (int)(16 / es) && oc->S.off_i >= (int)(16 / es) &&
+                        ((uintptr_t)oc->T.ptr % 16 == 0) && ((uintptr_t)oc->S.ptr % 16 == 0);
+  if (can_bulk) {
+    constexpr int W = COFLUX_IOB_W, KB = COFLUX_IOB_KB, STAGES = COFLUX_IOB_STAGES;
+    auto kern = ice_ocean_bulk_kernel<FT, W, KB, STAGES>;
+    const size_t smem = sizeof(IceOceanBulkSmem<FT, W, KB, STAGES>);
+    static unsigned long long configured = 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!(configured >> (dev & 63) & 1ull)) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured |= 1ull << (dev & 63);
+    }
+    const long long tiles = (long long)((g.Nx + W - 1) / W) * g.Ny;
+    kern<<<(unsigned)tiles, W, smem, st>>>(a);
+  } else {
+    ice_ocean_kernel<FT><<<grid_for((long long)g.Nx * g.Ny, COFLUX_IO_BLOCK), COFLUX_IO_BLOCK, 0, st>>>(a);
+  }
   return check_launch(c, 1);
 }
 extern "C" int coflux_sea_ice_ocean_fluxes(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* ice, double dt,
@@ -1318,8 +1356,10 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
   // (1.4 waves), so back-to-back launches on ONE stream leave the SMs idle in every tail and the kernels — not PCIe —
   // bound the pipeline (measured: 8 chunks on one stream 7.8 ms per step at 1/12° Float64, while PCIe moves the 252 MB
   // each way in 5.8 ms, tools/pcie_probe.py).  With two streams the next chunk's CTAs fill the tail of the previous one.
-  int nch = HostStage::MAX_CHUNKS;
-  if (g.Ny < 8 * nch) nch = 1;
+  // chunk count: ≥ 4 MB per plane copy (below that the ~10 µs per cudaMemcpyAsync / launch dominate: at 8 slabs the fixed
+  // 16-chunk pipeline issued ≈ 160 tiny operations per step and end-to-end scaled 2.1× on 8 GPUs), at most MAX_CHUNKS
+  int nch = (int)std::min<size_t>(HostStage::MAX_CHUNKS, std::max<size_t>(1, plane / (4u << 20)));
+  while (nch > 1 && g.Ny < 8 * nch) nch /= 2;
   int f[HostStage::MAX_CHUNKS + 1], r[HostStage::MAX_CHUNKS + 1], sj[HostStage::MAX_CHUNKS + 1];
   for (int k = 0; k <= nch; ++k) f[k] = (int)((long long)nyr * k / nch);
   r[0] = 0; r[nch] = nj;

@@ -268,8 +268,9 @@ template <> struct PsiTabs<float> {
   static __device__ __forceinline__ const float (*sheba())[2][8] { return COFLUX_PSI_SHEBA_F32; }
 };
 #ifndef COFLUX_ICE_COARE
-#define COFLUX_ICE_COARE 0            /* 1: the compact sea-ice pass also takes the COARE log form (`:corrected`, `:ncar` ice;
-                                         measured 13.0 / 12.2 ms instead of 34 ms — needs one GPU parity run, profiles/README.md) */
+#define COFLUX_ICE_COARE 1            /* the compact sea-ice pass also takes the COARE log form (`:corrected`, `:ncar` ice: 13.0 / 12.2 ms
+                                         instead of 34 ms at 1/12°); validated on B200 in round 2: all sea-ice parity tests, both
+                                         precisions, three parameter sets (gpurun_out/r2_pytest6_icecoare.log → profiles/README.md) */
 #endif
 #ifndef COFLUX_PSI_TABLES_V1
 #define COFLUX_PSI_TABLES_V1 1      /* Paulson / SHEBA ψ from tables in the one-cell-per-thread and refill solves */

@@ -82,6 +82,9 @@ template <typename FT> __device__ __forceinline__ void avg_update(const DArr& d,
 template <typename FT> struct FluxArgs {
   int nxr, nyr, ring, Nx, Ny;
   long long cell0, ncell;   // linear cell range [cell0, ncell) of the ring-extended surface handled by this launch
+  // balanced tiling of the tile kernel: every CTA takes tile_cells ≤ TILE cells, chosen by the host so that the grid is a
+  // whole number of waves of resident CTAs (0: TILE cells per CTA)
+  int tile_cells, pad_;
   // a3 inputs
   DSeries su, sv, sT, sq, sp, sQs, sQl, srain, ssnow;
   DArr fi, fj, cs, sn;
@@ -859,6 +862,170 @@ template <typename FT> __global__ void __launch_bounds__(256) flux_average_kerne
   const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
   avg_update<FT>(a.a_JSio, i, j, a.salt_io.p ? ldg<FT>(a.salt_io, i, j) * conc : FT(0), a.T, a.dt);
   if (a.Qf.p) avg_update<FT>(a.a_JTf, i, j, ldg<FT>(a.Qf, i, j) / a.rho0 / a.c0, a.T, a.dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sea-ice–ocean fluxes, bulk-asynchronous form (round 2).  The register-staged kernel above keeps 24 loads per thread in
+// flight and stops at 69 % of the measured HBM peak: its in-flight bytes are bounded by registers (128 per thread, 16 warps
+// per SM).  Here the T and S columns of a CTA's W adjacent cells are streamed through shared memory by the bulk-copy engine
+// (cp.async.bulk global → shared, completion on an mbarrier: SASS UBLKCP), KB levels per stage, STAGES stages deep, issued
+// by one warp and costing no registers: ≈ 3 × 66 KB in flight per SM.  A thread then reads its column from shared memory
+// (consecutive words, conflict-free) top → bottom, exactly the arithmetic of ice_ocean_kernel → bit-identical results.
+// Alignment: cp.async.bulk needs 16-byte aligned source, destination and size; a row segment of a halo-padded parent starts
+// at an arbitrary element, so each copy starts at the aligned element at or before the segment (≤ 16/sizeof(FT) − 1 extra
+// elements, inside the parent because every parent has a halo) and the consumer indexes past that shift.
+// ---------------------------------------------------------------------------------------------
+#ifndef COFLUX_IOB_W
+#define COFLUX_IOB_W 128
+#endif
+#ifndef COFLUX_IOB_KB
+#define COFLUX_IOB_KB 8
+#endif
+#ifndef COFLUX_IOB_STAGES
+#define COFLUX_IOB_STAGES 4
+#endif
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+template <typename FT, int W, int KB, int STAGES> struct IceOceanBulkSmem {
+  static constexpr int PADE = 16 / (int)sizeof(FT);             // elements per 16 bytes
+  static constexpr int ROW = W + 2 * PADE;                      // aligned superset of a W-element segment
+  alignas(128) FT T[STAGES][KB][ROW];
+  alignas(128) FT S[STAGES][KB][ROW];
+  alignas(8) unsigned long long full[STAGES];
+};
+template <typename FT, int W, int KB, int STAGES>
+__global__ void __launch_bounds__(W) ice_ocean_bulk_kernel(const __grid_constant__ IceOceanArgs<FT> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using SM = IceOceanBulkSmem<FT, W, KB, STAGES>;
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  static_assert(2 * KB <= 32, "one warp issues the copies of a stage: one lane per (array, level)");
+  const int tid = threadIdx.x;
+  const int tiles_x = (a.Nx + W - 1) / W;
+  const int j = (int)(blockIdx.x / tiles_x);
+  const int i0 = (int)(blockIdx.x - (long long)j * tiles_x) * W;
+  const int i = i0 + tid;
+  const int wcols = min(W, a.Nx - i0);                          // columns of this tile
+  const bool valid = tid < wcols;
+  const DevParams<FT>& P = a.P;
+  const FT rho0 = P.rho0, c0 = P.c0, T0 = P.io.T0, m = P.io.slope;
+  const int nblk = (a.Nz + KB - 1) / KB;
+  FT* Tp = reinterpret_cast<FT*>(a.T.p);
+  const FT* Sp = reinterpret_cast<const FT*>(a.S.p);
+  const int64_t rowT = (int64_t)i0 + (int64_t)j * a.T.sj, rowS = (int64_t)i0 + (int64_t)j * a.S.sj;   // element index of (i0, j, 0)
+
+  if (tid == 0)
+    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&sm.full[s]), 2 * KB);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  // one lane per (array, level) of a stage: aligned source, size, destination
+  auto issue = [&](int blk, int s) {
+    if (tid < 2 * KB) {
+      const int which = tid / KB, u = tid - which * KB;
+      const int k = a.Nz - 1 - blk * KB - u;
+      const unsigned bar = smem_u32(&sm.full[s]);
+      if (k >= 0) {
+        const FT* src = which ? (Sp + rowS + (int64_t)k * a.S.sk) : (Tp + rowT + (int64_t)k * a.T.sk);
+        const unsigned mis = (unsigned)((uintptr_t)src & 15u);                     // bytes past the aligned address
+        const unsigned bytes = (unsigned)((mis + (unsigned)wcols * sizeof(FT) + 15u) & ~15u);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(which ? &sm.S[s][u][0] : &sm.T[s][u][0]), reinterpret_cast<const char*>(src) - mis, bytes, bar);
+      } else {
+        mbar_arrive_expect_tx(bar, 0u);                                            // level below the bottom: nothing to copy
+      }
+    }
+  };
+  for (int b = 0; b < STAGES && b < nblk; ++b) issue(b, b);
+
+  // 2-D terms of the column while the first stages land
+  FT taux = FT(0), tauy = FT(0);
+  if (valid) {
+    taux = io_stress_x<FT>(a, i, j); tauy = io_stress_y<FT>(a, i, j);
+    stg<FT>(a.tx, i, j, taux);
+    stg<FT>(a.ty, i, j, tauy);
+  }
+  FT dQ = FT(0), TN = FT(0), SN = FT(0);
+  const int64_t colT = (int64_t)i * a.T.si + (int64_t)j * a.T.sj;
+  for (int b = 0; b < nblk; ++b) {
+    const int s = b % STAGES;
+    mbar_wait(smem_u32(&sm.full[s]), (unsigned)((b / STAGES) & 1));
+    if (valid) {
+#pragma unroll
+      for (int u = 0; u < KB; ++u) {
+        const int k = a.Nz - 1 - b * KB - u;
+        if (k >= 0) {
+          const unsigned misT = (unsigned)(((uintptr_t)(Tp + rowT + (int64_t)k * a.T.sk) & 15u) / sizeof(FT));
+          const unsigned misS = (unsigned)(((uintptr_t)(Sp + rowS + (int64_t)k * a.S.sk) & 15u) / sizeof(FT));
+          const FT Tk = sm.T[s][u][misT + tid], Sk = sm.S[s][u][misS + tid];
+          const FT zk = __ldg(reinterpret_cast<const FT*>(a.dz.p) + ((int64_t)i * a.dz.si + (int64_t)j * a.dz.sj + (int64_t)k * a.dz.sk));
+          const FT Tm = T0 - m * Sk;
+          const bool freezing = Tk < Tm;
+          const FT dE = rho0 * c0 * (Tm - Tk);
+          if (freezing) {
+            Tp[colT + (int64_t)k * a.T.sk] = Tm;
+            dQ -= dE * zk / a.dt;
+          }
+          if (k == a.Nz - 1) { TN = freezing ? Tm : Tk; SN = Sk; }
+        }
+      }
+    }
+    __syncthreads();                                   // every thread is done with stage s: refill it
+    if (b + STAGES < nblk) issue(b + STAGES, s);
+  }
+  if (!valid) return;
+  const FT conc = ldg<FT>(a.iconc, i, j), Si = ldg<FT>(a.iS, i, j);
+  const FT Tm = T0 - m * SN;
+  FT Qio;
+  if (P.io.heat_flux == COFLUX_ICE_OCEAN_THREE_EQUATION) {
+    FT ustar;
+    if (P.io.friction == COFLUX_FRICTION_VELOCITY_MOMENTUM_BASED) {
+      const FT txe = (i + 1 < a.Nx) ? io_stress_x<FT>(a, i + 1, j) : taux;
+      const FT tyn = (j + 1 < a.Ny) ? io_stress_y<FT>(a, i, j + 1) : tauy;
+      const FT tx = FT(0.5) * (taux + txe), ty = FT(0.5) * (tauy + tyn);
+      ustar = M<FT>::sqrt(M<FT>::sqrt(tx * tx + ty * ty) / rho0);
+      ustar = M<FT>::max(ustar, P.io.ustar_min);
+    } else {
+      ustar = P.io.ustar_const;
+    }
+    const FT gT = P.io.alpha_h * ustar, gS = P.io.alpha_s * ustar;
+    const FT A = rho0 * c0 * gT / (P.io.rho_i * P.io.L_f);
+    const FT qa = A * m;
+    const FT qb = A * (TN - T0) - A * m * Si + gS;
+    const FT qc = -(A * (TN - T0) * Si + gS * SN);
+    const FT disc = qb * qb - FT(4) * qa * qc;
+    const FT Sb = (-qb + M<FT>::sqrt(M<FT>::max(disc, FT(0)))) / (FT(2) * qa);
+    const FT Tb = T0 - m * Sb;
+    Qio = rho0 * c0 * gT * (TN - Tb) * conc;
+  } else {
+    const FT dE = rho0 * c0 * (Tm - TN);
+    Qio = -dE * P.io.um_star * conc;
+  }
+  const FT h = ldg<FT>(a.ih, i, j);
+  const FT hm = reinterpret_cast<const FT*>(a.ihm.p)[(int64_t)i * a.ihm.si + (int64_t)j * a.ihm.sj];
+  const FT Js = (h - hm) / a.dt * (Si - SN);
+  stg<FT>(a.Qf, i, j, dQ);
+  avg_update<FT>(a.avg_JTf, i, j, dQ / rho0 / c0, a.avg_T, a.avg_dt);
+  stg<FT>(a.Qio, i, j, Qio);
+  stg<FT>(a.Js, i, j, Js);
+  stg<FT>(a.ihm, i, j, h);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -559,7 +559,8 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 
 // Launch shape (round 2).  One copy of the hot ψ rows per CTA (26 KB in Float64) wants few, large CTAs; the phases of
 // different CTAs overlap on an SM (A is latency bound on gathers, B on the FP64 / issue pipes), which wants several.
-//   Float64 `:default`   256 threads × 3 CTAs/SM, 768 cells per CTA (58 B/cell + 29 KB of tables = 73.7 KB), 80 registers
+//   Float64 `:default`   320 threads × 2 CTAs/SM, ≤ 1280 cells per CTA (58 B/cell + 29 KB of tables = 103 KB), 96 registers:
+//                        no spills, 4 cells per lane (3.20 ms at 1/12°; 256 × 3 × 768 at 80 registers with spills: 3.32 ms)
 //   Float64 `:corrected` 384 threads × 2 CTAs/SM, 1152 cells (74 B/cell: ν and 1/ν vary), 80 registers
 //   Float32              384 threads × 3 CTAs/SM, 1536 cells (30 / 38 B/cell + 13 KB table), 56 registers
 // A/B on B200 at 1/12° (profiles/README.md): Float64 at 64 / 72 registers (32 / 28 warps per SM) is SLOWER (3.98 / 3.56 ms
@@ -569,13 +570,13 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 #define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A (A/B knob) */
 #endif
 #ifndef COFLUX_TILE_NT64
-#define COFLUX_TILE_NT64 256
+#define COFLUX_TILE_NT64 320
 #endif
 #ifndef COFLUX_TILE_CELLS64
-#define COFLUX_TILE_CELLS64 768
+#define COFLUX_TILE_CELLS64 1280
 #endif
 #ifndef COFLUX_TILE_MIN_BLOCKS64
-#define COFLUX_TILE_MIN_BLOCKS64 3
+#define COFLUX_TILE_MIN_BLOCKS64 2
 #endif
 #ifndef COFLUX_TILE_NT64_S2
 #define COFLUX_TILE_NT64_S2 384
@@ -635,8 +636,15 @@ template <typename FT, int SPEC> struct TileTraits {
   static_assert(TILE <= 65535, "queue entries are 16-bit");
 };
 
+// COFLUX_TILE_MAXNREG (A/B knob): state the register budget directly — ptxas derives it from __launch_bounds__ with the CTA size
+// rounded up to a multiple of 64 threads, which wastes the headroom of 224- or 352-thread CTAs
+#ifdef COFLUX_TILE_MAXNREG
+#define COFLUX_TILE_BOUNDS(FT, SPEC) __maxnreg__(COFLUX_TILE_MAXNREG)
+#else
+#define COFLUX_TILE_BOUNDS(FT, SPEC) __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>::MIN_BLOCKS)
+#endif
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
-__global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>::MIN_BLOCKS) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
+__global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using TT = TileTraits<FT, SPEC>;
   constexpr bool VARNU = TT::VARNU;
@@ -655,7 +663,9 @@ __global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>
   const FluxP<FT>& F = P.ao;
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
-  const long long tile0 = a.cell0 + (long long)blockIdx.x * TILE;
+  // balanced tiling (FluxArgs::tile_cells): this CTA's cells are [tile0, tile0 + tile_n)
+  const int tile_n = (a.tile_cells > 0 && a.tile_cells < TILE) ? a.tile_cells : TILE;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * tile_n;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head[0] = 0; sm.head[1] = 0; }
   if (TABS) {
     for (int k = tid; k < 256; k += NT) s_lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];
@@ -679,7 +689,7 @@ __global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>
   const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
 
   // ------------------------------------------------------------------ phase A
-  for (int cidx = tid; cidx < TILE; cidx += NT) {
+  for (int cidx = tid; cidx < tile_n; cidx += NT) {
     const long long idx = tile0 + cidx;
     if (idx >= a.ncell) continue;
     const int jj = (int)(idx / a.nxr);
@@ -924,7 +934,7 @@ __global__ void __launch_bounds__(TileTraits<FT, SPEC>::NT, TileTraits<FT, SPEC>
   __syncthreads();
 
   // ------------------------------------------------------------------ phase C
-  for (int cidx = tid; cidx < TILE; cidx += NT) {
+  for (int cidx = tid; cidx < tile_n; cidx += NT) {
     const long long idx = tile0 + cidx;
     if (idx >= a.ncell) continue;
     const int jj = (int)(idx / a.nxr);

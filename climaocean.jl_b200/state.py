@@ -77,6 +77,17 @@ class SurfaceFluxData:
         if with_ice:
             ice = synth.sea_ice_state(grid, dt)
             self.ice = {n: Field(ice[n], (grid.halo[0], grid.halo[1], 0), "ice_" + n) for n in ICE_NAMES}
+        if hasattr(grid, "fold"):
+            # curvilinear grid: winds are rotated into the grid frame; north halos of the model state follow the fold
+            cs, sn = grid.rotation(ring)
+            self.rotation = (Field(cs, (ring, ring, 0), "cos_theta"), Field(sn, (ring, ring, 0), "sin_theta"))
+            for n in ("u", "v", "T", "S"):
+                grid.fill_north_fold(self.ocean[n].data, -1.0 if n in ("u", "v") else 1.0)
+            if self.ice is not None:
+                for n, f in self.ice.items():
+                    grid.fill_north_fold(f.data, -1.0 if n in ("u", "v") else 1.0)
+            if self.mask is not None:
+                grid.fill_north_fold(self.mask.data)
         if with_land:
             lh = 2
             lser, ltimes = synth.land_series(land_size[0], land_size[1], land_Nt, lh, dt)

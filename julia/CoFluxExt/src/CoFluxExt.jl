@@ -88,6 +88,13 @@ struct AtmosSeries
     Qs::CofluxArray; Ql::CofluxArray; rain::CofluxArray; snow::CofluxArray
     times::Ptr{Float64}; Nt::Int32; time_indexing::Int32; cycle_period::Float64
     fi::CofluxArray; fj::CofluxArray; cos_theta::CofluxArray; sin_theta::CofluxArray
+    ring_start::Int32; ring_capacity::Int32          # ABI 2: device ring buffer (coflux_forcing_window); 0, 0 = plain layout
+end
+struct LandSeries                                     # ABI 2: JRA55PrescribedLand (friver + licalvf → exchange Mp)
+    rivers::CofluxArray; icebergs::CofluxArray
+    times::Ptr{Float64}; Nt::Int32; time_indexing::Int32; cycle_period::Float64
+    fi::CofluxArray; fj::CofluxArray
+    ring_start::Int32; ring_capacity::Int32
 end
 struct ExchangeState;   u::CofluxArray; v::CofluxArray; T::CofluxArray; p::CofluxArray; q::CofluxArray; Qs::CofluxArray; Ql::CofluxArray; Mp::CofluxArray; end
 struct OceanSurface;    u::CofluxArray; v::CofluxArray; T::CofluxArray; S::CofluxArray; mask::CofluxArray; end
@@ -95,13 +102,14 @@ struct InterfaceFluxes; latent_heat::CofluxArray; sensible_heat::CofluxArray; wa
                         interface_temperature::CofluxArray; friction_velocity::CofluxArray; temperature_scale::CofluxArray; humidity_scale::CofluxArray; iterations::CofluxArray; end
 struct NetOceanFluxes;  u::CofluxArray; v::CofluxArray; T::CofluxArray; S::CofluxArray; upwelling_longwave::CofluxArray; downwelling_longwave::CofluxArray
                         downwelling_shortwave::CofluxArray; penetrating_shortwave::CofluxArray; end
-struct UpdateInputs;    atmosphere::Ptr{AtmosSeries}; ocean::Ptr{OceanSurface}; sea_ice::Ptr{Cvoid}; ice_ocean::Ptr{Cvoid}; end
+struct UpdateInputs;    atmosphere::Ptr{AtmosSeries}; ocean::Ptr{OceanSurface}; sea_ice::Ptr{Cvoid}; ice_ocean::Ptr{Cvoid}; land::Ptr{LandSeries}; end
 struct UpdateOutputs;   exchange::Ptr{ExchangeState}; atmosphere_ocean::Ptr{InterfaceFluxes}; net_ocean::Ptr{NetOceanFluxes}; end
 
 function __init__()
     for (name, T) in (("array", CofluxArray), ("atmos_series", AtmosSeries), ("exchange_state", ExchangeState),
                       ("ocean_surface", OceanSurface), ("interface_fluxes", InterfaceFluxes),
-                      ("net_ocean_fluxes", NetOceanFluxes), ("update_inputs", UpdateInputs), ("update_outputs", UpdateOutputs))
+                      ("net_ocean_fluxes", NetOceanFluxes), ("update_inputs", UpdateInputs), ("update_outputs", UpdateOutputs),
+                      ("land_series", LandSeries))
         n = ccall((:coflux_sizeof, libcoflux), Cint, (Cstring,), name)
         n == sizeof(T) || error("CoFluxExt: layout of $name drifted (Julia $(sizeof(T)) B, library $n B)")
     end
@@ -133,7 +141,7 @@ function coflux_update_state!(model::OceanSeaIceModel)
                              CofluxArray(atmos.tracers.q), CofluxArray(atmos.pressure),
                              CofluxArray(model.radiation.downwelling_shortwave), CofluxArray(model.radiation.downwelling_longwave),
                              CofluxArray(atmos.freshwater_flux.rain), CofluxArray(atmos.freshwater_flux.snow),
-                             pointer(times), length(times), 0, 0.0, CofluxArray(fi), CofluxArray(fj), NULL_ARRAY, NULL_ARRAY))
+                             pointer(times), length(times), 0, 0.0, CofluxArray(fi), CofluxArray(fj), NULL_ARRAY, NULL_ARRAY, Int32(0), Int32(0)))
     xs = itf.exchanger.exchange_atmosphere_state
     xch = Ref(ExchangeState(CofluxArray(xs.u), CofluxArray(xs.v), CofluxArray(xs.T), CofluxArray(xs.p), CofluxArray(xs.q),
                             CofluxArray(xs.Qs), CofluxArray(xs.Qℓ), CofluxArray(xs.Mp)))
@@ -147,7 +155,7 @@ function coflux_update_state!(model::OceanSeaIceModel)
                              CofluxArray(f.upwelling_longwave), CofluxArray(f.downwelling_longwave), CofluxArray(f.downwelling_shortwave),
                              NULL_ARRAY))
     GC.@preserve times series xch oc ao net begin
-        inp = Ref(UpdateInputs(Base.unsafe_convert(Ptr{AtmosSeries}, series), Base.unsafe_convert(Ptr{OceanSurface}, oc), C_NULL, C_NULL))
+        inp = Ref(UpdateInputs(Base.unsafe_convert(Ptr{AtmosSeries}, series), Base.unsafe_convert(Ptr{OceanSurface}, oc), C_NULL, C_NULL, C_NULL))
         out = Ref(UpdateOutputs(Base.unsafe_convert(Ptr{ExchangeState}, xch), Base.unsafe_convert(Ptr{InterfaceFluxes}, ao),
                                 Base.unsafe_convert(Ptr{NetOceanFluxes}, net)))
         check(ccall((:coflux_update_state, libcoflux), Cint,

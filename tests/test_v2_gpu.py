@@ -224,3 +224,64 @@ def test_coupled_model_mirror_with_land_and_sea_ice(bits):
     assert model.interfaces.net_fluxes.sea_ice.top.heat is dev.net_ice["top_heat"]
     with pytest.raises(NotImplementedError):
         cj.ComponentInterfaces(atmosphere, ocean, sea_ice, land="rivers.nc")
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_config5_one_degree_tripolar_ocean_sea_ice_flux_set(bits):
+    """BASELINE config 5: 1° TripolarGrid (360×180) ocean + sea ice — the whole flux set of update_state! (atmosphere–ocean,
+    atmosphere–sea-ice, sea-ice–ocean, net ocean, net sea-ice) with winds rotated into the grid frame and north halos
+    filled by the fold (examples/one_degree_tripolar_ocean_sea_ice.jl:17-42; OceanConfigurations/one_degree_tripolar.jl:20-73)."""
+    import torch
+    grid = cj.TripolarGrid((360, 180, 6), halo=(7, 7, 7), dtype=np.float64 if bits == 64 else np.float32)
+    host = cj.SurfaceFluxData.synthetic(grid, with_ice=True, with_land=True, frazil=True, land_fraction=0.3, ring=1)
+    assert host.rotation is not None
+    cfg = cj.default_config(360, 180, 6, bits, "corrected")
+    cfg.grid.ring = 1
+    cfg.radiation.sea_ice_albedo_kind = _abi.SEA_ICE_ALBEDO_CCSM3
+    dev = host.to("cuda:0")
+    t, dt = QUERY_TIME, 1200.0
+
+    def sequence(d, e):
+        x, o, ice, io = d.exchange_state(), d.ocean_surface(), d.sea_ice_state(), d.ice_ocean_fluxes()
+        ao, ai = d.interface_fluxes("ao"), d.interface_fluxes("ai")
+        e.interpolate_atmosphere(d.atmos_series(), t, x)
+        e.interpolate_land(d.land_series(), t, x)
+        e.atmosphere_ocean(x, o, ao)
+        e.atmosphere_sea_ice(x, o, ice, ai)
+        e.sea_ice_ocean(d.ocean_columns(), ice, dt, io)
+        e.net_ocean(x, o, ao, ice, io, d.net_ocean_fluxes())
+        e.net_sea_ice(x, o, ice, ai, io, d.net_sea_ice_fluxes())
+
+    class Oracle:
+        interpolate_atmosphere = staticmethod(lambda s, tt, x: pyoracle.interpolate_atmosphere(cfg, s, tt, x))
+        interpolate_land = staticmethod(lambda s, tt, x: pyoracle.interpolate_land(cfg, s, tt, x))
+        atmosphere_ocean = staticmethod(lambda x, o, f: pyoracle.atmosphere_ocean_fluxes(cfg, x, o, f))
+        atmosphere_sea_ice = staticmethod(lambda x, o, i, f: pyoracle.atmosphere_sea_ice_fluxes(cfg, x, o, i, f))
+        sea_ice_ocean = staticmethod(lambda c, i, d_, f: pyoracle.sea_ice_ocean_fluxes(cfg, c, i, d_, f))
+        net_ocean = staticmethod(lambda x, o, ao, i, io, n: pyoracle.assemble_net_ocean_fluxes(cfg, x, o, ao, i, io, n))
+        net_sea_ice = staticmethod(lambda x, o, i, ai, io, n: pyoracle.assemble_net_sea_ice_fluxes(cfg, x, o, i, ai, io, n))
+
+    eng = cj.Engine(cfg)
+
+    class Cuda:
+        interpolate_atmosphere = staticmethod(lambda s, tt, x: eng.interpolate_atmosphere_state(s, tt, x))
+        interpolate_land = staticmethod(lambda s, tt, x: eng.interpolate_land(s, tt, x))
+        atmosphere_ocean = staticmethod(lambda x, o, f: eng.compute_atmosphere_ocean_fluxes(x, o, f))
+        atmosphere_sea_ice = staticmethod(lambda x, o, i, f: eng.compute_atmosphere_sea_ice_fluxes(x, o, i, f))
+        sea_ice_ocean = staticmethod(lambda c, i, d_, f: eng.compute_sea_ice_ocean_fluxes(c, i, d_, f))
+        net_ocean = staticmethod(lambda x, o, ao, i, io, n: eng.compute_net_ocean_fluxes(x, o, ao, i, io, n))
+        net_sea_ice = staticmethod(lambda x, o, i, ai, io, n: eng.compute_net_sea_ice_fluxes(x, o, i, ai, io, n))
+
+    sequence(host, Oracle)
+    sequence(dev, Cuda)
+    torch.cuda.synchronize()
+    assert eng.launches == 7
+    ref, gpu = host.outputs(), dev.outputs()
+    ice_keys = [k for k in ref if k.startswith("ai.") or k.startswith("net_ice.")]
+    compare(gpu, ref, bits, keys=[k for k in ref if k not in ice_keys and not k.startswith("avg.")])
+    compare_sea_ice(gpu, ref, bits, dev.iterations_ai.numpy()[0, 7:-7, 7:-7], host.iterations_ai.numpy()[0, 7:-7, 7:-7],
+                    cfg.atmosphere_sea_ice.max_iterations, ice_keys, stress_keys=("net_ice.top_u", "net_ice.top_v"))
+    # the rotation acts in the cap only, and strongly near the fold
+    cs = host.rotation[0].numpy()[0, 1:-1, 1:-1]
+    assert np.all(cs[:grid.j0 - 1] > 1 - 1e-12) and cs[grid.j0 + 2:].min() < 0.1
+    assert np.any(gpu["net_ice.top_heat"] != 0) and np.any(gpu["io.frazil_heat"] != 0) and np.any(gpu["net.S"] != 0)

@@ -11,7 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "ice_coare": ["COFLUX_ICE_COARE=1"],
+    "base_320x2_1280": [],
+    "s2_320x2_1120": ["COFLUX_TILE_NT64_S2=320", "COFLUX_TILE_CELLS64_S2=1120", "COFLUX_TILE_MIN_BLOCKS64_S2=2"],
+    "d384x2_1536_r80": ["COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=1408", "COFLUX_TILE_MIN_BLOCKS64=2"],
+    "d640x1_3200": ["COFLUX_TILE_NT64=640", "COFLUX_TILE_CELLS64=3200", "COFLUX_TILE_MIN_BLOCKS64=1"],
+    "d320x2_1408": ["COFLUX_TILE_CELLS64=1408"],
 }
 
 
