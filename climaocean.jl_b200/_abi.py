@@ -26,6 +26,7 @@ PROFILE_LOGARITHMIC, PROFILE_COARE_LOGARITHMIC = 0, 1
 VELOCITY_RELATIVE, VELOCITY_WIND = 0, 1
 STOP_CONVERGENCE, STOP_FIXED_ITERATIONS = 0, 1
 TEMPERATURE_BULK, TEMPERATURE_SKIN = 0, 1
+SKIN_CLAMPED_EXPLICIT, SKIN_LINEARIZED_LONGWAVE = 0, 1
 TEMPERATURE_CELSIUS, TEMPERATURE_KELVIN = 0, 1
 ICE_OCEAN_ICE_BATH, ICE_OCEAN_THREE_EQUATION = 0, 1
 FRICTION_VELOCITY_CONSTANT, FRICTION_VELOCITY_MOMENTUM_BASED = 0, 1
@@ -60,7 +61,7 @@ class ScalarRoughness(C.Structure):
 class FluxParams(C.Structure):
     _fields_ = [("formulation", i32), ("stability_functions", i32), ("similarity_form", i32),
                 ("velocity_formulation", i32), ("stop_kind", i32), ("max_iterations", i32),
-                ("interface_temperature", i32), ("reserved", i32),
+                ("interface_temperature", i32), ("skin_temperature_update", i32),
                 ("tolerance", f64), ("von_karman_constant", f64), ("turbulent_prandtl_number", f64),
                 ("gustiness_parameter", f64), ("minimum_gustiness", f64), ("initial_scale", f64),
                 ("ly_minimum_wind", f64), ("skin_max_delta_T", f64),

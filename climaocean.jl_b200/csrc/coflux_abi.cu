@@ -328,6 +328,8 @@ static int validate_flux(const coflux_flux_params& f, const char* who) {
     return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown solver stop criteria %d", who, f.stop_kind);
   if (f.interface_temperature < 0 || f.interface_temperature > COFLUX_TEMPERATURE_SKIN)
     return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown interface temperature formulation %d", who, f.interface_temperature);
+  if (f.skin_temperature_update != COFLUX_SKIN_CLAMPED_EXPLICIT && f.skin_temperature_update != COFLUX_SKIN_LINEARIZED_LONGWAVE)
+    return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: unknown skin temperature update %d", who, f.skin_temperature_update);
   if (f.max_iterations < 0 || f.max_iterations > 100000)
     return fail(COFLUX_ERR_INVALID_ARGUMENT, "%s: max_iterations out of range (%d)", who, f.max_iterations);
   const double vals[8] = {f.tolerance, f.von_karman_constant, f.turbulent_prandtl_number, f.gustiness_parameter,
@@ -451,7 +453,7 @@ template <typename FT> static FluxP<FT> to_dev(const coflux_flux_params& f) {
                    t.reynolds_b == q.reynolds_b && t.maximum_length == q.maximum_length && same_viscosity(t.viscosity, q.viscosity))
                       ? 1 : 0;
   d.same_visc = (same_viscosity(m.viscosity, t.viscosity) && same_viscosity(m.viscosity, q.viscosity)) ? 1 : 0;
-  d.pad_ = 0;
+  d.skin_update = f.skin_temperature_update;
   return d;
 }
 template <typename FT> static DevParams<FT> make_dev_params(const coflux_config& c) {
@@ -1076,10 +1078,12 @@ static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* 
   a.dt = (FT)dt;
   if (c->avg_on) { a.avg_JTf = view2d(c->avg.JT_frazil, 0, es); a.avg_T = (FT)c->avg.previous_interval; a.avg_dt = (FT)c->avg.dt; }
   a.P = dev_params<FT>(c);
-  // bulk-asynchronous form (cp.async.bulk → shared memory, mbarrier pipeline) whenever the columns are contiguous in i and the
-  // parents have a halo to absorb the 16-byte alignment slack; COFLUX_IO_BULK=0 selects the register-staged kernel (A/B)
-  static const bool bulk_off = [] { const char* e = std::getenv("COFLUX_IO_BULK"); return e && e[0] == '0'; }();
-  const bool can_bulk = !bulk_off && a.T.si == 1 && a.S.si == 1 && oc->T.off_i >= (int)(16 / es) && oc->S.off_i >= (int)(16 / es) &&
+  // COFLUX_IO_BULK=1 selects the bulk-asynchronous form (cp.async.bulk → shared memory, mbarrier pipeline; needs columns
+  // contiguous in i and a halo to absorb the 16-byte alignment slack).  Measured on B200 at 1/12°, Nz = 75 (round 2,
+  // profiles/README.md): bit-identical results but 2.61 ms (59 % of the HBM peak) against 2.26 ms (69 %) for the
+  // register-staged kernel — 1 KB row segments are too small for the copy engine — so the register-staged kernel stays.
+  static const bool bulk_on = [] { const char* e = std::getenv("COFLUX_IO_BULK"); return e && e[0] == '1'; }();
+  const bool can_bulk = bulk_on && a.T.si == 1 && a.S.si == 1 && oc->T.off_i >= (int)(16 / es) && oc->S.off_i >= (int)(16 / es) &&
                         ((uintptr_t)oc->T.ptr % 16 == 0) && ((uintptr_t)oc->S.ptr % 16 == 0);
   if (can_bulk) {
     constexpr int W = COFLUX_IOB_W, KB = COFLUX_IOB_KB, STAGES = COFLUX_IOB_STAGES;

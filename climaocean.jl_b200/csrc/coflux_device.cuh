@@ -123,7 +123,7 @@ template <typename FT> struct MomRough {
 };
 template <typename FT> struct ScaRough { int kind; FT fixed, A, b, lmax; Visc<FT> visc; };
 template <typename FT> struct FluxP {
-  int formulation, stability, form, velocity, stop_kind, maxit, itemp, same_scalar, same_visc, pad_;
+  int formulation, stability, form, velocity, stop_kind, maxit, itemp, same_scalar, same_visc, skin_update;
   FT tol, kappa, beta, ugmin, init, ly_umin, skin_max_dT;
   MomRough<FT> mr;
   ScaRough<FT> tr, qr;
@@ -558,6 +558,10 @@ template <typename FT, int SURF> struct CellSolver {
     FT Qv = -atm.rho * Ls * u0 * q0;
     FT Qa = Qv + Qu + Qc + Qd;
     FT Tstar = Tb - Qa * in.h_ice / P.io.k_ice;
+    if (F.skin_update == COFLUX_SKIN_LINEARIZED_LONGWAVE) {     // emitted long wave implicit: Q_u ≈ σ ε T_s⁻³ · T_s⁺
+      const FT alpha = P.sigma * P.emis_i * Ts * Ts * Ts / P.io.k_ice;
+      Tstar = (Tb - (Qd + Qc + Qv) * in.h_ice / P.io.k_ice) / (FT(1) + alpha * in.h_ice);
+    }
     if (Tstar != Tstar) Tstar = Ts;
     Tstar = M<FT>::max(FT(0), Tstar);
     FT Tnew = (in.h_ice >= P.io.h_c) ? Tstar : Tb;

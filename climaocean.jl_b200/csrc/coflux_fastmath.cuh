@@ -181,9 +181,36 @@ COFLUX_FM float rcp(float x) {
 }
 COFLUX_FM float div(float a, float b) { return a / b; }
 COFLUX_FM float sqrt(float x) { return ::sqrtf(x); }
-COFLUX_FM float cbrt(float x) { return ::cbrtf(x); }
-COFLUX_FM float log(float x, const double*) { return ::logf(x); }
-COFLUX_FM float exp(float x, const double*) { return ::expf(x); }
+// COFLUX_F32_FAST (A/B knob, default off): SFU forms of the three transcendental functions of the Float32 pass —
+// lg2.approx / ex2.approx (MUFU.LG2 / MUFU.EX2) with one Newton step for the cube root — instead of the CUDA library's
+// logf / expf / cbrtf (20–30 instructions each).  Accuracy: ≈ 2⁻²¹ absolute in log₂, i.e. ≤ 3e-7 relative in ln(h/ℓ) ≈ 10.
+#ifndef COFLUX_F32_FAST
+#define COFLUX_F32_FAST 0
+#endif
+COFLUX_FM float cbrt(float x) {
+#if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
+  float lg; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(lg * 0.333333343f));
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y * y));
+  return ::fmaf(-(::fmaf(y * y, y, -x)) * 0.333333343f, r, y);      // one Newton step: relative error ≈ 2⁻⁴⁰ → rounding
+#else
+  return ::cbrtf(x);
+#endif
+}
+COFLUX_FM float log(float x, const double*) {
+#if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
+  return __logf(x);
+#else
+  return ::logf(x);
+#endif
+}
+COFLUX_FM float exp(float x, const double*) {
+#if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
+  return __expf(x);
+#else
+  return ::expf(x);
+#endif
+}
 
 }  // namespace fm
 }  // namespace coflux

@@ -133,6 +133,19 @@ typedef enum { COFLUX_PROFILE_LOGARITHMIC = 0,       /* ln(h/ℓ) − ψ(h/L) + 
 typedef enum { COFLUX_VELOCITY_RELATIVE = 0, COFLUX_VELOCITY_WIND = 1 } coflux_velocity_formulation;
 typedef enum { COFLUX_STOP_CONVERGENCE = 0, COFLUX_STOP_FIXED_ITERATIONS = 1 } coflux_stop_kind;
 typedef enum { COFLUX_TEMPERATURE_BULK = 0, COFLUX_TEMPERATURE_SKIN = 1 } coflux_interface_temperature;
+/* How the SKIN temperature is advanced inside the similarity iteration (row a7).  With Q_a = Q_d + Q_u(T_s) + Q_c + Q_v the
+ * conductive balance through the slab is  T★ = T_b − Q_a h / k.
+ *   CLAMPED_EXPLICIT      T_s ← min(T_s + clamp(T★(T_s⁻) − T_s⁻, ±ΔT_max), T_melt): every flux at the previous iterate — the form the
+ *                         reference's SkinTemperature runs.  Its slope (h/k)·∂Q_a/∂T_s exceeds one for h ≳ 0.1 m: not a
+ *                         contraction; one ice cell in nine ends on a limit cycle at maxiter (tests/test_a7_conditioning.py).
+ *   LINEARIZED_LONGWAVE   the emitted long wave is taken implicitly, Q_u ≈ σ ε T_s⁻³ · T_s⁺:
+ *                         T★ = (T_b − (Q_d + Q_c + Q_v) h / k) / (1 + σ ε T_s⁻³ h / k), then the same clamp and melting cap.
+ *                         (The alternative upstream keeps commented out next to the explicit form.)  Removes the radiative
+ *                         part (4σεT³ ≈ 5 W m⁻² K⁻¹) of the slope.  Measured (tests/test_a7_conditioning.py): same fixed points,
+ *                         but the limit cycles barely recede (940 → 937 of 10 571 ice cells) — they are driven by the
+ *                         turbulent fluxes' own dependence on T_s through Δθ and Δq (ρ c_p C_h U ≈ 15 W m⁻² K⁻¹ and the
+ *                         latent analogue), which both forms lag.  Offered as a parameter; NOT the reference default.           */
+typedef enum { COFLUX_SKIN_CLAMPED_EXPLICIT = 0, COFLUX_SKIN_LINEARIZED_LONGWAVE = 1 } coflux_skin_temperature_update;
 
 typedef struct coflux_flux_params {
   int32_t formulation;              /* coflux_flux_formulation                                       */
@@ -142,7 +155,7 @@ typedef struct coflux_flux_params {
   int32_t stop_kind;                /* coflux_stop_kind                                              */
   int32_t max_iterations;           /* maxiter (CONVERGENCE) or n (FixedIterations(n))               */
   int32_t interface_temperature;    /* BULK (ocean) | SKIN (sea ice, row a7)                         */
-  int32_t reserved;
+  int32_t skin_temperature_update;  /* coflux_skin_temperature_update (SKIN only)                    */
   double  tolerance;                /* Σ|Δ(u★,θ★,q★)| < tolerance                                   */
   double  von_karman_constant;
   double  turbulent_prandtl_number; /* must be 1 (kept for struct parity)                            */

@@ -338,6 +338,11 @@ static FT SUF(skin_temperature)(const coflux_flux_params* P, const coflux_ice_oc
   FT Qv = -rho_a * Ls * ustar * qstar;
   FT Qa = Qv + Qu + Qc + Qd;
   FT Tstar = Tb - Qa * h_ice / k;
+  if (P->skin_temperature_update == COFLUX_SKIN_LINEARIZED_LONGWAVE) {
+    /* emitted long wave implicit: Q_u ≈ σ ε T_s⁻³ · T_s⁺ (include/coflux.h: coflux_skin_temperature_update) */
+    FT alpha = sigma * emis * Ts_prev * Ts_prev * Ts_prev / k;
+    Tstar = (Tb - (Qd + Qc + Qv) * h_ice / k) / ((FT)1 + alpha * h_ice);
+  }
   if (Tstar != Tstar) Tstar = Ts_prev;
   Tstar = FMAX((FT)0, Tstar);
   FT Tnew = (h_ice >= hc) ? Tstar : Tb;

@@ -210,7 +210,12 @@ def solve_cell(cfg, P, cell, surface_kind):
             emis, sigma = F(R.sea_ice_emissivity), F(R.stefan_boltzmann_constant)
             Qa = (-atm["rho"] * Ls * us * qs) + emis * sigma * Ts ** 4 + (-atm["rho"] * atm["cp"] * us * ts) + \
                  (-(1 - v["albedo"]) * v["Qs"] - emis * v["Ql"])
-            Tstar = max(F(0), Tb - Qa * v["h_ice"] / F(I.ice_conductivity))
+            k_ice = F(I.ice_conductivity)
+            Tstar = Tb - Qa * v["h_ice"] / k_ice
+            if P.skin_temperature_update == _abi.SKIN_LINEARIZED_LONGWAVE:
+                Qrest = Qa - emis * sigma * Ts ** 4
+                Tstar = (Tb - Qrest * v["h_ice"] / k_ice) / (1 + sigma * emis * Ts ** 3 / k_ice * v["h_ice"])
+            Tstar = max(F(0), Tstar)
             Tnew = Tstar if v["h_ice"] >= F(I.ice_consolidation_thickness) else Tb
             dT = Tnew - Ts
             step = min(F(P.skin_max_delta_T), abs(dT)) * mp.sign(dT)

@@ -47,3 +47,30 @@ def test_limit_cycles_make_float32_and_float64_disagree_where_the_iteration_does
     assert cyc32.sum() > cyc64.sum()
     print(flux_configuration, "limit-cycle cells:", cyc64.sum(), "(F64)", cyc32.sum(), "(F32) of", ice.sum(), " F32-vs-F64 Q_c spread: converged",
           d[conv].max(), " limit cycle", d[cyc64 | cyc32].max())
+
+
+def test_linearized_longwave_update_damps_the_iteration():
+    """COFLUX_SKIN_LINEARIZED_LONGWAVE (include/coflux.h): the emitted long wave taken implicitly.  Same fixed points wherever
+    both forms converge (the balance temperature does not depend on how it is approached).  Measured effect on the limit
+    cycles: marginal (940 → 937 of 10 571 cells) — the long wave contributes only ≈ 5 of the ≈ 20 W m⁻² K⁻¹ of ∂Q_a/∂T_s; the
+    cycle is driven by the lagged turbulent fluxes.  Documented as the answer to "is the clamped update the culprit?": no."""
+    from climaocean.jl_b200 import _abi
+    res = {}
+    for upd in (_abi.SKIN_CLAMPED_EXPLICIT, _abi.SKIN_LINEARIZED_LONGWAVE):
+        grid, host, cfg = make_case(160, 72, 4, 64, with_ice=True)
+        cfg.atmosphere_sea_ice.skin_temperature_update = upd
+        pyoracle.interpolate_atmosphere(cfg, host.atmos_series(), QUERY_TIME, host.exchange_state())
+        pyoracle.atmosphere_sea_ice_fluxes(cfg, host.exchange_state(), host.ocean_surface(), host.sea_ice_state(), host.interface_fluxes("ai"))
+        o = host.outputs()
+        o["its"] = host.iterations_ai.numpy()[0, 7:-7, 7:-7].copy()
+        res[upd] = (o, cfg.atmosphere_sea_ice.max_iterations)
+    (a, maxit), (b, _) = res[_abi.SKIN_CLAMPED_EXPLICIT], res[_abi.SKIN_LINEARIZED_LONGWAVE]
+    ice = a["its"] > 0
+    cyc_a, cyc_b = ((a["its"] >= maxit) & ice).sum(), ((b["its"] >= maxit) & ice).sum()
+    assert cyc_b <= cyc_a, (cyc_a, cyc_b)
+    both = ice & (a["its"] < maxit) & (b["its"] < maxit)
+    k = "ai.interface_temperature"
+    # both stop within the 1e-8 window of the same balance: the skin temperatures agree far better than the cycle amplitude
+    assert np.abs(a[k][both] - b[k][both]).max() < 1e-4
+    print("cells running to maxiter: explicit", cyc_a, " linearized long wave", cyc_b, " of", ice.sum(),
+          " mean passes", a["its"][ice].mean(), b["its"][ice].mean())

@@ -96,10 +96,12 @@ def test_sea_ice_ocean_fluxes_and_ice_aware_assembly(bits, flux_configuration):
 
 
 @pytest.mark.parametrize("bits", [64, 32])
-@pytest.mark.parametrize("flux_configuration", ["default", "corrected", "ncar"])
+@pytest.mark.parametrize("flux_configuration", ["default", "corrected", "ncar", "default+linearized_longwave"])
 def test_atmosphere_sea_ice_fluxes(bits, flux_configuration):
     import torch
-    grid, host, cfg = make_case(64, 28, 4, bits, with_ice=True, flux_configuration=flux_configuration)
+    grid, host, cfg = make_case(64, 28, 4, bits, with_ice=True, flux_configuration=flux_configuration.split("+")[0])
+    if flux_configuration.endswith("+linearized_longwave"):          # include/coflux.h: coflux_skin_temperature_update
+        cfg.atmosphere_sea_ice.skin_temperature_update = _abi.SKIN_LINEARIZED_LONGWAVE
     dev = host.to("cuda:0")
     pyoracle.interpolate_atmosphere(cfg, host.atmos_series(), QUERY_TIME, host.exchange_state())
     pyoracle.atmosphere_sea_ice_fluxes(cfg, host.exchange_state(), host.ocean_surface(), host.sea_ice_state(), host.interface_fluxes("ai"))

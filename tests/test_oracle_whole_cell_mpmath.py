@@ -61,9 +61,12 @@ def test_atmosphere_ocean_cell_solve_matches_50_digit_evaluation(flux_configurat
     print(flux_configuration, "worst relative deviation from the 50-digit fixed point:", worst)
 
 
-@pytest.mark.parametrize("flux_configuration", ["default", "corrected", "ncar"])
+@pytest.mark.parametrize("flux_configuration", ["default", "corrected", "ncar", "default+linearized_longwave"])
 def test_atmosphere_sea_ice_cell_solve_matches_50_digit_evaluation(flux_configuration):
-    cfg = cj.default_config(4, 4, 2, 64, flux_configuration)
+    linearized = flux_configuration.endswith("+linearized_longwave")
+    cfg = cj.default_config(4, 4, 2, 64, flux_configuration.split("+")[0])
+    if linearized:
+        cfg.atmosphere_sea_ice.skin_temperature_update = _abi.SKIN_LINEARIZED_LONGWAVE
     n = 64
     cells = _cells(n, 23, ice=True)
     out = np.zeros((n, 5))

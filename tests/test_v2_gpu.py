@@ -283,5 +283,5 @@ def test_config5_one_degree_tripolar_ocean_sea_ice_flux_set(bits):
                     cfg.atmosphere_sea_ice.max_iterations, ice_keys, stress_keys=("net_ice.top_u", "net_ice.top_v"))
     # the rotation acts in the cap only, and strongly near the fold
     cs = host.rotation[0].numpy()[0, 1:-1, 1:-1]
-    assert np.all(cs[:grid.j0 - 1] > 1 - 1e-12) and cs[grid.j0 + 2:].min() < 0.1
+    assert np.all(cs[:grid.j0 - 1] > 1 - 1e-6) and cs[grid.j0 + 2:].min() < 0.1
     assert np.any(gpu["net_ice.top_heat"] != 0) and np.any(gpu["io.frazil_heat"] != 0) and np.any(gpu["net.S"] != 0)

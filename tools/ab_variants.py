@@ -11,11 +11,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "base_320x2_1280": [],
-    "s2_320x2_1120": ["COFLUX_TILE_NT64_S2=320", "COFLUX_TILE_CELLS64_S2=1120", "COFLUX_TILE_MIN_BLOCKS64_S2=2"],
-    "d384x2_1536_r80": ["COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=1408", "COFLUX_TILE_MIN_BLOCKS64=2"],
-    "d640x1_3200": ["COFLUX_TILE_NT64=640", "COFLUX_TILE_CELLS64=3200", "COFLUX_TILE_MIN_BLOCKS64=1"],
-    "d320x2_1408": ["COFLUX_TILE_CELLS64=1408"],
+    "f32_libm": [],
+    "f32_fast": ["COFLUX_F32_FAST=1"],
+    "iob_256_8_3": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=3"],
+    "iob_256_8_2": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
+    "iob_256_4_6": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=4", "COFLUX_IOB_STAGES=6"],
+    "iob_288_8_3": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=3"],
+    "iob_288_8_2": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
+    "iob_288_5_5": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=5", "COFLUX_IOB_STAGES=5"],
+    "iob_384_8_2": ["COFLUX_IOB_W=384", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
 }
 
 
