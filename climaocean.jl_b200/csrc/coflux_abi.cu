@@ -1078,15 +1078,15 @@ static int do_io(coflux_ctx* c, coflux_ocean_columns* oc, coflux_sea_ice_state* 
   a.dt = (FT)dt;
   if (c->avg_on) { a.avg_JTf = view2d(c->avg.JT_frazil, 0, es); a.avg_T = (FT)c->avg.previous_interval; a.avg_dt = (FT)c->avg.dt; }
   a.P = dev_params<FT>(c);
-  // COFLUX_IO_BULK=1 selects the bulk-asynchronous form (cp.async.bulk → shared memory, mbarrier pipeline; needs columns
-  // contiguous in i and a halo to absorb the 16-byte alignment slack).  Measured on B200 at 1/12°, Nz = 75 (round 2,
-  // profiles/README.md): bit-identical results but 2.61 ms (59 % of the HBM peak) against 2.26 ms (69 %) for the
-  // register-staged kernel — 1 KB row segments are too small for the copy engine — so the register-staged kernel stays.
-  static const bool bulk_on = [] { const char* e = std::getenv("COFLUX_IO_BULK"); return e && e[0] == '1'; }();
-  const bool can_bulk = bulk_on && a.T.si == 1 && a.S.si == 1 && oc->T.off_i >= (int)(16 / es) && oc->S.off_i >= (int)(16 / es) &&
+  // The bulk-asynchronous form (cp.async.bulk → shared memory, mbarrier pipeline) whenever the columns are contiguous in i
+  // and the parents have a halo to absorb the 16-byte alignment slack: 1.66 ms = 93 % of the measured HBM peak at 1/12°,
+  // Nz = 75, Float64, against 2.26 ms = 69 % for the register-staged kernel (bit-identical results; profiles/README.md).
+  // COFLUX_IO_BULK=0 selects the register-staged kernel (A/B runs).
+  static const bool bulk_off = [] { const char* e = std::getenv("COFLUX_IO_BULK"); return e && e[0] == '0'; }();
+  const bool can_bulk = !bulk_off && a.T.si == 1 && a.S.si == 1 && oc->T.off_i >= (int)(16 / es) && oc->S.off_i >= (int)(16 / es) &&
                         ((uintptr_t)oc->T.ptr % 16 == 0) && ((uintptr_t)oc->S.ptr % 16 == 0);
   if (can_bulk) {
-    constexpr int W = COFLUX_IOB_W, KB = COFLUX_IOB_KB, STAGES = COFLUX_IOB_STAGES;
+    constexpr int W = (sizeof(FT) == 8) ? COFLUX_IOB_W : COFLUX_IOB_W32, KB = COFLUX_IOB_KB, STAGES = COFLUX_IOB_STAGES;
     auto kern = ice_ocean_bulk_kernel<FT, W, KB, STAGES>;
     const size_t smem = sizeof(IceOceanBulkSmem<FT, W, KB, STAGES>);
     static unsigned long long configured = 0;
@@ -1679,7 +1679,8 @@ extern "C" int coflux_closure_surface_forcing(coflux_ctx* c, const coflux_net_oc
 // ---------------------------------------------------------------------------------------------
 static int salt_workspace(coflux_ctx* c) {
   if (c->salt_ws) return COFLUX_OK;
-  CUDA_TRY(cudaMalloc(&c->salt_ws, sizeof(double) * (2 * SALT_BLOCKS + 2)));
+  CUDA_TRY(cudaMalloc(&c->salt_ws, sizeof(double) * (2 * SALT_BLOCKS + 4)));
+  CUDA_TRY(cudaMemset(c->salt_ws, 0, sizeof(double) * (2 * SALT_BLOCKS + 4)));     // [2·SALT_BLOCKS + 2 …]: grid-barrier words
   return COFLUX_OK;
 }
 template <typename FT>
@@ -1708,6 +1709,35 @@ static int do_subtract_mean(coflux_ctx* c, const coflux_salinity_normalization* 
   const long long cells = (long long)a.ni * a.nj;
   const unsigned grid = (unsigned)std::min<long long>((cells + 255) / 256, 148LL * 8);
   subtract_mean_kernel<FT><<<grid, 256, 0, st>>>(a);
+  return check_launch(c, 1);
+}
+// one cooperative launch (sums → grid barrier → subtraction); COFLUX_NORM_FUSED=0 keeps the two-launch form
+template <typename FT>
+static int do_normalize_fused(coflux_ctx* c, const coflux_salinity_normalization* n, cudaStream_t st, bool* done) {
+  static const bool fused = [] { const char* e = std::getenv("COFLUX_NORM_FUSED"); return !(e && e[0] == '0'); }();
+  *done = false;
+  if (!fused) return COFLUX_OK;
+  int per_sm = 0, sms = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, normalize_salinity_kernel<FT>, 256, 0));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  int grid = SALT_BLOCKS;                         // largest divisor of SALT_BLOCKS that is co-resident
+  while (grid > per_sm * sms || SALT_BLOCKS % grid) --grid;
+  if (grid < sms) return COFLUX_OK;               // not this device: two launches
+  const coflux_grid_desc& g = c->cfg.grid;
+  NormalizeArgs<FT> a;
+  memset(&a, 0, sizeof(a));
+  a.s.Nx = g.Nx; a.s.Ny = g.Ny;
+  a.s.flux = view2d(n->flux, 0, sizeof(FT)); a.s.add = view2d(n->additional, 0, sizeof(FT)); a.s.area = view2d(n->area, 0, sizeof(FT));
+  a.s.mask = view2d(n->mask, 0, 1);
+  a.s.partial = c->salt_ws;
+  a.m.p = static_cast<char*>(n->flux.ptr) + (int64_t)n->flux.off_k * n->flux.stride_k * (int64_t)sizeof(FT);
+  a.m.si = n->flux.stride_i; a.m.sj = n->flux.stride_j;
+  a.m.ni = g.Nx + 2 * n->flux.off_i; a.m.nj = g.Ny + 2 * n->flux.off_j;
+  a.vblocks = SALT_BLOCKS;
+  a.bar = reinterpret_cast<unsigned*>(c->salt_ws + 2 * SALT_BLOCKS + 2);
+  void* params[] = {&a};
+  CUDA_TRY(cudaLaunchCooperativeKernel((void*)normalize_salinity_kernel<FT>, dim3(grid), dim3(256), params, 0, st));
+  *done = true;
   return check_launch(c, 1);
 }
 static int check_norm(coflux_ctx* c, const coflux_salinity_normalization* n) {
@@ -1741,6 +1771,9 @@ extern "C" int coflux_normalize_salinity_flux(coflux_ctx* c, const coflux_salini
   rc = salt_workspace(c);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bool done = false;
+  rc = c->cfg.dtype == COFLUX_F64 ? do_normalize_fused<double>(c, n, st, &done) : do_normalize_fused<float>(c, n, st, &done);
+  if (rc || done) return rc;
   rc = c->cfg.dtype == COFLUX_F64 ? do_salt_sums<double>(c, n, nullptr, st) : do_salt_sums<float>(c, n, nullptr, st);
   if (rc) return rc;
   return c->cfg.dtype == COFLUX_F64 ? do_subtract_mean<double>(c, n, nullptr, st) : do_subtract_mean<float>(c, n, nullptr, st);

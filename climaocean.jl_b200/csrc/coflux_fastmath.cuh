@@ -181,11 +181,12 @@ COFLUX_FM float rcp(float x) {
 }
 COFLUX_FM float div(float a, float b) { return a / b; }
 COFLUX_FM float sqrt(float x) { return ::sqrtf(x); }
-// COFLUX_F32_FAST (A/B knob, default off): SFU forms of the three transcendental functions of the Float32 pass —
-// lg2.approx / ex2.approx (MUFU.LG2 / MUFU.EX2) with one Newton step for the cube root — instead of the CUDA library's
-// logf / expf / cbrtf (20–30 instructions each).  Accuracy: ≈ 2⁻²¹ absolute in log₂, i.e. ≤ 3e-7 relative in ln(h/ℓ) ≈ 10.
+// COFLUX_F32_FAST: SFU forms of the three transcendental functions of the Float32 pass — lg2.approx / ex2.approx (MUFU.LG2 /
+// MUFU.EX2) with one Newton step for the cube root — instead of the CUDA library's logf / expf / cbrtf (20–30 instructions
+// each).  Accuracy: ≈ 2⁻²¹ absolute in log₂, i.e. ≤ 3e-7 relative in ln(h/ℓ) ≈ 10.  Measured on B200 (round 2): 2.35 → 2.15 ms at
+// 1/12°, and the CUDA-vs-oracle error distribution is unchanged (max|d|/max|b| 3.3e-7, p99 5.4e-6: profiles/README.md).
 #ifndef COFLUX_F32_FAST
-#define COFLUX_F32_FAST 0
+#define COFLUX_F32_FAST 1
 #endif
 COFLUX_FM float cbrt(float x) {
 #if defined(__CUDA_ARCH__) && COFLUX_F32_FAST

@@ -875,14 +875,20 @@ template <typename FT> __global__ void __launch_bounds__(256) flux_average_kerne
 // at an arbitrary element, so each copy starts at the aligned element at or before the segment (≤ 16/sizeof(FT) − 1 extra
 // elements, inside the parent because every parent has a halo) and the consumer indexes past that shift.
 // ---------------------------------------------------------------------------------------------
+// Tile shape, A/B-measured on B200 at 1/12°, Nz = 75 (profiles/README.md; fraction of the measured HBM peak, Float64):
+//   W × KB × STAGES   128×8×4 59 %   256×8×3 73 %   256×8×2 90 %   288×8×2 93 %   384×8×2 90 %   256×4×6 67 %   288×5×5 40 %
+// Row segments of ≥ 2 KB per copy, few deep stages, three CTAs per SM.  (Register-staged kernel: 69 %.)
 #ifndef COFLUX_IOB_W
-#define COFLUX_IOB_W 128
+#define COFLUX_IOB_W 288            /* Float64 (4320 = 15 × 288) */
+#endif
+#ifndef COFLUX_IOB_W32
+#define COFLUX_IOB_W32 256          /* Float32 */
 #endif
 #ifndef COFLUX_IOB_KB
 #define COFLUX_IOB_KB 8
 #endif
 #ifndef COFLUX_IOB_STAGES
-#define COFLUX_IOB_STAGES 4
+#define COFLUX_IOB_STAGES 2
 #endif
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -1039,15 +1045,13 @@ template <typename FT> struct SaltSumArgs {
   DArr flux, add, area, mask;
   double* partial;      // [2 * gridDim.x]
 };
-template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(const __grid_constant__ SaltSumArgs<FT> a) {
+// One (virtual) thread's share of the two sums: elements first, first + stride, …, four loads in flight; the order
+// in which a thread adds its elements is fixed, so the result is bit-reproducible.  (i, j) advance incrementally —
+// a 64-bit division per element would make this streaming kernel compute bound.
+template <typename FT> __device__ __forceinline__ void salt_thread_sums(const SaltSumArgs<FT>& a, long long idx, long long stride, double& num, double& den) {
   const long long n = (long long)a.Nx * a.Ny;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  double num = 0.0, den = 0.0;
-  // 4 independent loads in flight per thread; the order in which a thread adds its elements is fixed, so the
-  // result stays bit-reproducible
-  // (i, j) advance incrementally — a 64-bit division per element would make this streaming kernel compute bound
+  num = 0.0; den = 0.0;
   const int di = (int)(stride % a.Nx), dj = (int)(stride / a.Nx);
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
   while (idx < n) {
     double f[4], A[4];
@@ -1065,16 +1069,24 @@ template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(c
 #pragma unroll
     for (int u = 0; u < 4; ++u) { num = fma(f[u], A[u], num); den += A[u]; }
   }
+}
+// warp shuffle → CTA (8 warps) → partial[vb]; fixed order
+__device__ __forceinline__ void salt_block_partial(double num, double den, double* sn, double* sd, double* partial, int vb) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
-  __shared__ double sn[8], sd[8];
   if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double tn = 0.0, td = 0.0;
     for (int w = 0; w < 8; ++w) { tn += sn[w]; td += sd[w]; }
-    a.partial[2 * blockIdx.x] = tn; a.partial[2 * blockIdx.x + 1] = td;
+    partial[2 * vb] = tn; partial[2 * vb + 1] = td;
   }
+}
+template <typename FT> __global__ void __launch_bounds__(256) salt_sums_kernel(const __grid_constant__ SaltSumArgs<FT> a) {
+  double num, den;
+  salt_thread_sums<FT>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x, num, den);
+  __shared__ double sn[8], sd[8];
+  salt_block_partial(num, den, sn, sd, a.partial, blockIdx.x);
 }
 // one warp, fixed order: lane l adds partials l, l+32, …; then a shuffle tree
 __device__ __forceinline__ void salt_reduce_partials(const double* partial, int nblocks, double& num, double& den) {
@@ -1095,25 +1107,10 @@ template <typename FT> struct SubMeanArgs {
   const double* sums;   // {Σ f·Az, Σ Az}, or (nblocks > 0) the CTA partials of salt_sums_kernel
   int nblocks;
 };
-template <typename FT> __global__ void __launch_bounds__(256) subtract_mean_kernel(const __grid_constant__ SubMeanArgs<FT> a) {
-  __shared__ double tot[2];
-  if (a.nblocks > 0) {                 // single-slab form: every CTA reduces the partials itself (same order as the
-    if (threadIdx.x < 32) {            // final kernel → same bits), which saves a launch
-      double num, den;
-      salt_reduce_partials(a.sums, a.nblocks, num, den);
-      if (threadIdx.x == 0) { tot[0] = num; tot[1] = den; }
-    }
-    __syncthreads();
-  } else if (threadIdx.x == 0) {
-    tot[0] = a.sums[0]; tot[1] = a.sums[1];
-  }
-  if (a.nblocks <= 0) __syncthreads();
-  const double den = tot[1];
-  const FT mean = (den != 0.0) ? (FT)(tot[0] / den) : FT(0);
+// parent element idx, idx + stride, …: four loads in flight, then four stores
+template <typename FT> __device__ __forceinline__ void subtract_thread(const SubMeanArgs<FT>& a, FT mean, long long idx, long long stride) {
   const long long n = (long long)a.ni * a.nj;
-  const long long stride = (long long)gridDim.x * blockDim.x;
   const int di = (int)(stride % a.ni), dj = (int)(stride / a.ni);
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int j = (int)(idx / a.ni), i = (int)(idx - (long long)j * a.ni);
   while (idx < n) {
     FT v[4];
@@ -1131,6 +1128,71 @@ template <typename FT> __global__ void __launch_bounds__(256) subtract_mean_kern
 #pragma unroll
     for (int u = 0; u < 4; ++u) if (q[u]) *q[u] = v[u] - mean;
   }
+}
+template <typename FT> __global__ void __launch_bounds__(256) subtract_mean_kernel(const __grid_constant__ SubMeanArgs<FT> a) {
+  __shared__ double tot[2];
+  if (a.nblocks > 0) {                 // single-slab form: every CTA reduces the partials itself (same order as the
+    if (threadIdx.x < 32) {            // final kernel → same bits), which saves a launch
+      double num, den;
+      salt_reduce_partials(a.sums, a.nblocks, num, den);
+      if (threadIdx.x == 0) { tot[0] = num; tot[1] = den; }
+    }
+  } else if (threadIdx.x == 0) {
+    tot[0] = a.sums[0]; tot[1] = a.sums[1];
+  }
+  __syncthreads();
+  const double den = tot[1];
+  const FT mean = (den != 0.0) ? (FT)(tot[0] / den) : FT(0);
+  subtract_thread<FT>(a, mean, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// NormalizeSalinity in ONE cooperative launch: every CTA sums `vblocks / gridDim.x` virtual blocks of the two-launch
+// form (same partials, same order → same bits), a grid barrier, then every CTA reduces the partials itself and
+// subtracts the mean from its share of the parent.  The second pass finds the flux field in L2 (62 MB of 126 MB at
+// 1/12° F64), so DRAM sees 17 B/cell of reads and 8 B/cell of writes.  The barrier is a self-resetting
+// count + generation pair, so a captured graph can replay the launch.
+template <typename FT> struct NormalizeArgs {
+  SaltSumArgs<FT> s;
+  SubMeanArgs<FT> m;
+  int vblocks;
+  unsigned* bar;        // {arrived, generation}
+};
+template <typename FT> __global__ void __launch_bounds__(256) normalize_salinity_kernel(const __grid_constant__ NormalizeArgs<FT> a) {
+  __shared__ double sn[8], sd[8], tot[2];
+  const int V = a.vblocks / (int)gridDim.x;
+  const long long vstride = (long long)a.vblocks * blockDim.x;
+  for (int v = 0; v < V; ++v) {
+    const int vb = (int)blockIdx.x * V + v;
+    double num, den;
+    salt_thread_sums<FT>(a.s, (long long)vb * blockDim.x + threadIdx.x, vstride, num, den);
+    salt_block_partial(num, den, sn, sd, a.s.partial, vb);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    volatile unsigned* gen = a.bar + 1;
+    const unsigned g = *gen;           // cannot move on before this CTA has arrived
+    __threadfence();
+    if (atomicAdd(a.bar, 1u) == gridDim.x - 1) {
+      a.bar[0] = 0;
+      __threadfence();
+      atomicAdd(a.bar + 1, 1u);
+    } else {
+      while (*gen == g) __nanosleep(64);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double num = 0.0, den = 0.0;
+    for (int b = threadIdx.x; b < a.vblocks; b += 32) { num += __ldcg(a.s.partial + 2 * b); den += __ldcg(a.s.partial + 2 * b + 1); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { num += __shfl_down_sync(0xffffffffu, num, o); den += __shfl_down_sync(0xffffffffu, den, o); }
+    if (threadIdx.x == 0) { tot[0] = num; tot[1] = den; }
+  }
+  __syncthreads();
+  const double den = tot[1];
+  const FT mean = (den != 0.0) ? (FT)(tot[0] / den) : FT(0);
+  subtract_thread<FT>(a.m, mean, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 }  // namespace coflux

@@ -566,6 +566,10 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 // A/B on B200 at 1/12° (profiles/README.md): Float64 at 64 / 72 registers (32 / 28 warps per SM) is SLOWER (3.98 / 3.56 ms
 // against 3.32 ms: the spills cost more than the extra warps hide); Float32 256 × 4 × 1024 2.40 ms, 384 × 3 × 1536 2.34 ms.
 // Round-1 shape for reference (table in global memory): 128 threads × 6 CTAs, 384 cells (profiles/README.md).
+#ifndef COFLUX_TILE_CARRY2
+#define COFLUX_TILE_CARRY2 0     /* 1: Δu, Δv, ρ_a, c_p,m of every cell stay in shared memory between phase A and phase C (32 B per cell more)
+                                   instead of being re-read / parked in the ρτ output arrays (A/B knob) */
+#endif
 #ifndef COFLUX_TILE_PRE1
 #define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A (A/B knob) */
 #endif
@@ -612,6 +616,7 @@ template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT inu[(LEAN && VARNU) ? TILE : 1];                     // 1/ν (lean pass)
   FT us1[LEAN ? TILE : 1], chi1[LEAN ? TILE : 1];         // state after the lock-step first pass (lean pass)
+  FT du[COFLUX_TILE_CARRY2 ? TILE : 1], dv[COFLUX_TILE_CARRY2 ? TILE : 1], rho[COFLUX_TILE_CARRY2 ? TILE : 1], cp[COFLUX_TILE_CARRY2 ? TILE : 1];
   unsigned short queue[TILE];
   int n_front, n_back, head[2];     // head[0]: next unstable cell (front of the queue), head[1]: next stable cell (back)
 };
@@ -738,7 +743,11 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
       const FT x = MP::div(FT(1) - s, FT(1) - s + P.wmf_alpha * s);
       const FT theta_a = Ta + MP::div(P.g * P.h, atm.cp_m);
       const SurfaceState<FT> S = surface_state<FT, 0, MP>(P, F, atm, pa, theta_a, x, Ts);
+#if COFLUX_TILE_CARRY2
+      sm.du[cidx] = du; sm.dv[cidx] = dv; sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
+#else
       stg<FT>(a.rtx, i, j, atm.rho); stg<FT>(a.rty, i, j, atm.cp_m);     // parked for phase C (see TileSmem)
+#endif
       if (fixed ? (F.maxit > 0) : true) {
         queued = true;
         FT c1, c2;
@@ -946,9 +955,12 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
     const FT us = sm.U2[cidx], ts = sm.dth[cidx], qs = sm.dq[cidx];
     if (act) {
       // the exchange state was written by this very thread in phase A (or is an input): plain loads
+      const FT Ta = reinterpret_cast<const FT*>(a.xT.p)[(int64_t)i * a.xT.si + (int64_t)j * a.xT.sj];
+#if COFLUX_TILE_CARRY2
+      const FT du = sm.du[cidx], dv = sm.dv[cidx], rho = sm.rho[cidx], cp = sm.cp[cidx];
+#else
       const FT ua = reinterpret_cast<const FT*>(a.xu.p)[(int64_t)i * a.xu.si + (int64_t)j * a.xu.sj];
       const FT va = reinterpret_cast<const FT*>(a.xv.p)[(int64_t)i * a.xv.si + (int64_t)j * a.xv.sj];
-      const FT Ta = reinterpret_cast<const FT*>(a.xT.p)[(int64_t)i * a.xT.si + (int64_t)j * a.xT.sj];
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) {
         du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
@@ -956,6 +968,7 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
       } else { du = ua; dv = va; }
       const FT rho = reinterpret_cast<const FT*>(a.rtx.p)[(int64_t)i * a.rtx.si + (int64_t)j * a.rtx.sj];
       const FT cp = reinterpret_cast<const FT*>(a.rty.p)[(int64_t)i * a.rty.si + (int64_t)j * a.rty.sj];
+#endif
       FT taux, tauy;
       if constexpr (LEAN) {
         const FT d2 = du * du + dv * dv;

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import climaocean.jl_b200 as cj
-from tests.test_full_size import _case, _oracle_band, BAND
+from tests.test_full_size import _case, _oracle_rows
 from tests.common import QUERY_TIME
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 grid, host, dev, cfg = _case("twelfth", 64, sys.argv[2] if len(sys.argv) > 2 else "default")
@@ -12,7 +12,7 @@ eng = cj.Engine(cfg)
 inp, out = dev.update_bundles()
 eng.update_state(inp, out, QUERY_TIME); torch.cuda.synchronize()
 gpu = dev.outputs(); its_g = dev.iterations.numpy()[0, 7:-7, 7:-7][:rows].copy()
-ref = _oracle_band(host, cfg, rows); its_r = host.iterations.numpy()[0, 7:-7, 7:-7][:rows].copy()
+ref = _oracle_rows(host, cfg, 0, rows); its_r = host.iterations.numpy()[0, 7:-7, 7:-7][:rows].copy()
 print("iteration mismatches", int((its_g != its_r).sum()), "of", its_r.size)
 for k in sorted(ref):
     if k not in gpu or not (k.startswith("ao.") or k.startswith("net.") or k.startswith("exchange.")): continue

@@ -1,11 +1,11 @@
 """Parity at BASELINE.json's full sizes (1/4° 1440×600 and 1/12° 4320×1800) through properties that do not need
 the CPU oracle to cover the whole grid:
 
-  * band parity   — the oracle recomputes latitude rows of the SAME full-grid inputs (it runs on sub-grid views of the same
-                    host arrays: every descriptor's row offset is shifted to the band): five 12-row bands spread from the
-                    southern to the northern edge plus 300 single rows drawn at random (≈ 20 % of the 1/12° grid, every
-                    regime of the synthetic inputs), for all three flux configurations; the CUDA result of the full-grid
-                    launch must match there to the north_star tolerance;
+  * whole-grid parity — the OpenMP oracle recomputes EVERY cell of the same full-grid inputs (7.8 M cells at 1/12°, a few
+                    seconds on the box's host cores), for all three flux configurations and both precisions; the CUDA
+                    result of the full-grid launch must match everywhere to the north_star tolerance and, in Float64, with
+                    the same iteration count in every cell.  (The oracle runs on sub-grid views of the same host arrays
+                    — every descriptor's row offset shifted — in blocks of rows, so a failure names its latitude.);
   * determinism   — two launches give bit-identical outputs;
   * decomposition — the pipelined HOST-buffer entry (row-chunked launches, `coflux_update_state_host`) reproduces the
                     single-launch device path bit for bit, i.e. a cell's result does not depend on how the grid is cut;
@@ -24,9 +24,7 @@ from tests.common import FLOOR, QUERY_TIME, RTOL, np_dtype, rel_err
 pytestmark = pytest.mark.gpu
 
 SIZES = {"quarter": (1440, 600, 10), "twelfth": (4320, 1800, 75)}
-BAND = 12          # latitude rows per band recomputed by the oracle
-N_BANDS = 5        # bands, evenly spread over the grid (south edge … north edge)
-N_RANDOM_ROWS = {"quarter": 100, "twelfth": 300}
+BLOCK = 300        # latitude rows per oracle call (the whole grid is covered, block by block)
 
 
 def _case(res, bits, flux_configuration):
@@ -72,7 +70,7 @@ def _oracle_rows(host, cfg_full, j0, rows):
 @pytest.mark.parametrize("res,bits,flux_configuration", [("quarter", 64, "default"), ("quarter", 64, "corrected"), ("quarter", 32, "default"),
                                                          ("quarter", 64, "ncar"), ("twelfth", 64, "default"), ("twelfth", 64, "corrected"),
                                                          ("twelfth", 64, "ncar"), ("twelfth", 32, "default")])
-def test_full_size_band_parity_determinism_closure(res, bits, flux_configuration):
+def test_full_size_whole_grid_parity_determinism_closure(res, bits, flux_configuration):
     import torch
     grid, host, dev, cfg = _case(res, bits, flux_configuration)
     eng = cj.Engine(cfg)
@@ -82,11 +80,9 @@ def test_full_size_band_parity_determinism_closure(res, bits, flux_configuration
     first = dev.outputs()
     its = dev.iterations.numpy()[0, 7:-7, 7:-7].copy()
 
-    # band parity against the oracle on the same inputs: N_BANDS bands south → north, then random single rows
+    # parity against the oracle on the same inputs, every row of the grid
     Ny = grid.Ny
-    starts = [int(round(b * (Ny - BAND) / (N_BANDS - 1))) for b in range(N_BANDS)]
-    rng = np.random.default_rng(2026)
-    windows = [(j0, BAND) for j0 in starts] + [(int(j), 1) for j in rng.choice(Ny, N_RANDOM_ROWS[res], replace=False)]
+    windows = [(j0, min(BLOCK, Ny - j0)) for j0 in range(0, Ny, BLOCK)]
     bad, checked = {}, 0
     scale = {k: float(np.max(np.abs(v))) for k, v in first.items()}
     for j0, rows in windows:
@@ -100,8 +96,9 @@ def test_full_size_band_parity_determinism_closure(res, bits, flux_configuration
                 if not (e <= RTOL[bits]):
                     bad[(k, j0)] = e
         assert np.array_equal(host.iterations.numpy()[0, 7 + j0:7 + j0 + rows, 7:-7], its[j0:j0 + rows]) or bits == 32, f"iteration counts differ in rows {j0}…"
-    assert not bad, f"band parity failures at {res} f{bits} {flux_configuration}: {dict(list(bad.items())[:8])}"
-    print(f"{res} f{bits} {flux_configuration}: {checked} of {Ny} rows checked against the oracle")
+    assert not bad, f"parity failures at {res} f{bits} {flux_configuration}: {dict(list(bad.items())[:8])}"
+    assert checked == Ny
+    print(f"{res} f{bits} {flux_configuration}: all {checked} rows ({checked * grid.Nx} cells) checked against the oracle")
 
     # determinism: bit-identical relaunch
     eng.update_state(inp, out, QUERY_TIME)

@@ -11,15 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "f32_libm": [],
-    "f32_fast": ["COFLUX_F32_FAST=1"],
-    "iob_256_8_3": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=3"],
-    "iob_256_8_2": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
-    "iob_256_4_6": ["COFLUX_IOB_W=256", "COFLUX_IOB_KB=4", "COFLUX_IOB_STAGES=6"],
-    "iob_288_8_3": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=3"],
-    "iob_288_8_2": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
-    "iob_288_5_5": ["COFLUX_IOB_W=288", "COFLUX_IOB_KB=5", "COFLUX_IOB_STAGES=5"],
-    "iob_384_8_2": ["COFLUX_IOB_W=384", "COFLUX_IOB_KB=8", "COFLUX_IOB_STAGES=2"],
+    "base_park": [],
+    "carry2_320x2_896": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_CELLS64=896", "COFLUX_TILE_CELLS64_S2=768"],
+    "carry2_320x2_960_k5": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_CELLS64=960", "COFLUX_PSI_SM_KHI=5", "COFLUX_TILE_CELLS64_S2=768"],
+    "io32_512": ["COFLUX_IOB_W32=512"],
+    "io32_384": ["COFLUX_IOB_W32=384"],
+    "io32_576": ["COFLUX_IOB_W32=576"],
+    "carry2_384x2_896_r80": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=896", "COFLUX_TILE_CELLS64_S2=768"],
 }
 
 
