@@ -355,7 +355,7 @@ def main():
     rank_kernel_ms = gather_over_ranks(dist, flux_ms, device, world)
     rank_step_ms = gather_over_ranks(dist, time_device_steps.local_ms, device, world)
     its = dev.iterations.numpy()[0, 7:-7, 7:-7]
-    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,768,1> (fused interpolate + similarity solve + tracer/radiative assembly)",
+    roof = {"bound": "hbm", "kernel": "flux_tile_kernel<double,1,1,1280,1>, 320 threads x 2 CTAs/SM (fused interpolate + similarity solve + tracer/radiative assembly)",
             "achieved": cells_local * WORDS_FLUX_KERNEL * 8 / (flux_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "peak_source": peak_src, "traffic": load_traffic(cells_local),
             "algorithmic_bytes_per_cell": WORDS_FLUX_KERNEL * 8, "kernel_ms": flux_ms, "stress_kernel_ms": stress_ms,
@@ -412,10 +412,21 @@ def main():
             if k >= 3:
                 tn.append(a_.elapsed_time(b_))
         tnm = float(np.mean(tn))
-        extras["normalize_salinity_f64"] = {"ms": tnm, "launches": 2, "algorithmic_bytes_per_cell": 24,
+        n0 = eng.launches
+        eng.normalize_salinity_flux(norm, st0)
+        extras["normalize_salinity_f64"] = {"ms": tnm, "launches": eng.launches - n0, "algorithmic_bytes_per_cell": 24,
                                             "achieved_GBs": cells_global * 24 / (tnm * 1e-3) / 1e9,
                                             "roofline_frac": cells_global * 24 / (tnm * 1e-3) / 1e9 / peak,
-                                            "note": "two ~25 us kernels: launch ramps are a third of the time"}
+                                            "note": "one cooperative launch: sums, grid barrier, subtraction (the second pass reads the flux plane from L2)"}
+        # running time averages (omip_diagnostics.jl:125-158) attached to the step: epilogues of the flux and stress kernels,
+        # 6 ocean-only averages read + written per cell = 12 more words; no extra launch
+        dev.allocate_averages()
+        eng.attach_flux_averages(dev.flux_averages(0.0, 600.0))
+        mavg, lavg, favg, savg, _ = time_device_steps(eng, dev, max(5, args.steps // 2), 3, None, device)
+        eng.attach_flux_averages(None)
+        extras["step_with_time_averages_f64"] = {"ms_per_step": mavg, "flux_kernel_ms": favg, "stress_kernel_ms": savg,
+                                                 "extra_ms_vs_plain_step": mavg - ms, "launches_per_step": lavg / max(5, args.steps // 2)}
+        del dev.averages
         # closure surface-forcing front ends (KPP u★, Bo; NEMO-TKE u★², e_surf): stand-alone kernel, 6 reads + 4 writes per cell
         cf = dev.closure_forcing()
         netb = dev.net_ocean_fluxes()
@@ -467,6 +478,19 @@ def main():
         tam = float(np.mean(tai))
         extras["atmosphere_sea_ice_kernel_f64"] = {"ms": tam, "Mcells/s": cells_global / (tam * 1e-3) / 1e6,
                                                    "ice_covered_fraction": float((di.ice["concentration"].data > 0).double().mean())}
+        # compute_net_sea_ice_fluxes! (top / bottom heat fluxes + face stresses over ice; 12 reads + 4 writes per cell)
+        net_i, io_i = di.net_sea_ice_fluxes(), di.ice_ocean_fluxes()
+        tni = []
+        for k in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); ei.compute_net_sea_ice_fluxes(xch_i, oc_i, ice, ai_i, io_i, net_i, st); b.record(st)
+            torch.cuda.synchronize()
+            if k >= 3:
+                tni.append(a.elapsed_time(b))
+        tnim = float(np.mean(tni))
+        extras["net_sea_ice_fluxes_kernel_f64"] = {"ms": tnim, "algorithmic_bytes_per_cell": 16 * 8 + 1,
+                                                   "achieved_GBs": cells_global * 129 / (tnim * 1e-3) / 1e9,
+                                                   "roofline_frac": cells_global * 129 / (tnim * 1e-3) / 1e9 / peak}
         ei.close(); del di, hi, T0
 
     multi_gpu_check = None

@@ -892,11 +892,25 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   long long grid = grid_for(n, TILE);
   b.tile_cells = 0;
   static const bool balance = [] { const char* e = std::getenv("COFLUX_BALANCE"); return !(e && e[0] == '0'); }();
+  b.stagger = 0;
+  // COFLUX_STAGGER=1: staggered start of the CTAs that share an SM (see flux_tile_kernel), for launches of ≥ 2 waves
+  static const int stagger = [] { const char* e = std::getenv("COFLUX_STAGGER"); return e ? atoi(e) : 0; }();   // 2: interleaved
   if (balance && n > slots * (TILE / 4)) {
     const long long waves = (n + slots * TILE - 1) / (slots * TILE);
-    const long long per = (n + waves * slots - 1) / (waves * slots);           // cells per CTA, ≤ TILE
-    b.tile_cells = (int)per;
-    grid = (n + per - 1) / per;
+    long long per = (n + waves * slots - 1) / (waves * slots);                 // cells per CTA, ≤ TILE
+    const int m = TT::MIN_BLOCKS, S = sm_count[dev & 63];
+    if (stagger && waves >= 2 && m >= 2 && S < 65536) {
+      const long long unit = 8 * m;                                            // fractions of a tile stay multiples of 8 cells
+      per = std::min<long long>((per + unit - 1) / unit * unit, TILE / unit * unit);
+      const long long full = (n + per - 1) / per;                              // full-tile equivalents needed
+      const long long nmid = std::max<long long>(0, full - (long long)m * S);
+      b.tile_cells = (int)per;
+      b.stagger = m << 16 | S | (stagger == 2 ? 1 << 24 : 0);
+      grid = (long long)m * S + nmid + (long long)(m - 1) * S;
+    } else {
+      b.tile_cells = (int)per;
+      grid = (n + per - 1) / per;
+    }
   }
   kern<<<(unsigned)grid, TT::NT, smem, st>>>(b);
   return COFLUX_OK;
@@ -1036,6 +1050,9 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
     CUDA_TRY(cudaGetDevice(&dev));
     if (!(configured >> (dev & 63) & 1ull)) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      // no shared-memory carve-out preference: the pass reads its log / exp / ψ tables from global memory through L1, and
+      // giving the L1 up costs more than larger tiles gain (measured, 1/12° Float64, 92 % ice cover: tile 256 at the
+      // default carve-out 16.9 ms; at the maximum carve-out tile 256 18.3 ms, 320 × 5 CTAs 17.8, 384 17.0, 512 × 3 CTAs 18.8)
       configured |= 1ull << (dev & 63);
     }
     kern<<<grid_for(a.ncell, TILE), 128, smem, st>>>(a);

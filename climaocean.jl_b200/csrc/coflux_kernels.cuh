@@ -84,7 +84,7 @@ template <typename FT> struct FluxArgs {
   long long cell0, ncell;   // linear cell range [cell0, ncell) of the ring-extended surface handled by this launch
   // balanced tiling of the tile kernel: every CTA takes tile_cells ≤ TILE cells, chosen by the host so that the grid is a
   // whole number of waves of resident CTAs (0: TILE cells per CTA)
-  int tile_cells, pad_;
+  int tile_cells, stagger;     // balanced tiling: cells per CTA; stagger = m << 16 | S (launch_tile_spec), 0 = none
   // a3 inputs
   DSeries su, sv, sT, sq, sp, sQs, sQl, srain, ssnow;
   DArr fi, fj, cs, sn;

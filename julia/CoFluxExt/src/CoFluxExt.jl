@@ -102,6 +102,15 @@ struct InterfaceFluxes; latent_heat::CofluxArray; sensible_heat::CofluxArray; wa
                         interface_temperature::CofluxArray; friction_velocity::CofluxArray; temperature_scale::CofluxArray; humidity_scale::CofluxArray; iterations::CofluxArray; end
 struct NetOceanFluxes;  u::CofluxArray; v::CofluxArray; T::CofluxArray; S::CofluxArray; upwelling_longwave::CofluxArray; downwelling_longwave::CofluxArray
                         downwelling_shortwave::CofluxArray; penetrating_shortwave::CofluxArray; end
+struct SeaIceState;     thickness::CofluxArray; previous_thickness::CofluxArray; concentration::CofluxArray; salinity::CofluxArray
+                        u::CofluxArray; v::CofluxArray; top_temperature::CofluxArray; snow_thickness::CofluxArray; albedo::CofluxArray; end
+struct IceOceanFluxes;  frazil_heat::CofluxArray; interface_heat::CofluxArray; salt::CofluxArray; x_momentum::CofluxArray; y_momentum::CofluxArray; end
+struct NetSeaIceFluxes; top_heat::CofluxArray; bottom_heat::CofluxArray; top_u::CofluxArray; top_v::CofluxArray; end        # ABI 2
+struct FluxAverages                                   # ABI 2: WindowedTimeAverage accumulators (omip_diagnostics.jl:125-158)
+    tau_x::CofluxArray; tau_y::CofluxArray; JT::CofluxArray; JS::CofluxArray; Qc::CofluxArray; Qv::CofluxArray
+    JT_atmosphere_ocean::CofluxArray; JT_ice_ocean::CofluxArray; JS_ice_ocean::CofluxArray; JT_frazil::CofluxArray
+    previous_interval::Float64; dt::Float64
+end
 struct UpdateInputs;    atmosphere::Ptr{AtmosSeries}; ocean::Ptr{OceanSurface}; sea_ice::Ptr{Cvoid}; ice_ocean::Ptr{Cvoid}; land::Ptr{LandSeries}; end
 struct UpdateOutputs;   exchange::Ptr{ExchangeState}; atmosphere_ocean::Ptr{InterfaceFluxes}; net_ocean::Ptr{NetOceanFluxes}; end
 
@@ -109,7 +118,8 @@ function __init__()
     for (name, T) in (("array", CofluxArray), ("atmos_series", AtmosSeries), ("exchange_state", ExchangeState),
                       ("ocean_surface", OceanSurface), ("interface_fluxes", InterfaceFluxes),
                       ("net_ocean_fluxes", NetOceanFluxes), ("update_inputs", UpdateInputs), ("update_outputs", UpdateOutputs),
-                      ("land_series", LandSeries))
+                      ("land_series", LandSeries), ("sea_ice_state", SeaIceState), ("ice_ocean_fluxes", IceOceanFluxes),
+                      ("net_sea_ice_fluxes", NetSeaIceFluxes), ("flux_averages", FluxAverages))
         n = ccall((:coflux_sizeof, libcoflux), Cint, (Cstring,), name)
         n == sizeof(T) || error("CoFluxExt: layout of $name drifted (Julia $(sizeof(T)) B, library $n B)")
     end
@@ -196,6 +206,50 @@ function normalize_salinity!(n, sim; area::CofluxArray, mask::CofluxArray = NULL
                 ctx.handle, norm, Ptr{Cvoid}(UInt(CUDA.stream().handle))))
     # distributed: coflux_salinity_flux_sums → MPI.Allreduce!(sums, +, comm) → coflux_subtract_mean_flux
     return nothing
+end
+
+
+# compute_net_sea_ice_fluxes! (ABI 2) — what the coupled model hands to ClimaSeaIce after the flux solves.  UNEXECUTED.
+function compute_net_sea_ice_fluxes!(ctx::CofluxContext, xch::Ref{ExchangeState}, oc::Ref{OceanSurface}, ice::Ref{SeaIceState},
+                                     ai::Ref{InterfaceFluxes}, io::Ref{IceOceanFluxes}, net::Ref{NetSeaIceFluxes})
+    check(ccall((:coflux_assemble_net_sea_ice_fluxes, libcoflux), Cint,
+                (Ptr{Cvoid}, Ref{ExchangeState}, Ref{OceanSurface}, Ref{SeaIceState}, Ref{InterfaceFluxes}, Ref{IceOceanFluxes},
+                 Ref{NetSeaIceFluxes}, Ptr{Cvoid}),
+                ctx.handle, xch, oc, ice, ai, io, net, Ptr{Cvoid}(UInt(CUDA.stream().handle))))
+end
+
+# Time-averaged flux outputs (ABI 2): attach once per collection with the seconds already in the window and this Δt;
+# the next update_state! / compute_sea_ice_ocean_fluxes! update the running means in their epilogues.  UNEXECUTED.
+attach_flux_averages!(ctx::CofluxContext, avg::Ref{FluxAverages}) =
+    check(ccall((:coflux_attach_flux_averages, libcoflux), Cint, (Ptr{Cvoid}, Ref{FluxAverages}), ctx.handle, avg))
+detach_flux_averages!(ctx::CofluxContext) =
+    check(ccall((:coflux_attach_flux_averages, libcoflux), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.handle, C_NULL))
+
+# Device forcing window (ABI 2): `time_indices_in_memory` levels of every series in a device ring, uploads on the
+# window's own copy stream, ordered against the compute stream by events.  UNEXECUTED.
+mutable struct ForcingWindow
+    handle :: Ptr{Cvoid}
+end
+function ForcingWindow(ctx::CofluxContext, n_fields::Integer, plane_elements::Integer, capacity::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:coflux_forcing_window_create, libcoflux), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int32, Int64, Int32),
+                h, ctx.handle, n_fields, plane_elements, capacity))
+    w = ForcingWindow(h[])
+    finalizer(x -> ccall((:coflux_forcing_window_destroy, libcoflux), Cint, (Ptr{Cvoid},), x.handle), w)
+    return w
+end
+upload!(w::ForcingWindow, level::Integer, host_planes::Vector{Ptr{Cvoid}}) =      # pinned host planes, one per field
+    check(ccall((:coflux_forcing_window_upload, libcoflux), Cint, (Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}), w.handle, level, host_planes))
+wait_levels!(w::ForcingWindow, first::Integer, last::Integer) =
+    check(ccall((:coflux_forcing_window_wait, libcoflux), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                w.handle, first, last, Ptr{Cvoid}(UInt(CUDA.stream().handle))))
+release_levels!(w::ForcingWindow, first::Integer, last::Integer) =
+    check(ccall((:coflux_forcing_window_release, libcoflux), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                w.handle, first, last, Ptr{Cvoid}(UInt(CUDA.stream().handle))))
+function field_pointer(w::ForcingWindow, field::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:coflux_forcing_window_field, libcoflux), Cint, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), w.handle, field, p))
+    return p[]        # capacity × plane_elements elements; describe it with CofluxArray(...; stride_n = plane_elements) and ring_start / ring_capacity
 end
 
 end # module

@@ -11,13 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
-    "base_park": [],
-    "carry2_320x2_896": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_CELLS64=896", "COFLUX_TILE_CELLS64_S2=768"],
-    "carry2_320x2_960_k5": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_CELLS64=960", "COFLUX_PSI_SM_KHI=5", "COFLUX_TILE_CELLS64_S2=768"],
-    "io32_512": ["COFLUX_IOB_W32=512"],
-    "io32_384": ["COFLUX_IOB_W32=384"],
-    "io32_576": ["COFLUX_IOB_W32=576"],
-    "carry2_384x2_896_r80": ["COFLUX_TILE_CARRY2=1", "COFLUX_TILE_NT64=384", "COFLUX_TILE_CELLS64=896", "COFLUX_TILE_CELLS64_S2=768"],
+    "base": [],
+    "ice384x4": ["COFLUX_ICE_TILE_CELLS=384"],
+    "ice512x3": ["COFLUX_ICE_TILE_CELLS=512", "COFLUX_ICE_MIN_BLOCKS=3"],
+    "ice256x5": ["COFLUX_ICE_MIN_BLOCKS=5"],
+    "ice320x5": ["COFLUX_ICE_TILE_CELLS=320", "COFLUX_ICE_MIN_BLOCKS=5"],
 }
 
 
