@@ -509,13 +509,14 @@ def main():
             ef.update_state(inp_f, out_f, QUERY_TIME, torch.cuda.current_stream())
             torch.cuda.synchronize()
             nx = NX // world
-            bad = []
+            bad, bad_fields = [], {}
             for r in range(world):
                 want = [bit_checksum(getattr(df, g)[n], r * nx, (r + 1) * nx) for g, n in CHECK_FIELDS]
                 got = [int(v) for v in allsums[r].tolist()]
                 if want != got:
                     bad.append(r)
-            multi_gpu_check = {"bitwise_match_vs_single_gpu": not bad, "mismatching_slabs": bad,
+                    bad_fields[str(r)] = [f"{g}.{n}" for (g, n), w_, g_ in zip(CHECK_FIELDS, want, got) if w_ != g_]
+            multi_gpu_check = {"bitwise_match_vs_single_gpu": not bad, "mismatching_slabs": bad, "mismatching_fields": bad_fields,
                                "fields": [f"{g}.{n}" for g, n in CHECK_FIELDS],
                                "how": "sum of raw bit patterns (mod 2^64) of every slab's interior vs the same columns of a one-GPU solve of the whole grid"}
             ef.close(); del df, hf

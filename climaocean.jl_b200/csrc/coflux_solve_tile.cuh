@@ -571,7 +571,11 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
                                    instead of being re-read / parked in the ρτ output arrays (A/B knob) */
 #endif
 #ifndef COFLUX_TILE_PRE1
-#define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A (A/B knob) */
+#define COFLUX_TILE_PRE1 1     /* first pass in lock step in phase A; 0: every pass in phase B and 16 B per queued cell less (A/B knob) */
+#endif
+#ifndef COFLUX_TILE_C2CONST
+#define COFLUX_TILE_C2CONST 0  /* lean pass: the q★ coefficient of b★ is g·δ for every cell (it is (g/T_v)·(δ·T_v) up to rounding): 8 B per
+                                  queued cell less (A/B knob) */
 #endif
 #ifndef COFLUX_TILE_NT64
 #define COFLUX_TILE_NT64 320
@@ -612,10 +616,10 @@ template <> __device__ __forceinline__ bool same_bits<float>(float a, float b) {
 // element; the lines are still in L2 when phase C overwrites them with the stresses), not in shared memory: 16 B per
 // cell less, i.e. more cells per lane for the same footprint.
 template <typename FT, int TILE, bool VARNU, bool LEAN> struct TileSmem {
-  FT U2[TILE], dth[TILE], dq[TILE], c1[TILE], c2[TILE];
+  FT U2[TILE], dth[TILE], dq[TILE], c1[TILE], c2[(LEAN && COFLUX_TILE_C2CONST) ? 1 : TILE];
   FT nu[VARNU ? TILE : 1];                                // air viscosity at T_s (only when it varies)
   FT inu[(LEAN && VARNU) ? TILE : 1];                     // 1/ν (lean pass)
-  FT us1[LEAN ? TILE : 1], chi1[LEAN ? TILE : 1];         // state after the lock-step first pass (lean pass)
+  FT us1[(LEAN && COFLUX_TILE_PRE1) ? TILE : 1], chi1[(LEAN && COFLUX_TILE_PRE1) ? TILE : 1];   // state after the lock-step first pass (lean pass)
   FT du[COFLUX_TILE_CARRY2 ? TILE : 1], dv[COFLUX_TILE_CARRY2 ? TILE : 1], rho[COFLUX_TILE_CARRY2 ? TILE : 1], cp[COFLUX_TILE_CARRY2 ? TILE : 1];
   unsigned short queue[TILE];
   int n_front, n_back, head[2];     // head[0]: next unstable cell (front of the queue), head[1]: next stable cell (back)
@@ -774,7 +778,7 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
         FT c1, c2;
         if constexpr (LEAN) {    // b★ = c1·θ★ + c2·q★
           const FT gTv = P.g * fm::rcp(S.T_v);
-          c1 = gTv * (FT(1) + delta * S.q_vap); c2 = gTv * (delta * S.T_v);
+          c1 = gTv * (FT(1) + delta * S.q_vap); c2 = COFLUX_TILE_C2CONST ? P.g * delta : gTv * (delta * S.T_v);
           const FT inv_nu = VARNU ? fm::rcp(S.nu_m) : K.inv_nu;
           if (VARNU) sm.inu[cidx] = inv_nu;
           // first pass, in lock step (every lane busy, one code path)
@@ -791,10 +795,11 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
             queued = false;
             sm.U2[cidx] = us; sm.dth[cidx] = ts; sm.dq[cidx] = qs; SI::set(sm.c1[cidx], 1);
           }
-          sm.us1[cidx] = pre ? us : FT(-1); sm.chi1[cidx] = chi;
+          if constexpr (COFLUX_TILE_PRE1 != 0) { sm.us1[cidx] = pre ? us : FT(-1); sm.chi1[cidx] = chi; }
         } else { c1 = S.T_v; c2 = S.q_vap; }
         if (queued) {
-          sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.c1[cidx] = c1; sm.c2[cidx] = c2;
+          sm.U2[cidx] = U2; sm.dth[cidx] = S.dtheta; sm.dq[cidx] = S.dq; sm.c1[cidx] = c1;
+          if constexpr (!(LEAN && COFLUX_TILE_C2CONST)) sm.c2[cidx] = c2;
           if (VARNU) sm.nu[cidx] = S.nu_m;
           // stability class of every later pass: sign of the buoyancy scale ∝ Δθ·a1 + a2·Δq (χ_θ = χ_q > 0)
           const bool unstable = LEAN ? ((S.dtheta * c1 + c2 * S.dq) < FT(0)) : ((S.dtheta * (FT(1) + delta * S.q_vap) + (delta * S.T_v) * S.dq) < FT(0));
@@ -847,12 +852,15 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
       slot = -1;
       if (pos < (cls ? n_back : n_front)) {
         slot = cls ? sm.queue[TILE - 1 - pos] : sm.queue[pos];
-        lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.c1[slot]; lc.cb2 = sm.c2[slot];
+        lc.U2 = sm.U2[slot]; lc.dth = sm.dth[slot]; lc.dq = sm.dq[slot]; lc.cb1 = sm.c1[slot];
+        if constexpr (COFLUX_TILE_C2CONST != 0) lc.cb2 = P.g * delta; else lc.cb2 = sm.c2[slot];
         { const FT v = fm::fma_(F.ugmin, F.ugmin, lc.U2); lc.Ustab = (v > FT(0)) ? fm::sqrt(v) : FT(0); }
         if (VARNU) { nu = sm.nu[slot]; lc.inv_nu = sm.inu[slot]; lc.bnu = F.mr.beta_s * nu; }
-        us = sm.us1[slot];
-        if (us >= FT(0)) { const FT chi = sm.chi1[slot]; ts = chi * lc.dth; qs = chi * lc.dq; it = 1; }
-        else { us = ts = qs = F.init; it = 0; }
+        if constexpr (COFLUX_TILE_PRE1 != 0) {
+          us = sm.us1[slot];
+          if (us >= FT(0)) { const FT chi = sm.chi1[slot]; ts = chi * lc.dth; qs = chi * lc.dq; it = 1; }
+          else { us = ts = qs = F.init; it = 0; }
+        } else { us = ts = qs = F.init; it = 0; }
       }
     };
     // rare tail of a cell's iteration: the Brent bookkeeping lives in the cell's own shared-memory slots

@@ -135,8 +135,10 @@ class LatitudeLongitudeGrid:
         return (self.Nx, self.Ny, self.Nz)
 
     def lambda_centers(self, i):
-        L0, L1 = self.longitude
-        return L0 + (np.asarray(i, dtype=np.float64) + 0.5) * ((L1 - L0) / self.Nx)
+        # a slab evaluates the GLOBAL grid's expression at its global column index, so that its coordinates — and the
+        # fractional source indices built from them — carry the same bits as a one-process solve of the whole grid
+        L0, L1 = self.global_longitude or self.longitude
+        return L0 + (np.asarray(i, dtype=np.float64) + self.i_offset + 0.5) * ((L1 - L0) / (self.global_Nx or self.Nx))
 
     def phi_centers(self, j):
         P0, P1 = self.latitude
@@ -156,7 +158,8 @@ class LatitudeLongitudeGrid:
         dphi = (P1 - P0) / self.Ny
         j = np.arange(-Hy, self.Ny + Hy, dtype=np.float64)
         south, north = np.deg2rad(P0 + j * dphi), np.deg2rad(P0 + (j + 1.0) * dphi)
-        dlam = np.deg2rad((self.longitude[1] - self.longitude[0]) / self.Nx)
+        L0, L1 = self.global_longitude or self.longitude
+        dlam = np.deg2rad((L1 - L0) / (self.global_Nx or self.Nx))
         return (radius ** 2 * dlam * (np.sin(north) - np.sin(south))).astype(self.dtype)
 
     def slab(self, rank, world_size):
@@ -169,10 +172,12 @@ class LatitudeLongitudeGrid:
                                   self.latitude, self.z, self.halo, self.dtype)
         g.i_offset = rank * nx
         g.global_Nx = self.Nx
+        g.global_longitude = self.longitude
         return g
 
     i_offset = 0
     global_Nx = None
+    global_longitude = None
 
 
 def fractional_indices(grid, source_Nx, source_Ny, ring=1, source_longitude=(0.0, 360.0),

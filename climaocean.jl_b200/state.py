@@ -152,7 +152,7 @@ class SurfaceFluxData:
         g0 = self.grid
         assert g0.Nz == 1 and g0.halo[2] == 0
         g = LatitudeLongitudeGrid((g0.Nx, g0.Ny, Nz), g0.longitude, g0.latitude, g0.z, (g0.halo[0], g0.halo[1], Hz), g0.dtype)
-        g.i_offset, g.global_Nx = g0.i_offset, g0.global_Nx
+        g.i_offset, g.global_Nx, g.global_longitude = g0.i_offset, g0.global_Nx, g0.global_longitude
         o = self.to(device)
         o.grid = g
         tdt = torch.float64 if np.dtype(self.dtype) == np.float64 else torch.float32

@@ -1,4 +1,6 @@
-"""Committed golden fixtures (tests/golden/*.npz — ORACLE-generated, see make_golden.py).
+"""Committed fixtures (tests/golden/*.npz — ORACLE-generated, see make_golden.py): SELF-CONSISTENCY only.  They guard the
+oracle and the CUDA path against drift between commits; they say nothing about agreement with the Julia reference
+(tests/test_julia_golden.py is the slot for reference-generated vectors).
 CPU: the oracle still reproduces them (to 1e-13 in Float64 — glibc's libm dispatches FMA / non-FMA
 variants per host CPU, so bitwise equality across machines is not guaranteed).  GPU: the CUDA path matches them within the
 north_star tolerances without executing the oracle."""
@@ -14,7 +16,7 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_oracle_reproduces_golden(name):
+def test_self_consistency_oracle_reproduces_its_own_fixture(name):
     gold = np.load(os.path.join(HERE, name + ".npz"))
     res = run_case(CASES[name])
     bits = CASES[name]["bits"]
@@ -28,7 +30,7 @@ def test_oracle_reproduces_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_cuda_matches_golden(name):
+def test_self_consistency_cuda_matches_oracle_generated_fixture(name):
     spec = CASES[name]
     gold = np.load(os.path.join(HERE, name + ".npz"))
     grid, host, cfg = make_case(spec["Nx"], spec["Ny"], spec["Nz"], spec["bits"], flux_configuration=spec["flux_configuration"])

@@ -83,3 +83,28 @@ def test_two_slabs_reproduce_the_single_domain_solve(mode):
         assert np.array_equal(a, b), (mode, n)
     if mode == "seam":
         assert seam_bytes == (20 + 2 * 4) * 8          # one column of ρτx, Float64, halo rows included
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_slab_coordinates_carry_the_bits_of_the_global_grid(world):
+    """At 1/12° Δλ = 360/4320 is not representable: a slab that evaluated λ from its own west edge would get fractional
+    source indices one ulp away from the one-process solve (seen as a checksum mismatch of slab 1 in bench.py --gpus 2).
+    Slabs evaluate the global expression at the global column index instead."""
+    import climaocean.jl_b200 as cj
+    from climaocean.jl_b200.fields import fractional_indices
+    full = cj.LatitudeLongitudeGrid((4320, 60, 1), latitude=(-75.0, 75.0), halo=(7, 7, 0))
+    FI, FJ = fractional_indices(full, 640, 320)
+    for rank in range(world):
+        g = full.slab(rank, world)
+        fi, fj = fractional_indices(g, 640, 320)
+        nx = g.Nx
+        assert np.array_equal(fi[0, :, 1:-1], FI[0, :, 1 + rank * nx:1 + (rank + 1) * nx])
+        assert np.array_equal(fi[0, :, 0], FI[0, :, rank * nx]) and np.array_equal(fi[0, :, -1], FI[0, :, 1 + (rank + 1) * nx])
+        assert np.array_equal(fj, FJ[:, :, :nx + 2])
+        assert np.array_equal(g.horizontal_areas(), full.horizontal_areas())
+        host = cj.SurfaceFluxData.synthetic(g, ring=1)
+        ref = cj.SurfaceFluxData.synthetic(full, ring=1) if rank == 0 else ref
+        for n in ("u", "v", "T", "S"):
+            a, b = host.ocean[n].numpy(), ref.ocean[n].numpy()
+            H = 7
+            assert np.array_equal(a[:, :, H:-H], b[:, :, H + rank * nx:H + (rank + 1) * nx]), n

@@ -12,10 +12,11 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
     "base": [],
-    "ice384x4": ["COFLUX_ICE_TILE_CELLS=384"],
-    "ice512x3": ["COFLUX_ICE_TILE_CELLS=512", "COFLUX_ICE_MIN_BLOCKS=3"],
-    "ice256x5": ["COFLUX_ICE_MIN_BLOCKS=5"],
-    "ice320x5": ["COFLUX_ICE_TILE_CELLS=320", "COFLUX_ICE_MIN_BLOCKS=5"],
+    "pre0_1280": ["COFLUX_TILE_PRE1=0"],
+    "pre0_1920": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_CELLS64=1920"],
+    "pre0_c2c_2240": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=2240"],
+    "pre0_c2c_2496": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=2496"],
+    "pre1_c2c_1600": ["COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=1600"],
 }
 
 
