@@ -853,9 +853,51 @@ template <typename FT> static bool ice_tile_eligible(const coflux_ctx* c) {
          F.stop_kind == COFLUX_STOP_CONVERGENCE && F.maxit >= 1;
 }
 // (the tile kernel parks ρ_a, c_p,m in the ρτx / ρτy output arrays between its phases: both must be present)
-template <typename FT> static bool tile_eligible(const coflux_ctx* c, const FluxArgs<FT>& a) {
+// Uniform layout of the tile kernel (FluxArgs::usj, ssj): every 2-D surface array it touches is contiguous in i with one
+// and the same row pitch, and so are the atmosphere series among themselves — the case for Oceananigans parents living on
+// one grid.  Anything else (transposed or differently padded fields) takes the one-cell-per-thread kernel, which addresses
+// every array through its own strides.
+template <typename FT> static bool uniform_layout(FluxArgs<FT>& a) {
+  const DArr* s2[] = {&a.xu, &a.xv, &a.xT, &a.xp, &a.xq, &a.xQs, &a.xQl, &a.xMp, &a.ou, &a.ov, &a.oT, &a.oS,
+                      &a.Qv, &a.Qc, &a.Fv, &a.rtx, &a.rty, &a.Tsout, &a.ust, &a.tst, &a.qst, &a.conc, &a.Qio, &a.salt_io,
+                      &a.JT, &a.JS, &a.Qu, &a.Qal, &a.Qts, &a.J0,
+                      &a.avg.JT, &a.avg.JS, &a.avg.Qc, &a.avg.Qv, &a.avg.JTao, &a.avg.JTio, &a.avg.JSio};
+  int64_t pitch = 0;
+  for (const DArr* d : s2) {
+    if (!d->p) continue;
+    if (d->si != 1 || d->sj <= 0) return false;
+    if (!pitch) pitch = d->sj;
+    if (d->sj != pitch) return false;
+  }
+  if (!pitch || pitch * (int64_t)(a.nyr + 2) >= (int64_t)1 << 31) return false;
+  for (const DArr* d : {&a.mask, &a.iters})                  // uint8 / int32 planes: same ELEMENT layout
+    if (d->p && (d->si != 1 || d->sj != pitch)) return false;
+  a.usj = (int)pitch;
+  int64_t fp = 0;                                            // fi, fj, cos θ, sin θ: parents of the ring-extended surface
+  for (const DArr* d : {&a.fi, &a.fj, &a.cs, &a.sn}) {
+    if (!d->p) continue;
+    if (d->si != 1 || d->sj <= 0) return false;
+    if (!fp) fp = d->sj;
+    if (d->sj != fp) return false;
+  }
+  if (fp * (int64_t)(a.nyr + 2) >= (int64_t)1 << 31) return false;
+  a.fsj = (int)fp;
+  const DSeries* ss[] = {&a.su, &a.sv, &a.sT, &a.sq, &a.sp, &a.sQs, &a.sQl, &a.srain, &a.ssnow};
+  int64_t sp = 0;
+  for (const DSeries* d : ss) {
+    if (!d->p1) continue;
+    if (d->si != 1 || d->sj <= 0) return false;
+    if (!sp) sp = d->sj;
+    if (d->sj != sp) return false;
+  }
+  if (sp >= 46340) return false;                 // gather offsets j·ssj + i stay inside 32 bits for any source grid of < 46 340 rows
+  a.ssj = (int)sp;
+  return true;
+}
+template <typename FT> static bool tile_eligible(const coflux_ctx* c, FluxArgs<FT>& a) {
   const FluxP<FT>& F = dev_params<FT>(c).ao;
-  return !force_v1() && a.rtx.p && a.rty.p && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1;
+  return !force_v1() && a.rtx.p && a.rty.p && F.formulation == COFLUX_FLUXES_SIMILARITY_THEORY && F.itemp == COFLUX_TEMPERATURE_BULK && F.same_visc && F.maxit >= 1 &&
+         uniform_layout<FT>(a);
 }
 // compile-time specialisation of the hot loop for the OMIP parameter sets (0 = generic)
 template <typename FT> static int tile_spec(const coflux_ctx* c) {

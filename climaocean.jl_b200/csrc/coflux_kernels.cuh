@@ -85,6 +85,11 @@ template <typename FT> struct FluxArgs {
   // balanced tiling of the tile kernel: every CTA takes tile_cells ≤ TILE cells, chosen by the host so that the grid is a
   // whole number of waves of resident CTAs (0: TILE cells per CTA)
   int tile_cells, stagger;     // balanced tiling: cells per CTA; stagger = m << 16 | S (launch_tile_spec), 0 = none
+  // uniform layout (tile kernel; set by the host, which makes it a condition of tile eligibility): every 2-D surface array
+  // the kernel touches has stride_i == 1 and the SAME row pitch usj (elements) — true for Oceananigans parents on one grid —
+  // so a cell's element offset j·usj + i is computed once and shared by ≈ 70 loads and stores; ssj: the same for the
+  // atmosphere series (one gather-offset set for all nine).  32-bit: a plane has < 2³¹ elements (checked).
+  int usj, ssj, fsj;           // fsj: row pitch of fi, fj, cos θ, sin θ (ring-extended parents)
   // a3 inputs
   DSeries su, sv, sT, sq, sp, sQs, sQl, srain, ssnow;
   DArr fi, fj, cs, sn;
@@ -115,6 +120,18 @@ __device__ __forceinline__ FT interp_series(const DSeries& s, int i0, int j0, in
                                             FT w11, FT nfrac) {
   const int64_t o00 = (int64_t)i0 * s.si + (int64_t)j0 * s.sj, o01 = (int64_t)i0 * s.si + (int64_t)j1 * s.sj;
   const int64_t o10 = (int64_t)i1 * s.si + (int64_t)j0 * s.sj, o11 = (int64_t)i1 * s.si + (int64_t)j1 * s.sj;
+  const FT* a1 = reinterpret_cast<const FT*>(s.p1);
+  const FT* a2 = reinterpret_cast<const FT*>(s.p2);
+  FT v100 = __ldg(a1 + o00), v101 = __ldg(a1 + o01), v110 = __ldg(a1 + o10), v111 = __ldg(a1 + o11);
+  FT v200 = __ldg(a2 + o00), v201 = __ldg(a2 + o01), v210 = __ldg(a2 + o10), v211 = __ldg(a2 + o11);
+  FT p1 = w00 * v100 + w01 * v101 + w10 * v110 + w11 * v111;
+  FT p2 = w00 * v200 + w01 * v201 + w10 * v210 + w11 * v211;
+  return p2 * nfrac + p1 * (FT(1) - nfrac);
+}
+
+// the same with the four gather offsets given (uniform series layout: computed once for all series of a cell)
+template <typename FT>
+__device__ __forceinline__ FT interp_series_u(const DSeries& s, int o00, int o01, int o10, int o11, FT w00, FT w01, FT w10, FT w11, FT nfrac) {
   const FT* a1 = reinterpret_cast<const FT*>(s.p1);
   const FT* a2 = reinterpret_cast<const FT*>(s.p2);
   FT v100 = __ldg(a1 + o00), v101 = __ldg(a1 + o01), v110 = __ldg(a1 + o10), v111 = __ldg(a1 + o11);
@@ -192,6 +209,19 @@ __device__ __forceinline__ void avg_epilogue(const AvgArgs<FT>& g, int i, int j,
 #pragma unroll
   for (int k = 0; k < 7; ++k)
     if (p[k]) *p[k] = (old[k] * g.T + x[k] * g.dt) / (g.T + g.dt);
+}
+
+// the same with the cell's element offset given (uniform layout of the tile kernel)
+template <typename FT>
+__device__ __forceinline__ void avg_epilogue_u(const AvgArgs<FT>& g, int off, FT JT, FT JS, FT Qc, FT Qv, const FT* parts) {
+  const DArr* d[7] = {&g.JT, &g.JS, &g.Qc, &g.Qv, &g.JTao, &g.JTio, &g.JSio};
+  const FT x[7] = {JT, JS, Qc, Qv, parts[0], parts[1], parts[2]};
+  FT old[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) old[k] = d[k]->p ? reinterpret_cast<const FT*>(d[k]->p)[off] : FT(0);
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+    if (d[k]->p) reinterpret_cast<FT*>(d[k]->p)[off] = (old[k] * g.T + x[k] * g.dt) / (g.T + g.dt);
 }
 
 template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE>

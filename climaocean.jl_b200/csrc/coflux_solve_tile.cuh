@@ -718,48 +718,59 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
   const FT delta = c.eps - FT(1);
   const bool fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
 
+  // (ii, jj) of the tile's first cell: ONE 64-bit division per thread; a cell's own row / column follow from a 32-bit one
+  const int tile_jj0 = (int)(tile0 / a.nxr);
+  const int tile_ii0 = (int)(tile0 - (long long)tile_jj0 * a.nxr);
+  const unsigned nxr_u = (unsigned)a.nxr;
+
   // ------------------------------------------------------------------ phase A
   for (int cidx = tid; cidx < tile_n; cidx += NT) {
     const long long idx = tile0 + cidx;
     if (idx >= a.ncell) continue;
-    const int jj = (int)(idx / a.nxr);
-    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const unsigned t = (unsigned)(tile_ii0 + cidx), dj = t / nxr_u;
+    const int jj = tile_jj0 + (int)dj, ii = (int)(t - dj * nxr_u);
     const int i = ii - a.ring, j = jj - a.ring;
     FT ua, va, Ta, pa, qa;
+    const int off = j * a.usj + i;          // element offset of the cell in every 2-D surface array (uniform layout)
+    auto LD = [&](const DArr& d, int o) -> FT { return __ldg(reinterpret_cast<const FT*>(d.p) + o); };
+    auto ST = [&](const DArr& d, FT v) { if (d.p) reinterpret_cast<FT*>(d.p)[off] = v; };
     if (INTERP) {
-      const FT fi = ldgs<FT>(a.fi, i, j), fj = ldgs<FT>(a.fj, i, j);
+      const int foff = j * a.fsj + i;
+      const FT fi = LD(a.fi, foff), fj = LD(a.fj, foff);
       const int i0 = (int)M<FT>::trunc(fi), j0 = (int)M<FT>::trunc(fj);
       const int i1 = i0 + ((fi > FT(0)) - (fi < FT(0))), j1 = j0 + ((fj > FT(0)) - (fj < FT(0)));
       const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
       const FT w00 = (FT(1) - xi) * (FT(1) - eta), w01 = (FT(1) - xi) * eta, w10 = xi * (FT(1) - eta), w11 = xi * eta;
-      ua = interp_series<FT>(a.su, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      va = interp_series<FT>(a.sv, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      Ta = interp_series<FT>(a.sT, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      qa = interp_series<FT>(a.sq, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      pa = interp_series<FT>(a.sp, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      const FT Qs = interp_series<FT>(a.sQs, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      const FT Ql = interp_series<FT>(a.sQl, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+      const int o00 = j0 * a.ssj + i0, o01 = j1 * a.ssj + i0, o10 = j0 * a.ssj + i1, o11 = j1 * a.ssj + i1;   // one set for all series
+      ua = interp_series_u<FT>(a.su, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      va = interp_series_u<FT>(a.sv, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      Ta = interp_series_u<FT>(a.sT, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      qa = interp_series_u<FT>(a.sq, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      pa = interp_series_u<FT>(a.sp, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      const FT Qs = interp_series_u<FT>(a.sQs, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      const FT Ql = interp_series_u<FT>(a.sQl, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
       FT Mp = FT(0);
-      if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-      if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-          if (a.lfi.p) Mp += land_freshwater<FT>(a, i, j);
+      if (a.srain.p1) Mp += interp_series_u<FT>(a.srain, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      if (a.ssnow.p1) Mp += interp_series_u<FT>(a.ssnow, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      if (a.lfi.p) Mp += land_freshwater<FT>(a, i, j);
       if (a.cs.p && a.sn.p) {
-        const FT cs = ldgs<FT>(a.cs, i, j), sn = ldgs<FT>(a.sn, i, j);
+        const FT cs = LD(a.cs, foff), sn = LD(a.sn, foff);
         const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
         ua = ur; va = vr;
       }
-      stg<FT>(a.xu, i, j, ua); stg<FT>(a.xv, i, j, va); stg<FT>(a.xT, i, j, Ta); stg<FT>(a.xp, i, j, pa);
-      stg<FT>(a.xq, i, j, qa); stg<FT>(a.xQs, i, j, Qs); stg<FT>(a.xQl, i, j, Ql); stg<FT>(a.xMp, i, j, Mp);
+      ST(a.xu, ua); ST(a.xv, va); ST(a.xT, Ta); ST(a.xp, pa);
+      ST(a.xq, qa); ST(a.xQs, Qs); ST(a.xQl, Ql); ST(a.xMp, Mp);
     } else {
-      ua = ldgs<FT>(a.xu, i, j); va = ldgs<FT>(a.xv, i, j); Ta = ldgs<FT>(a.xT, i, j); pa = ldgs<FT>(a.xp, i, j);
-      qa = ldgs<FT>(a.xq, i, j);
+      ua = LD(a.xu, off); va = LD(a.xv, off); Ta = LD(a.xT, off); pa = LD(a.xp, off);
+      qa = LD(a.xq, off);
     }
     bool queued = false, finished_in_a = false;
-    if (is_active(a.mask, i, j)) {
-      const FT uo = (ldgs<FT>(a.ou, i, j) + ldgs<FT>(a.ou, i + 1, j)) * FT(0.5);
-      const FT vo = (ldgs<FT>(a.ov, i, j) + ldgs<FT>(a.ov, i, j + 1)) * FT(0.5);
-      const FT Ts = ldgs<FT>(a.oT, i, j) + P.T_offset;
-      const FT So = ldgs<FT>(a.oS, i, j);
+    const bool wet = !a.mask.p || __ldg(reinterpret_cast<const uint8_t*>(a.mask.p) + off) != 0;
+    if (wet) {
+      const FT uo = (LD(a.ou, off) + LD(a.ou, off + 1)) * FT(0.5);
+      const FT vo = (LD(a.ov, off) + LD(a.ov, off + a.usj)) * FT(0.5);
+      const FT Ts = LD(a.oT, off) + P.T_offset;
+      const FT So = LD(a.oS, off);
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) { du = ua - uo; dv = va - vo; } else { du = ua; dv = va; }
       const FT U2 = du * du + dv * dv;
@@ -771,7 +782,7 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
 #if COFLUX_TILE_CARRY2
       sm.du[cidx] = du; sm.dv[cidx] = dv; sm.rho[cidx] = atm.rho; sm.cp[cidx] = atm.cp_m;
 #else
-      stg<FT>(a.rtx, i, j, atm.rho); stg<FT>(a.rty, i, j, atm.cp_m);     // parked for phase C (see TileSmem)
+      ST(a.rtx, atm.rho); ST(a.rty, atm.cp_m);     // parked for phase C (see TileSmem)
 #endif
       if (fixed ? (F.maxit > 0) : true) {
         queued = true;
@@ -810,7 +821,7 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
       }
     }
     if (!queued && !finished_in_a) {      // finished on the spot: land, or a zero-pass solve
-      const FT r0 = is_active(a.mask, i, j) ? F.init : FT(0);
+      const FT r0 = wet ? F.init : FT(0);
       sm.U2[cidx] = r0; sm.dth[cidx] = r0; sm.dq[cidx] = r0; SI::set(sm.c1[cidx], 0);
     }
   }
@@ -975,28 +986,32 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
   for (int cidx = tid; cidx < tile_n; cidx += NT) {
     const long long idx = tile0 + cidx;
     if (idx >= a.ncell) continue;
-    const int jj = (int)(idx / a.nxr);
-    const int ii = (int)(idx - (long long)jj * a.nxr);
+    const unsigned t = (unsigned)(tile_ii0 + cidx), dj = t / nxr_u;
+    const int jj = tile_jj0 + (int)dj, ii = (int)(t - dj * nxr_u);
     const int i = ii - a.ring, j = jj - a.ring;
-    const FT Tunits = ldg<FT>(a.oT, i, j);
-    const bool act = is_active(a.mask, i, j);
+    const int off = j * a.usj + i;          // uniform layout (see phase A)
+    auto LD = [&](const DArr& d, int o) -> FT { return __ldg(reinterpret_cast<const FT*>(d.p) + o); };
+    auto LDP = [&](const DArr& d) -> FT { return reinterpret_cast<const FT*>(d.p)[off]; };   // plain load: written by this thread in phase A
+    auto ST = [&](const DArr& d, FT v) { if (d.p) reinterpret_cast<FT*>(d.p)[off] = v; };
+    const FT Tunits = LD(a.oT, off);
+    const bool act = !a.mask.p || __ldg(reinterpret_cast<const uint8_t*>(a.mask.p) + off) != 0;
     FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0);
     const FT us = sm.U2[cidx], ts = sm.dth[cidx], qs = sm.dq[cidx];
     if (act) {
       // the exchange state was written by this very thread in phase A (or is an input): plain loads
-      const FT Ta = reinterpret_cast<const FT*>(a.xT.p)[(int64_t)i * a.xT.si + (int64_t)j * a.xT.sj];
+      const FT Ta = LDP(a.xT);
 #if COFLUX_TILE_CARRY2
       const FT du = sm.du[cidx], dv = sm.dv[cidx], rho = sm.rho[cidx], cp = sm.cp[cidx];
 #else
-      const FT ua = reinterpret_cast<const FT*>(a.xu.p)[(int64_t)i * a.xu.si + (int64_t)j * a.xu.sj];
-      const FT va = reinterpret_cast<const FT*>(a.xv.p)[(int64_t)i * a.xv.si + (int64_t)j * a.xv.sj];
+      const FT ua = LDP(a.xu);
+      const FT va = LDP(a.xv);
       FT du, dv;
       if (F.velocity == COFLUX_VELOCITY_RELATIVE) {
-        du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
-        dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+        du = ua - (LD(a.ou, off) + LD(a.ou, off + 1)) * FT(0.5);
+        dv = va - (LD(a.ov, off) + LD(a.ov, off + a.usj)) * FT(0.5);
       } else { du = ua; dv = va; }
-      const FT rho = reinterpret_cast<const FT*>(a.rtx.p)[(int64_t)i * a.rtx.si + (int64_t)j * a.rtx.sj];
-      const FT cp = reinterpret_cast<const FT*>(a.rty.p)[(int64_t)i * a.rty.si + (int64_t)j * a.rty.sj];
+      const FT rho = LDP(a.rtx);
+      const FT cp = LDP(a.rty);
 #endif
       FT taux, tauy;
       if constexpr (LEAN) {
@@ -1015,25 +1030,25 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
       Fv = -rho * us * qs;
       rtx = rho * taux; rty = rho * tauy;
     }
-    stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
-    stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tunits);
-    stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
-    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? SI::get(sm.c1[cidx]) : 0;
+    ST(a.Qv, Qv); ST(a.Qc, Qc); ST(a.Fv, Fv);
+    ST(a.rtx, rtx); ST(a.rty, rty); ST(a.Tsout, Tunits);
+    ST(a.ust, us); ST(a.tst, ts); ST(a.qst, qs);
+    if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[off] = act ? SI::get(sm.c1[cidx]) : 0;
     if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
     if (ASSEMBLE) {
       if (i >= 0 && i < a.Nx && j >= 0 && j < a.Ny) {
-        const FT Qs = reinterpret_cast<const FT*>(a.xQs.p)[(int64_t)i * a.xQs.si + (int64_t)j * a.xQs.sj];
-        const FT Ql = reinterpret_cast<const FT*>(a.xQl.p)[(int64_t)i * a.xQl.si + (int64_t)j * a.xQl.sj];
-        const FT Mp = reinterpret_cast<const FT*>(a.xMp.p)[(int64_t)i * a.xMp.si + (int64_t)j * a.xMp.sj];
-        const FT So = ldg<FT>(a.oS, i, j);
-        const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
-        const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
-        const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
+        const FT Qs = LDP(a.xQs);
+        const FT Ql = LDP(a.xQl);
+        const FT Mp = LDP(a.xMp);
+        const FT So = LD(a.oS, off);
+        const FT conc = a.conc.p ? LD(a.conc, off) : FT(0);
+        const FT Qio = a.Qio.p ? LD(a.Qio, off) : FT(0);
+        const FT sio = a.salt_io.p ? LD(a.salt_io, off) : FT(0);
         FT JT, JS, Qu, Qal, Qts, J0, parts[3];
         assemble_tracers<FT>(P, act, conc, So, Tunits + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio, JT, JS, Qu, Qal, Qts, J0, parts);
-        stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
-        stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
-            if (a.avg.on) avg_epilogue<FT>(a.avg, i, j, JT, JS, Qc, Qv, parts);
+        ST(a.JT, JT); ST(a.JS, JS); ST(a.Qu, Qu); ST(a.Qal, Qal);
+        ST(a.Qts, Qts); ST(a.J0, J0);
+        if (a.avg.on) avg_epilogue_u<FT>(a.avg, off, JT, JS, Qc, Qv, parts);
       }
     }
   }

@@ -200,3 +200,29 @@ def test_host_buffer_entry_matches_device_path(bits):
     for n, key in (("u", "net.u"), ("v", "net.v"), ("T", "net.T"), ("S", "net.S"), ("Qv", "ao.latent_heat"), ("Qc", "ao.sensible_heat")):
         got = outs[n].numpy()[H:-H, H:-H]
         assert rel_err(got, ref[key], bits) <= RTOL[bits], key
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_mixed_parent_layouts_take_the_strided_kernel(bits):
+    """The tile kernel shares one element offset among all 2-D surface arrays (uniform layout: what Oceananigans parents on
+    one grid have).  A caller whose fields are padded differently is still served — by the one-cell-per-thread kernel,
+    which addresses every array through its own strides — with the same results."""
+    import torch
+    from climaocean.jl_b200.fields import Field
+    grid, host, cfg = make_case(72, 30, 4, bits, land_fraction=0.2)
+    ref = oracle_update(host, cfg)
+    uniform, _ = gpu_update(host, cfg)
+    dev = host.to("cuda:0")
+    size2 = (grid.Nx, grid.Ny, 1)
+    dev.net["T"] = Field.zeros(size2, (9, 8, 0), dev.dtype, "cuda:0", "net_T_wide")                 # wider halo → other row pitch
+    dev.ao["latent_heat"] = Field.zeros(size2, (7, 11, 0), dev.dtype, "cuda:0", "Qv_tall")
+    eng = cj.Engine(cfg)
+    inp, out = dev.update_bundles()
+    eng.update_state(inp, out, QUERY_TIME)
+    torch.cuda.synchronize()
+    mixed = dev.outputs()
+    compare(mixed, ref, bits)
+    for k in ("net.T", "ao.latent_heat", "net.S", "net.u"):
+        assert mixed[k].shape == uniform[k].shape
+        assert rel_err(mixed[k], uniform[k], bits) <= RTOL[bits], k
+    eng.close()
