@@ -253,7 +253,12 @@ def cpu_baseline(host, cfg, target_seconds=12.0):
     while total_t < target_seconds * 0.8 and reps < 16:
         dt, cells = oracle_rate(host, cfg, rows, cores)
         total_t += dt; total_c += cells; reps += 1
+    # one core beside it: ≈ 2 s of the same rows
+    rows1 = int(max(4, min(Ny, rate / max(cores, 1) * 2.0 / Nx)))
+    dt1, cells1 = oracle_rate(host, cfg, rows1, 1)
+    pyoracle.set_threads(cores)
     return {"value": total_c / total_t / 1e6, "unit": "Mcells/s", "cores": cores, "kind": "port",
+            "single_core_value": cells1 / dt1 / 1e6,
             "build": "gcc -O3 -march=native -fopenmp (oracle/Makefile: fast), built on this host",
             "sample": f"CPU oracle (C restatement, OpenMP) update_state on the first {rows} of {Ny} latitude rows "
                       f"({Nx * rows} cells) of the same workload, {reps} pass(es), {total_t:.1f} s",
