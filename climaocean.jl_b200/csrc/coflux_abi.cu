@@ -842,6 +842,9 @@ static bool refill_v1() {
 #ifndef COFLUX_ICE_TILE_CELLS
 #define COFLUX_ICE_TILE_CELLS 256
 #endif
+#ifndef COFLUX_ICE_QUEUE_CELLS
+#define COFLUX_ICE_QUEUE_CELLS 8192    /* most cells of one CTA of ice_queue_kernel (2-byte queue entries in shared memory) */
+#endif
 template <typename FT> static bool ice_tile_eligible(const coflux_ctx* c) {
   static const bool off = [] { const char* e = std::getenv("COFLUX_ICE_TILE"); return e && e[0] == '0'; }();
   const FluxP<FT>& F = dev_params<FT>(c).ai;
@@ -1083,7 +1086,27 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
   if (rc) return rc;
   fill_interface_out<FT>(f, a);
   a.Ttop_out = view2d(ice->top_temperature, 0, es);
-  if (ice_tile_eligible<FT>(c)) {
+  // COFLUX_ICE_QUEUE=1: queue form (cells wait in global memory, thousands per tile; needs the six output arrays it parks a
+  // cell's state in).  Bit-identical, but SLOWER on B200 (1/12°, 92 % ice cover: 19.9 vs 16.9 ms `:default`, 15.2 vs 13.1
+  // `:corrected`, 13.3 vs 12.6 `:ncar`, Float32 13.6 vs 11.0): with ≈ one lane of a warp popping a cell per pass, the warp
+  // waits for a DRAM round trip per pass, which costs more than the idle lanes of the tile form.  Kept as an A/B knob.
+  static const bool queue_on = [] { const char* e = std::getenv("COFLUX_ICE_QUEUE"); return e && e[0] == '1'; }();
+  if (ice_tile_eligible<FT>(c) && queue_on && a.Qv.p && a.Qc.p && a.Fv.p && a.rtx.p && a.rty.p && a.Tsout.p) {
+    constexpr int TILE = COFLUX_ICE_QUEUE_CELLS;
+    static int sm_count[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!sm_count[dev & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    // every CTA the same number of cells: one wave when the grid fits (≥ 2 cells per lane), else a whole number of waves
+    const long long n = a.ncell - a.cell0, slots = (long long)sm_count[dev & 63] * COFLUX_ICE_MIN_BLOCKS;
+    long long per = std::max<long long>(256, (n + slots - 1) / slots);
+    if (per > TILE) {
+      const long long waves = (n + slots * TILE - 1) / (slots * TILE);
+      per = (n + waves * slots - 1) / (waves * slots);
+    }
+    a.tile_cells = (int)per;
+    ice_queue_kernel<FT, TILE><<<(unsigned)((n + per - 1) / per), 128, 0, st>>>(a);
+  } else if (ice_tile_eligible<FT>(c)) {
     constexpr int TILE = COFLUX_ICE_TILE_CELLS;
     auto kern = ice_tile_kernel<FT, TILE>;
     const size_t smem = sizeof(IceTileSmem<FT, TILE>);

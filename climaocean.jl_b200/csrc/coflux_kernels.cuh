@@ -588,6 +588,154 @@ __global__ void __launch_bounds__(128, COFLUX_ICE_MIN_BLOCKS) ice_tile_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Queue form of the same solve: the cells of a tile wait in GLOBAL memory, not in shared memory.
+// With 2–100 passes per cell (mean 29 in Float64, one cell in eight on a limit cycle) and the two cells per lane that
+// 134 B of shared memory per queued cell allow, ice_tile_kernel keeps only 15.5 of 32 lanes busy: every tile ends with a
+// long tail of a few slow cells (ncu, round 2).  Here phase A parks the five numbers init() derives (ρ_a, c_p,m, q_v, θ_a,
+// ‖Δu‖²) and the albedo in the cell's own elements of six OUTPUT arrays (Q_v, Q_c, F_v, ρτx, ρτy, T_s — overwritten with
+// the results when the cell finishes); everything else a pass needs is an input and is simply read again.  Shared memory
+// holds only the 2-byte queue entries, so a tile is thousands of cells (tens per lane) and the tail all but disappears.
+// Popping a cell costs 14 scattered loads, finishing one 6 loads + 11 scattered stores — against ≈ 29 passes of ≈ 800
+// instructions.  Phase C is gone: the lane that finishes a cell computes and stores its fluxes.  All arithmetic is
+// CellSolver's, in the same order: results are bit-identical to ice_tile_kernel and flux_kernel<FT,1,…>.
+// MEASURED (B200, round 2): lane occupancy does improve, the time does not — 19.9 ms against 16.9 ms for ice_tile_kernel at
+// 1/12° with 92 % ice cover.  About one lane of every warp pops a cell per pass, and its scattered loads stall the whole
+// warp for a memory round trip; the shared-memory pop of the tile form costs ≈ 30 cycles.  Opt-in: COFLUX_ICE_QUEUE=1.
+// ---------------------------------------------------------------------------------------------
+template <int TILE> struct IceQueueSmem {
+  unsigned short queue[TILE];
+  int n_queued, head;
+};
+template <typename FT> __device__ __forceinline__ FT ldc(const DArr& a, int i, int j) {      // coherent load (parked values)
+  return reinterpret_cast<const FT*>(a.p)[(int64_t)i * a.si + (int64_t)j * a.sj];
+}
+// fluxes and stores of one finished (or inactive) cell — phase C of ice_tile_kernel, cell by cell
+template <typename FT>
+__device__ __forceinline__ void ice_finish_cell(const FluxArgs<FT>& a, int i, int j, bool act, FT us, FT ts, FT qs, FT Ts, FT rho, FT cp, FT Ta, int it) {
+  const DevParams<FT>& P = a.P;
+  const FluxP<FT>& F = P.ai;
+  const FT Tunits = ldg<FT>(a.oT, i, j);
+  FT Qv = FT(0), Qc = FT(0), Fv = FT(0), rtx = FT(0), rty = FT(0), Tsout = Tunits;
+  if (act) {
+    const FT ua = ldg<FT>(a.xu, i, j), va = ldg<FT>(a.xv, i, j);
+    FT du, dv;
+    if (F.velocity == COFLUX_VELOCITY_RELATIVE) {
+      du = ua - (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+      dv = va - (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+    } else { du = ua; dv = va; }
+    const FT dU = M<FT>::sqrt(du * du + dv * dv);
+    const FT taux = (dU == FT(0)) ? dU : -us * us * du / dU;
+    const FT tauy = (dU == FT(0)) ? dU : -us * us * dv / dU;
+    const ThermoC<FT>& c = P.th;
+    const FT LH = c.LH_s0 + (c.cp_v - c.cp_i) * (Ta - c.T_0);
+    Qv = -rho * us * qs * LH;
+    Qc = -rho * cp * us * ts;
+    Fv = -rho * us * qs;
+    rtx = rho * taux; rty = rho * tauy;
+    Tsout = Ts - P.T_offset;
+  } else { us = ts = qs = FT(0); }
+  stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
+  stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tsout);
+  stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
+  stg<FT>(a.Ttop_out, i, j, Tsout);
+  if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = act ? it : 0;
+  if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
+}
+template <typename FT, int TILE>
+__global__ void __launch_bounds__(128, COFLUX_ICE_MIN_BLOCKS) ice_queue_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  __shared__ IceQueueSmem<TILE> sm;
+  const DevParams<FT>& P = a.P;
+  const FluxP<FT>& F = P.ai;
+  const int tid = threadIdx.x;
+  const int tile_n = (a.tile_cells > 0 && a.tile_cells < TILE) ? a.tile_cells : TILE;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * tile_n;
+  const int tile_jj0 = (int)(tile0 / a.nxr);
+  const int tile_ii0 = (int)(tile0 - (long long)tile_jj0 * a.nxr);
+  const unsigned nxr_u = (unsigned)a.nxr;
+  if (tid == 0) { sm.n_queued = 0; sm.head = 0; }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase A: init() of every cell, all lanes busy
+  for (int cidx = tid; cidx < tile_n; cidx += 128) {
+    if (tile0 + cidx >= a.ncell) break;
+    const unsigned t = (unsigned)(tile_ii0 + cidx), dj = t / nxr_u;
+    const int i = (int)(t - dj * nxr_u) - a.ring, j = tile_jj0 + (int)dj - a.ring;
+    CellIn<FT> in;
+    in.ua = ldg<FT>(a.xu, i, j); in.va = ldg<FT>(a.xv, i, j); in.Ta = ldg<FT>(a.xT, i, j); in.pa = ldg<FT>(a.xp, i, j);
+    in.qa = ldg<FT>(a.xq, i, j); in.Qs = ldg<FT>(a.xQs, i, j); in.Ql = ldg<FT>(a.xQl, i, j);
+    in.us = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
+    in.vs = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
+    in.Ts0 = ldg<FT>(a.oT, i, j) + P.T_offset;
+    in.So = FT(0);
+    in.h_ice = ldg<FT>(a.ih, i, j);
+    in.S_ice = ldg<FT>(a.iS, i, j);
+    in.albedo = sea_ice_albedo<FT>(P, a.ialb, a.ih, a.ihs, i, j, in.Ts0);
+    const FT conc = ldg<FT>(a.iconc, i, j);
+    const bool act = is_active(a.mask, i, j) && (conc > FT(0)) && (in.h_ice > FT(0));
+    if (act) {
+      CellSolver<FT, 1> s;
+      s.init(P, F, in);
+      if (s.go) {
+        stg<FT>(a.Qv, i, j, s.atm.rho); stg<FT>(a.Qc, i, j, s.atm.cp_m); stg<FT>(a.Fv, i, j, s.atm.q_vap);
+        stg<FT>(a.rtx, i, j, s.theta_a); stg<FT>(a.rty, i, j, s.du2dv2); stg<FT>(a.Tsout, i, j, in.albedo);
+        sm.queue[atomicAdd(&sm.n_queued, 1)] = (unsigned short)cidx;
+      } else {
+        ice_finish_cell<FT>(a, i, j, true, s.ustar, s.tstar, s.qstar, s.Ts, s.atm.rho, s.atm.cp_m, in.Ta, s.it);
+      }
+    } else {
+      ice_finish_cell<FT>(a, i, j, false, FT(0), FT(0), FT(0), in.Ts0, FT(0), FT(0), in.Ta, 0);
+    }
+  }
+  __syncthreads();
+  const int n_total = sm.n_queued;
+
+  // ------------------------------------------------------------------ phase B: lane refill; a finished cell is stored by its lane
+  CellSolver<FT, 1> s;
+  int ci = 0, cj = 0;
+  bool busy = false;
+  {   // everything init() derives from the parameters alone
+    CellIn<FT> z{};
+    z.Ta = FT(280); z.pa = FT(1e5); z.qa = FT(1e-3); z.Ts0 = FT(270); z.h_ice = FT(1);
+    s.in = z;
+    s.x = FT(1);
+    s.delta = P.th.eps - FT(1);
+    s.ly = false; s.U_ly = FT(0); s.rcdn_ly = FT(0); s.lnh10 = FT(0);
+    s.fixed = (F.stop_kind == COFLUX_STOP_FIXED_ITERATIONS);
+    s.ice_fast = true;
+    s.lnh_lu = M<FT>::log(P.h / F.mr.fixed); s.lnh_lt = M<FT>::log(P.h / F.tr.fixed); s.lnh_lq = M<FT>::log(P.h / F.qr.fixed);
+    s.du = s.dv = FT(0);
+  }
+  auto pop = [&]() {
+    const int pos = atomicAdd(&sm.head, 1);
+    busy = false;
+    if (pos < n_total) {
+      busy = true;
+      const unsigned t = (unsigned)(tile_ii0 + (int)sm.queue[pos]), dj = t / nxr_u;
+      ci = (int)(t - dj * nxr_u) - a.ring; cj = tile_jj0 + (int)dj - a.ring;
+      s.in.Ta = ldg<FT>(a.xT, ci, cj); s.in.pa = ldg<FT>(a.xp, ci, cj); s.in.Qs = ldg<FT>(a.xQs, ci, cj); s.in.Ql = ldg<FT>(a.xQl, ci, cj);
+      s.in.S_ice = ldg<FT>(a.iS, ci, cj); s.in.h_ice = ldg<FT>(a.ih, ci, cj);
+      s.atm.rho = ldc<FT>(a.Qv, ci, cj); s.atm.cp_m = ldc<FT>(a.Qc, ci, cj); s.atm.q_vap = ldc<FT>(a.Fv, ci, cj);
+      s.theta_a = ldc<FT>(a.rtx, ci, cj); s.du2dv2 = ldc<FT>(a.rty, ci, cj); s.in.albedo = ldc<FT>(a.Tsout, ci, cj);
+      s.ustar = F.init; s.tstar = F.init; s.qstar = F.init;
+      s.Ts = ldg<FT>(a.oT, ci, cj) + P.T_offset;
+      s.it = 0; s.go = true;
+      s.su = s.ustar; s.st = s.tstar; s.sq = s.qstar; s.sT = s.Ts; s.sr = s.rcdn_ly;
+      s.snap_it = 0; s.window = 1; s.stop_at = -1;
+    }
+  };
+  pop();
+  while (__any_sync(0xffffffffu, busy)) {
+    if (busy) {
+      s.pass(P, F);
+      if (!s.go) {
+        ice_finish_cell<FT>(a, ci, cj, true, s.ustar, s.tstar, s.qstar, s.Ts, s.atm.rho, s.atm.cp_m, s.in.Ta, s.it);
+        pop();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // centre → face momentum fluxes (A9)
 // ---------------------------------------------------------------------------------------------
 // by-products of the net fluxes for the ocean mixing closures (KPP/kpp_surface_forcing.jl:18-29,
