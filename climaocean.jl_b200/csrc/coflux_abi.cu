@@ -1315,7 +1315,8 @@ template <typename FT> static int launch_flux_rows(coflux_ctx* c, FluxArgs<FT> a
     int rc = launch_tile<FT, true, true>(c, a, st);
     if (rc) return rc;
   } else {
-    flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
+    if (uniform_layout<FT>(a)) flux_kernel<FT, 0, true, true, true, true><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
+    else flux_kernel<FT, 0, true, true, true><<<grid_for(a.ncell - a.cell0, 128), 128, 0, st>>>(a);
   }
   return check_launch(c, 1);
 }

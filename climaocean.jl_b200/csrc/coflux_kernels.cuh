@@ -224,55 +224,83 @@ __device__ __forceinline__ void avg_epilogue_u(const AvgArgs<FT>& g, int off, FT
     if (d[k]->p) reinterpret_cast<FT*>(d[k]->p)[off] = (old[k] * g.T + x[k] * g.dt) / (g.T + g.dt);
 }
 
-template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE>
+// UNI: uniform parent layout (FluxArgs::usj, ssj, fsj — see flux_tile_kernel): one element offset per cell for all surface
+// arrays, one gather-offset set for all series, 32-bit index arithmetic.  Used for the fused ocean path when the host has
+// verified the layout (`:ncar`: 1.88 → see profiles/README.md); UNI = false addresses every array through its own strides.
+template <typename FT, int SURF, bool INTERP, bool SOLVE, bool ASSEMBLE, bool UNI = false>
 __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxArgs<FT> a) {
+  static_assert(!UNI || SURF == 0, "the uniform-layout form covers the ocean surface arrays only");
   const long long idx = a.cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.ncell) return;
-  const int jj = (int)(idx / a.nxr);
-  const int ii = (int)(idx - (long long)jj * a.nxr);
+  int ii, jj;
+  if constexpr (UNI) { const unsigned u = (unsigned)idx, q = u / (unsigned)a.nxr; jj = (int)q; ii = (int)(u - q * (unsigned)a.nxr); }
+  else { jj = (int)(idx / a.nxr); ii = (int)(idx - (long long)jj * a.nxr); }
   const int i = ii - a.ring, j = jj - a.ring;
+  const int off = UNI ? j * a.usj + i : 0;
+  auto L = [&](const DArr& d, int di = 0, int dj = 0) -> FT {
+    if constexpr (UNI) return __ldg(reinterpret_cast<const FT*>(d.p) + (off + di + dj * a.usj));
+    else return ldg<FT>(d, i + di, j + dj);
+  };
+  auto S = [&](const DArr& d, FT v) {
+    if constexpr (UNI) { if (d.p) reinterpret_cast<FT*>(d.p)[off] = v; }
+    else stg<FT>(d, i, j, v);
+  };
+  auto wet = [&]() -> bool {
+    if constexpr (UNI) return !a.mask.p || __ldg(reinterpret_cast<const uint8_t*>(a.mask.p) + off) != 0;
+    else return is_active(a.mask, i, j);
+  };
 
   FT ua, va, Ta, pa, qa, Qs, Ql, Mp;
   if (INTERP) {
-    const FT fi = ldg<FT>(a.fi, i, j), fj = ldg<FT>(a.fj, i, j);
+    const int foff = UNI ? j * a.fsj + i : 0;
+    FT fi, fj;
+    if constexpr (UNI) { fi = __ldg(reinterpret_cast<const FT*>(a.fi.p) + foff); fj = __ldg(reinterpret_cast<const FT*>(a.fj.p) + foff); }
+    else { fi = ldg<FT>(a.fi, i, j); fj = ldg<FT>(a.fj, i, j); }
     const int i0 = (int)M<FT>::trunc(fi), j0 = (int)M<FT>::trunc(fj);
     const int i1 = i0 + ((fi > FT(0)) - (fi < FT(0))), j1 = j0 + ((fj > FT(0)) - (fj < FT(0)));
     const FT xi = fi - M<FT>::floor(fi), eta = fj - M<FT>::floor(fj);
     const FT w00 = (FT(1) - xi) * (FT(1) - eta), w01 = (FT(1) - xi) * eta, w10 = xi * (FT(1) - eta), w11 = xi * eta;
-    ua = interp_series<FT>(a.su, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    va = interp_series<FT>(a.sv, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    Ta = interp_series<FT>(a.sT, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    qa = interp_series<FT>(a.sq, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    pa = interp_series<FT>(a.sp, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    Qs = interp_series<FT>(a.sQs, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    Ql = interp_series<FT>(a.sQl, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    const int o00 = j0 * a.ssj + i0, o01 = j1 * a.ssj + i0, o10 = j0 * a.ssj + i1, o11 = j1 * a.ssj + i1;
+    auto SER = [&](const DSeries& d) -> FT {
+      if constexpr (UNI) return interp_series_u<FT>(d, o00, o01, o10, o11, w00, w01, w10, w11, a.nfrac);
+      else return interp_series<FT>(d, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    };
+    ua = SER(a.su);
+    va = SER(a.sv);
+    Ta = SER(a.sT);
+    qa = SER(a.sq);
+    pa = SER(a.sp);
+    Qs = SER(a.sQs);
+    Ql = SER(a.sQl);
     Mp = FT(0);
-    if (a.srain.p1) Mp += interp_series<FT>(a.srain, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
-    if (a.ssnow.p1) Mp += interp_series<FT>(a.ssnow, i0, j0, i1, j1, w00, w01, w10, w11, a.nfrac);
+    if (a.srain.p1) Mp += SER(a.srain);
+    if (a.ssnow.p1) Mp += SER(a.ssnow);
     if (a.lfi.p) Mp += land_freshwater<FT>(a, i, j);
     if (a.cs.p && a.sn.p) {
-      const FT cs = ldg<FT>(a.cs, i, j), sn = ldg<FT>(a.sn, i, j);
+      FT cs, sn;
+      if constexpr (UNI) { cs = __ldg(reinterpret_cast<const FT*>(a.cs.p) + foff); sn = __ldg(reinterpret_cast<const FT*>(a.sn.p) + foff); }
+      else { cs = ldg<FT>(a.cs, i, j); sn = ldg<FT>(a.sn, i, j); }
       const FT ur = ua * cs + va * sn, vr = -ua * sn + va * cs;
       ua = ur; va = vr;
     }
-    stg<FT>(a.xu, i, j, ua); stg<FT>(a.xv, i, j, va); stg<FT>(a.xT, i, j, Ta); stg<FT>(a.xp, i, j, pa);
-    stg<FT>(a.xq, i, j, qa); stg<FT>(a.xQs, i, j, Qs); stg<FT>(a.xQl, i, j, Ql); stg<FT>(a.xMp, i, j, Mp);
+    S(a.xu, ua); S(a.xv, va); S(a.xT, Ta); S(a.xp, pa);
+    S(a.xq, qa); S(a.xQs, Qs); S(a.xQl, Ql); S(a.xMp, Mp);
   } else {
-    ua = ldg<FT>(a.xu, i, j); va = ldg<FT>(a.xv, i, j); Ta = ldg<FT>(a.xT, i, j); pa = ldg<FT>(a.xp, i, j);
-    qa = ldg<FT>(a.xq, i, j); Qs = ldg<FT>(a.xQs, i, j); Ql = ldg<FT>(a.xQl, i, j);
-    Mp = (ASSEMBLE && a.xMp.p) ? ldg<FT>(a.xMp, i, j) : FT(0);
+    ua = L(a.xu); va = L(a.xv); Ta = L(a.xT); pa = L(a.xp);
+    qa = L(a.xq); Qs = L(a.xQs); Ql = L(a.xQl);
+    Mp = (ASSEMBLE && a.xMp.p) ? L(a.xMp) : FT(0);
   }
   if (!SOLVE) return;
 
   const DevParams<FT>& P = a.P;
   CellIn<FT> in;
   in.ua = ua; in.va = va; in.Ta = Ta; in.pa = pa; in.qa = qa; in.Qs = Qs; in.Ql = Ql;
-  in.us = (ldg<FT>(a.ou, i, j) + ldg<FT>(a.ou, i + 1, j)) * FT(0.5);
-  in.vs = (ldg<FT>(a.ov, i, j) + ldg<FT>(a.ov, i, j + 1)) * FT(0.5);
-  const FT Tunits = ldg<FT>(a.oT, i, j);
+  in.us = (L(a.ou) + L(a.ou, 1, 0)) * FT(0.5);
+  in.vs = (L(a.ov) + L(a.ov, 0, 1)) * FT(0.5);
+  const FT Tunits = L(a.oT);
   in.Ts0 = Tunits + P.T_offset;
-  in.So = (SURF == 0) ? ldg<FT>(a.oS, i, j) : FT(0);
-  bool act = is_active(a.mask, i, j);
+  in.So = (SURF == 0) ? L(a.oS) : FT(0);
+  bool act = wet();
   if (SURF == 1) {
     in.h_ice = ldg<FT>(a.ih, i, j);
     in.S_ice = ldg<FT>(a.iS, i, j);
@@ -301,24 +329,30 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
     Tsout = o.Ts - P.T_offset;
     us = o.ustar; ts = o.tstar; qs = o.qstar; its = o.it;
   }
-  stg<FT>(a.Qv, i, j, Qv); stg<FT>(a.Qc, i, j, Qc); stg<FT>(a.Fv, i, j, Fv);
-  stg<FT>(a.rtx, i, j, rtx); stg<FT>(a.rty, i, j, rty); stg<FT>(a.Tsout, i, j, Tsout);
-  stg<FT>(a.ust, i, j, us); stg<FT>(a.tst, i, j, ts); stg<FT>(a.qst, i, j, qs);
-  if (SURF == 1) stg<FT>(a.Ttop_out, i, j, Tsout);
-  if (a.iters.p) reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = its;
+  S(a.Qv, Qv); S(a.Qc, Qc); S(a.Fv, Fv);
+  S(a.rtx, rtx); S(a.rty, rty); S(a.Tsout, Tsout);
+  S(a.ust, us); S(a.tst, ts); S(a.qst, qs);
+  if (SURF == 1) S(a.Ttop_out, Tsout);
+  if (a.iters.p) {
+    if constexpr (UNI) reinterpret_cast<int32_t*>(a.iters.p)[off] = its;
+    else reinterpret_cast<int32_t*>(a.iters.p)[(int64_t)i * a.iters.si + (int64_t)j * a.iters.sj] = its;
+  }
   if (a.seam_east && i == a.Nx - 1 && j >= 0 && j < a.Ny) reinterpret_cast<FT*>(a.seam_east)[j] = rtx;
 
   if (ASSEMBLE) {
     if (i >= 0 && i < a.Nx && j >= 0 && j < a.Ny) {
-      const FT conc = a.conc.p ? ldg<FT>(a.conc, i, j) : FT(0);
-      const FT Qio = a.Qio.p ? ldg<FT>(a.Qio, i, j) : FT(0);
-      const FT sio = a.salt_io.p ? ldg<FT>(a.salt_io, i, j) : FT(0);
+      const FT conc = a.conc.p ? L(a.conc) : FT(0);
+      const FT Qio = a.Qio.p ? L(a.Qio) : FT(0);
+      const FT sio = a.salt_io.p ? L(a.salt_io) : FT(0);
       FT JT, JS, Qu, Qal, Qts, J0, parts[3];
-      assemble_tracers<FT>(P, is_active(a.mask, i, j), conc, in.So, Tsout + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio,
+      assemble_tracers<FT>(P, wet(), conc, in.So, Tsout + P.T_offset, Qs, Ql, Mp, Qc, Qv, Fv, Qio, sio,
                            JT, JS, Qu, Qal, Qts, J0, parts);
-      stg<FT>(a.JT, i, j, JT); stg<FT>(a.JS, i, j, JS); stg<FT>(a.Qu, i, j, Qu); stg<FT>(a.Qal, i, j, Qal);
-      stg<FT>(a.Qts, i, j, Qts); stg<FT>(a.J0, i, j, J0);
-      if (a.avg.on) avg_epilogue<FT>(a.avg, i, j, JT, JS, Qc, Qv, parts);
+      S(a.JT, JT); S(a.JS, JS); S(a.Qu, Qu); S(a.Qal, Qal);
+      S(a.Qts, Qts); S(a.J0, J0);
+      if (a.avg.on) {
+        if constexpr (UNI) avg_epilogue_u<FT>(a.avg, off, JT, JS, Qc, Qv, parts);
+        else avg_epilogue<FT>(a.avg, i, j, JT, JS, Qc, Qv, parts);
+      }
     }
   }
 }
