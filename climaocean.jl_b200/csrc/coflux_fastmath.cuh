@@ -172,22 +172,36 @@ COFLUX_FM double exp(double x, const double* tab) {
 // ---- Float32 overloads: the CUDA single-precision functions (already SFU-based and short), so that the same pass
 // template serves both precisions -----------------------------------------------------------------------
 COFLUX_FM float fma_(float a, float b, float c) { return ::fmaf(a, b, c); }
+// COFLUX_F32_FAST (see below): 1/x and √x of the Float32 PASS from the SFU — rcp.approx + one Newton step (≤ 1 ulp; the
+// IEEE __frcp_rn is 8 instructions with a slow-path branch and was 6 % of the Float32 kernel's instructions, whose issue
+// slots are 82 % busy) and sqrt.approx (≈ 1 ulp; sqrtf: 10 instructions).  The phase-A thermodynamics do not come through
+// here (M<float>: IEEE division, powf, expf), because Δq amplifies their errors a hundredfold.
+#ifndef COFLUX_F32_FAST
+#define COFLUX_F32_FAST 1
+#endif
 COFLUX_FM float rcp(float x) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return ::fmaf(r, ::fmaf(-x, r, 1.0f), r);
+#elif defined(__CUDA_ARCH__)
   return __frcp_rn(x);
 #else
   return 1.0f / x;
 #endif
 }
 COFLUX_FM float div(float a, float b) { return a / b; }
-COFLUX_FM float sqrt(float x) { return ::sqrtf(x); }
+COFLUX_FM float sqrt(float x) {
+#if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return ::sqrtf(x);
+#endif
+}
 // COFLUX_F32_FAST: SFU forms of the three transcendental functions of the Float32 pass — lg2.approx / ex2.approx (MUFU.LG2 /
 // MUFU.EX2) with one Newton step for the cube root — instead of the CUDA library's logf / expf / cbrtf (20–30 instructions
 // each).  Accuracy: ≈ 2⁻²¹ absolute in log₂, i.e. ≤ 3e-7 relative in ln(h/ℓ) ≈ 10.  Measured on B200 (round 2): 2.35 → 2.15 ms at
 // 1/12°, and the CUDA-vs-oracle error distribution is unchanged (max|d|/max|b| 3.3e-7, p99 5.4e-6: profiles/README.md).
-#ifndef COFLUX_F32_FAST
-#define COFLUX_F32_FAST 1
-#endif
 COFLUX_FM float cbrt(float x) {
 #if defined(__CUDA_ARCH__) && COFLUX_F32_FAST
   float lg; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
