@@ -429,6 +429,9 @@ __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P
 // One cell's interface solve as an object: init() hoists everything invariant under the iteration, pass() is one
 // fixed-point pass (sets `go`), finish() hands the scales back.  solve_cell() runs it start to finish in one thread
 // (flux_kernel); flux_refill_kernel keeps one solver per lane and refills a lane as soon as its cell has converged.
+#ifndef COFLUX_ICE_PSI_SERIES
+#define COFLUX_ICE_PSI_SERIES 1    /* sea-ice pass: ψ(ℓ/L★) by a Taylor polynomial instead of a table row (A/B knob) */
+#endif
 template <typename FT, int SURF> struct CellSolver {
   using MP = typename DefaultMP<FT>::type;
   CellIn<FT> in;
@@ -490,7 +493,26 @@ template <typename FT, int SURF> struct CellSolver {
 
   // ψ of the ice-solve parameter sets at one argument: Paulson table (ζ < 0), SHEBA table or −5ζ (ζ ≥ 0); the
   // first-order term below the table (|x| < 2⁻³⁰: the quadratic term is < 1e-18), the formulas above it
+  // |x| < 2⁻¹¹: degree-7 Taylor polynomial about 0 (truncation ≤ 9e-17 relative; coefficients from 60-digit mpmath
+  // expansions of the Paulson (x < 0) and SHEBA (x > 0) functions).  The arguments ℓ/L★ of the logarithmic profile form
+  // live here (ℓ = 5e-4 … 5e-5 m), three of the five ψ evaluations of a pass: no table row, no load.
+  static __device__ __forceinline__ FT psi_ice_small(bool stable, FT x, int which) {
+    FT c1, c2, c3, c4, c5, c6, c7;
+    if (!stable) {
+      if (which) { c1 = FT(-8); c2 = FT(-48); c3 = FT(-426.66666666666666667); c4 = FT(-4480); c5 = FT(-51609.6); c6 = FT(-630784); c7 = FT(-8032841.1428571428571); }
+      else { c1 = FT(-4); c2 = FT(-20); c3 = FT(-160); c4 = FT(-1560); c5 = FT(-16972.8); c6 = FT(-198016); c7 = FT(-2424685.7142857142857); }
+    } else {
+      if (which) { c1 = FT(-5); c2 = FT(5); c3 = FT(-8.3333333333333333333); c4 = FT(16.25); c5 = FT(-34); c6 = FT(74.166666666666666667); c7 = FT(-166.42857142857142857); }
+      else { c1 = FT(-5); c2 = FT(1.08974358974358974359); c3 = FT(-0.3736576813499890422967); c4 = FT(0.1384112454132177998056);
+             c5 = FT(-0.04402388764903304932638); c6 = FT(0.003071835405143235340764); c7 = FT(0.01474035094893286164122); }
+    }
+    FT p = c7;
+    p = p * x + c6; p = p * x + c5; p = p * x + c4; p = p * x + c3; p = p * x + c2; p = p * x + c1;
+    return p * x;
+  }
   __device__ __forceinline__ FT psi_ice(int stab, FT zz, int which) const {
+    if (COFLUX_ICE_PSI_SERIES && M<FT>::abs(zz) < FT(4.8828125e-4) && (zz < FT(0) || stab != COFLUX_STABILITY_LARGE_YEAGER))
+      return psi_ice_small(zz >= FT(0), zz, which);
     if (zz < FT(0)) {
       const FT mz = -zz;
       if (psi_tab_in_range(mz)) return psi_tab_eval(PsiTabs<FT>::paulson(), mz, which);
@@ -531,8 +553,9 @@ template <typename FT, int SURF> struct CellSolver {
     } else {
       FT prof_q = lnh_lq - psi_hs, prof_t = lnh_lt - psi_hs;
       if (logform) {
-        prof_q += psi_ice(stab, F.qr.fixed * invL, 1);
-        prof_t += psi_ice(stab, F.tr.fixed * invL, 1);
+        const FT pq = psi_ice(stab, F.qr.fixed * invL, 1);
+        prof_q += pq;
+        prof_t += (F.tr.fixed == F.qr.fixed) ? pq : psi_ice(stab, F.tr.fixed * invL, 1);   // the same number, bit for bit
       }
       const FT chi_u = MP::div(kappa, prof_u);
       const FT chi_q = (prof_q > FT(0)) ? MP::div(kappa, prof_q) : FT(0);
