@@ -12,11 +12,10 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "climaocean.jl_b200", "lib", "variants")
 VARIANTS = {
     "base": [],
-    "pre0_1280": ["COFLUX_TILE_PRE1=0"],
-    "pre0_1920": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_CELLS64=1920"],
-    "pre0_c2c_2240": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=2240"],
-    "pre0_c2c_2496": ["COFLUX_TILE_PRE1=0", "COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=2496"],
-    "pre1_c2c_1600": ["COFLUX_TILE_C2CONST=1", "COFLUX_TILE_CELLS64=1600"],
+    "ice256x5": ["COFLUX_ICE_MIN_BLOCKS=5"],
+    "ice192x5": ["COFLUX_ICE_MIN_BLOCKS=5", "COFLUX_ICE_TILE_CELLS=192"],
+    "ice256x6": ["COFLUX_ICE_MIN_BLOCKS=6"],
+    "ice_noseries": ["COFLUX_ICE_PSI_SERIES=0"],
 }
 
 
