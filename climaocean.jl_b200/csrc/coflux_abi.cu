@@ -929,6 +929,9 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   // Balanced tiling.  CTAs are dispatched as slots free up, so a launch lasts ceil(#CTAs / resident slots) CTA lifetimes
   // (measured: a 1/8 longitude slab of the 1/12° grid, 2.85 waves of 768-cell tiles, took exactly 3 × 168 µs).  Every CTA
   // therefore takes the same number of cells, chosen so that the grid is a whole number of waves: no ragged last wave.
+  // Two refinements were measured and dropped (profiles/README.md): a staggered start of the CTAs that share an SM, and
+  // tiles quantised to whole cells per lane (full tiles + one lighter last wave): both within ±2 % of this, either way.
+  // COFLUX_BALANCE=0: plain tiles of TILE cells.
   static int sm_count[64] = {};
   if (!sm_count[dev & 63]) CUDA_TRY(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
   FluxArgs<FT> b = a;
@@ -937,25 +940,11 @@ template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC> static int launch_t
   long long grid = grid_for(n, TILE);
   b.tile_cells = 0;
   static const bool balance = [] { const char* e = std::getenv("COFLUX_BALANCE"); return !(e && e[0] == '0'); }();
-  b.stagger = 0;
-  // COFLUX_STAGGER=1: staggered start of the CTAs that share an SM (see flux_tile_kernel), for launches of ≥ 2 waves
-  static const int stagger = [] { const char* e = std::getenv("COFLUX_STAGGER"); return e ? atoi(e) : 0; }();   // 2: interleaved
   if (balance && n > slots * (TILE / 4)) {
     const long long waves = (n + slots * TILE - 1) / (slots * TILE);
-    long long per = (n + waves * slots - 1) / (waves * slots);                 // cells per CTA, ≤ TILE
-    const int m = TT::MIN_BLOCKS, S = sm_count[dev & 63];
-    if (stagger && waves >= 2 && m >= 2 && S < 65536) {
-      const long long unit = 8 * m;                                            // fractions of a tile stay multiples of 8 cells
-      per = std::min<long long>((per + unit - 1) / unit * unit, TILE / unit * unit);
-      const long long full = (n + per - 1) / per;                              // full-tile equivalents needed
-      const long long nmid = std::max<long long>(0, full - (long long)m * S);
-      b.tile_cells = (int)per;
-      b.stagger = m << 16 | S | (stagger == 2 ? 1 << 24 : 0);
-      grid = (long long)m * S + nmid + (long long)(m - 1) * S;
-    } else {
-      b.tile_cells = (int)per;
-      grid = (n + per - 1) / per;
-    }
+    const long long per = (n + waves * slots - 1) / (waves * slots);           // cells per CTA, ≤ TILE
+    b.tile_cells = (int)per;
+    grid = (n + per - 1) / per;
   }
   kern<<<(unsigned)grid, TT::NT, smem, st>>>(b);
   return COFLUX_OK;

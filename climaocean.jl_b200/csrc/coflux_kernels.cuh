@@ -84,7 +84,7 @@ template <typename FT> struct FluxArgs {
   long long cell0, ncell;   // linear cell range [cell0, ncell) of the ring-extended surface handled by this launch
   // balanced tiling of the tile kernel: every CTA takes tile_cells ≤ TILE cells, chosen by the host so that the grid is a
   // whole number of waves of resident CTAs (0: TILE cells per CTA)
-  int tile_cells, stagger;     // balanced tiling: cells per CTA; stagger = m << 16 | S (launch_tile_spec), 0 = none
+  int tile_cells, pad_;
   // uniform layout (tile kernel; set by the host, which makes it a condition of tile eligibility): every 2-D surface array
   // the kernel touches has stride_i == 1 and the SAME row pitch usj (elements) — true for Oceananigans parents on one grid —
   // so a cell's element offset j·usj + i is computed once and shared by ≈ 70 loads and stores; ssj: the same for the

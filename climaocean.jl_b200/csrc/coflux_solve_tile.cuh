@@ -673,29 +673,9 @@ __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_const
   const ThermoC<FT>& c = P.th;
   const int tid = threadIdx.x;
   // balanced tiling (FluxArgs::tile_cells): this CTA's cells are [tile0, tile0 + tile_n)
-  int tile_n = (a.tile_cells > 0 && a.tile_cells < TILE) ? a.tile_cells : TILE;
-  long long tile0 = a.cell0 + (long long)blockIdx.x * tile_n;
-  if (a.stagger) {
-    // Staggered start (launch_tile_spec): the m CTAs that share an SM begin with tiles of m/m, (m−1)/m, … 1/m of the full
-    // size, so that from then on one of them is in its memory phases (A, C) while the others iterate (B); the last
-    // (m−1)·S CTAs are the complementary fractions, so the slots still finish together.  q = tile_n / m cells.
-    const int S = a.stagger & 0xffff, m = (a.stagger >> 16) & 0xff, q = tile_n / m, b = (int)blockIdx.x;
-    const bool inter = (a.stagger >> 24) != 0;        // the SM's CTAs are b, b+1, … (interleaved) rather than b, b+S, …
-    const int first = m * S, last0 = (int)gridDim.x - (m - 1) * S;
-    const long long head = (long long)S * q * (m * (m + 1) / 2);
-    if (b < first) {
-      const int k = inter ? b % m : b / S, r = inter ? b / m : b - k * S;
-      tile_n = q * (m - k);
-      tile0 = a.cell0 + (long long)S * q * (k * m - k * (k - 1) / 2) + (long long)r * tile_n;
-    } else if (b < last0) {
-      tile0 = a.cell0 + head + (long long)(b - first) * tile_n;
-    } else {
-      const int j = inter ? (b - last0) % (m - 1) : (b - last0) / S, r = inter ? (b - last0) / (m - 1) : (b - last0) - j * S;
-      const long long mid = (long long)(last0 - first) * tile_n;
-      tile_n = q * (m - 1 - j);
-      tile0 = a.cell0 + head + mid + (long long)S * q * (j * (m - 1) - j * (j - 1) / 2) + (long long)r * tile_n;
-    }
-  }
+  // balanced tiling (FluxArgs::tile_cells): this CTA's cells are [tile0, tile0 + tile_n)
+  const int tile_n = (a.tile_cells > 0 && a.tile_cells < TILE) ? a.tile_cells : TILE;
+  const long long tile0 = a.cell0 + (long long)blockIdx.x * tile_n;
   if (tid == 0) { sm.n_front = 0; sm.n_back = 0; sm.head[0] = 0; sm.head[1] = 0; }
   if (TABS) {
     for (int k = tid; k < 256; k += NT) s_lgt[k] = (&COFLUX_LOG_TABLE[0][0])[k];

@@ -8,6 +8,7 @@ from bench import make_host_case, make_cfg, time_device_steps, NX, NY, NZ
 bits = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 names = sys.argv[2:] or ["default", "corrected"]
 NX = int(os.environ.get('QB_NX', NX))      # e.g. QB_NX=540: one of 8 longitude slabs of the 1/12 degree grid
+NY = int(os.environ.get('QB_NY', NY))      # e.g. QB_NX=1440 QB_NY=600: the 1/4 degree grid
 grid, host = make_host_case(NX, NY, bits, 0, 1)
 dev = host.to_device_columns("cuda:0", NZ)
 for name in names:
