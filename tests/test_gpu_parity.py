@@ -202,14 +202,15 @@ def test_host_buffer_entry_matches_device_path(bits):
         assert rel_err(got, ref[key], bits) <= RTOL[bits], key
 
 
+@pytest.mark.parametrize("flux_configuration", ["default", "ncar"])
 @pytest.mark.parametrize("bits", [64, 32])
-def test_mixed_parent_layouts_take_the_strided_kernel(bits):
+def test_mixed_parent_layouts_take_the_strided_kernel(bits, flux_configuration):
     """The tile kernel shares one element offset among all 2-D surface arrays (uniform layout: what Oceananigans parents on
     one grid have).  A caller whose fields are padded differently is still served — by the one-cell-per-thread kernel,
     which addresses every array through its own strides — with the same results."""
     import torch
     from climaocean.jl_b200.fields import Field
-    grid, host, cfg = make_case(72, 30, 4, bits, land_fraction=0.2)
+    grid, host, cfg = make_case(72, 30, 4, bits, land_fraction=0.2, flux_configuration=flux_configuration)
     ref = oracle_update(host, cfg)
     uniform, _ = gpu_update(host, cfg)
     dev = host.to("cuda:0")
@@ -225,4 +226,6 @@ def test_mixed_parent_layouts_take_the_strided_kernel(bits):
     for k in ("net.T", "ao.latent_heat", "net.S", "net.u"):
         assert mixed[k].shape == uniform[k].shape
         assert rel_err(mixed[k], uniform[k], bits) <= RTOL[bits], k
+        if flux_configuration == "ncar":       # one and the same kernel, two ways of addressing: the same bits
+            assert np.array_equal(mixed[k], uniform[k]), k
     eng.close()
