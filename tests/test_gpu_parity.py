@@ -229,3 +229,28 @@ def test_mixed_parent_layouts_take_the_strided_kernel(bits, flux_configuration):
         if flux_configuration == "ncar":       # one and the same kernel, two ways of addressing: the same bits
             assert np.array_equal(mixed[k], uniform[k]), k
     eng.close()
+
+
+@pytest.mark.parametrize("bits", [64, 32])
+def test_series_with_their_own_padding_take_the_strided_kernel(bits):
+    """One gather-offset set serves all nine atmosphere series only when they share a layout; a series padded differently
+    (here: the short-wave radiation with a wider halo) sends the call to the strided kernel — same results."""
+    import torch
+    from climaocean.jl_b200.fields import FieldTimeSeries
+    grid, host, cfg = make_case(72, 30, 4, bits)
+    ref = oracle_update(host, cfg)
+    uniform, _ = gpu_update(host, cfg)
+    dev = host.to("cuda:0")
+    q = dev.atmos["Qs"]
+    H = q.halo[0]
+    wide = torch.nn.functional.pad(q.data, (3, 3, 2, 2))                      # (Nt, 1, nj + 4, ni + 6)
+    dev.atmos["Qs"] = FieldTimeSeries(wide.contiguous(), (H + 3, q.halo[1] + 2, 0), q.times, "Qs_wide")
+    eng = cj.Engine(cfg)
+    inp, out = dev.update_bundles()
+    eng.update_state(inp, out, QUERY_TIME)
+    torch.cuda.synchronize()
+    mixed = dev.outputs()
+    compare(mixed, ref, bits)
+    for k in ("net.T", "exchange.Qs", "net.downwelling_shortwave"):
+        assert rel_err(mixed[k], uniform[k], bits) <= RTOL[bits], k
+    eng.close()
