@@ -1432,9 +1432,15 @@ static int do_update_host(coflux_ctx* c, const coflux_atmos_series* atm, const c
   // (1.4 waves), so back-to-back launches on ONE stream leave the SMs idle in every tail and the kernels — not PCIe —
   // bound the pipeline (measured: 8 chunks on one stream 7.8 ms per step at 1/12° Float64, while PCIe moves the 252 MB
   // each way in 5.8 ms, tools/pcie_probe.py).  With two streams the next chunk's CTAs fill the tail of the previous one.
+  // Measured and NOT used (round 2): letting the kernels store the results straight into the caller's mapped pinned planes
+  // instead of staging them and copying device→host — 8.1 ms against 7.5 ms per step at 1/12° Float64; the copy engine moves
+  // the data faster than the SMs' stores over PCIe.  Chunk sweep (COFLUX_HOST_CHUNKS): 2 / 4 / 6 / 8 / 10–15 / 16 chunks:
+  // 12.2 / 8.8 / 8.0 / 7.7 / 7.6 / 7.5 ms.
   // chunk count: ≥ 4 MB per plane copy (below that the ~10 µs per cudaMemcpyAsync / launch dominate: at 8 slabs the fixed
   // 16-chunk pipeline issued ≈ 160 tiny operations per step and end-to-end scaled 2.1× on 8 GPUs), at most MAX_CHUNKS
   int nch = (int)std::min<size_t>(HostStage::MAX_CHUNKS, std::max<size_t>(1, plane / (4u << 20)));
+  static const int forced_chunks = [] { const char* e = std::getenv("COFLUX_HOST_CHUNKS"); return e ? atoi(e) : 0; }();   // A/B knob
+  if (forced_chunks > 0) nch = std::min(forced_chunks, (int)HostStage::MAX_CHUNKS);
   while (nch > 1 && g.Ny < 8 * nch) nch /= 2;
   int f[HostStage::MAX_CHUNKS + 1], r[HostStage::MAX_CHUNKS + 1], sj[HostStage::MAX_CHUNKS + 1];
   for (int k = 0; k <= nch; ++k) f[k] = (int)((long long)nyr * k / nch);
