@@ -488,7 +488,7 @@ template <typename FT, int TILE> struct IceTileSmem {
 #endif
 template <typename FT, int TILE>
 __global__ void __launch_bounds__(128, COFLUX_ICE_MIN_BLOCKS) ice_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   IceTileSmem<FT, TILE>& sm = *reinterpret_cast<IceTileSmem<FT, TILE>*>(smem_raw);
   const DevParams<FT>& P = a.P;
   const FluxP<FT>& F = P.ai;

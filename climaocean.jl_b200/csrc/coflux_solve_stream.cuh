@@ -81,7 +81,7 @@ __device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p
 
 template <typename FT, bool INTERP, bool ASSEMBLE, int SPEC>
 __global__ void __launch_bounds__(StreamTraits<FT, SPEC>::NT, 1) flux_stream_kernel(const __grid_constant__ FluxArgs<FT> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using TT = StreamTraits<FT, SPEC>;
   constexpr bool VARNU = TT::VARNU;
   constexpr bool TABS = TT::F64;

@@ -654,7 +654,7 @@ template <typename FT, int SPEC> struct TileTraits {
 #endif
 template <typename FT, bool INTERP, bool ASSEMBLE, int TILE, int SPEC>
 __global__ void COFLUX_TILE_BOUNDS(FT, SPEC) flux_tile_kernel(const __grid_constant__ FluxArgs<FT> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   using TT = TileTraits<FT, SPEC>;
   constexpr bool VARNU = TT::VARNU;
   constexpr bool LEAN = TT::LEAN;
