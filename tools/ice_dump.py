@@ -5,11 +5,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 import climaocean.jl_b200 as cj
-from tests.common import make_case, QUERY_TIME
+QUERY_TIME = 1.37 * 10800.0          # tests/common.py
 out = sys.argv[1]
 bits = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 name = sys.argv[3] if len(sys.argv) > 3 else "default"
-grid, host, cfg = make_case(700, 333, 3, bits, flux_configuration=name, with_ice=True, land_fraction=0.2)
+dtype = np.float64 if bits == 64 else np.float32
+grid = cj.LatitudeLongitudeGrid((700, 333, 3), latitude=(-60.0, 60.0), halo=(7, 7, 7), dtype=dtype)
+host = cj.SurfaceFluxData.synthetic(grid, ring=1, with_ice=True, land_fraction=0.2)
+cfg = cj.default_config(700, 333, 3, bits, name)
+cfg.grid.ring = 1
 dev = host.to("cuda:0")
 eng = cj.Engine(cfg)
 eng.interpolate_atmosphere_state(dev.atmos_series(), QUERY_TIME, dev.exchange_state())
