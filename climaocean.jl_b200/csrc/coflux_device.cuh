@@ -192,11 +192,15 @@ template <typename FT> __device__ __forceinline__ FT liquid_fraction(const Therm
   if (T <= c.T_in) return FT(0);
   return (T - c.T_in) / (c.T_fr - c.T_in);
 }
-template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q) {
+// ps_liquid (optional): the saturation pressure over LIQUID water at this T, if the caller has it.  For T above freezing
+// the liquid fraction is exactly 1, LH_0 and Δcp below are then exactly the liquid constants, and the saturation pressure
+// computed here would be the same number, bit for bit — so it is reused instead of recomputed (a pow and an exp).
+template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q,
+                                                                                               const FT* ps_liquid = nullptr) {
   FT lam = liquid_fraction(c, T);
   FT LH_0 = lam * c.LH_v0 + (FT(1) - lam) * c.LH_s0;
   FT dcp = lam * (c.cp_v - c.cp_l) + (FT(1) - lam) * (c.cp_v - c.cp_i);
-  FT ps = psat_generic<FT, MP>(c, T, LH_0, dcp);
+  FT ps = (ps_liquid && lam == FT(1)) ? *ps_liquid : psat_generic<FT, MP>(c, T, LH_0, dcp);
   FT denom = p - ps;
   FT q_vs = (denom > FT(0)) ? MP::div(c.Rd_over_Rv * (FT(1) - q) * ps, denom) : M<FT>::inf();
   FT q_c = M<FT>::max(q - q_vs, FT(0));
@@ -417,7 +421,7 @@ __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P
   s.qs = qstar * x;
   s.dq = atm.q_vap - s.qs;
   s.dtheta = theta_a - Ts;
-  Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs);
+  Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs, (SURF == 0) ? &ps : nullptr);
   s.T_v = surf.T_v;
   s.q_vap = surf.q_vap;
   s.nu_m = air_viscosity(F.mr.visc, Ts);
