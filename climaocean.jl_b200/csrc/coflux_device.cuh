@@ -595,7 +595,7 @@ template <typename FT, int SURF> struct CellSolver {
     FT Qc = -atm.rho * atm.cp_m * u0 * t0;
     FT Qv = -atm.rho * Ls * u0 * q0;
     FT Qa = Qv + Qu + Qc + Qd;
-    FT Tstar = Tb - Qa * in.h_ice / P.io.k_ice;
+    FT Tstar = Tb - MP::div(Qa * in.h_ice, P.io.k_ice);      // MP::div: the lean division (bit-identical to IEEE, a third of the instructions)
     if (F.skin_update == COFLUX_SKIN_LINEARIZED_LONGWAVE) {     // emitted long wave implicit: Q_u ≈ σ ε T_s⁻³ · T_s⁺
       const FT alpha = P.sigma * P.emis_i * Ts * Ts * Ts / P.io.k_ice;
       Tstar = (Tb - (Qd + Qc + Qv) * in.h_ice / P.io.k_ice) / (FT(1) + alpha * in.h_ice);
