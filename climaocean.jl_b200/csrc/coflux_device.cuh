@@ -196,17 +196,17 @@ template <typename FT, class MP = M<FT>>
 __device__ __forceinline__ FT psat_pure(const ThermoC<FT>& c, FT T, FT a, FT b) {
   return c.p_tr * MP::pow(MP::div(T, c.T_tr), a) * MP::exp(b * (c.inv_T_tr - MP::div(FT(1), T)));
 }
-template <typename FT> __device__ __forceinline__ FT liquid_fraction(const ThermoC<FT>& c, FT T) {
+template <typename FT, class MP = M<FT>> __device__ __forceinline__ FT liquid_fraction(const ThermoC<FT>& c, FT T) {
   if (T > c.T_fr) return FT(1);
   if (T <= c.T_in) return FT(0);
-  return (T - c.T_in) / (c.T_fr - c.T_in);
+  return MP::div(T - c.T_in, c.T_fr - c.T_in);
 }
 // ps_liquid (optional): the saturation pressure over LIQUID water at this T, if the caller has it.  For T above freezing
 // the liquid fraction is exactly 1, LH_0 and Δcp below are then exactly the liquid constants, and the saturation pressure
 // computed here would be the same number, bit for bit — so it is reused instead of recomputed (a pow and an exp).
 template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q,
                                                                                                const FT* ps_liquid = nullptr) {
-  FT lam = liquid_fraction(c, T);
+  FT lam = liquid_fraction<FT, MP>(c, T);
   FT LH_0 = lam * c.LH_v0 + (FT(1) - lam) * c.LH_s0;
   FT dcp = lam * (c.cp_v - c.cp_l) + (FT(1) - lam) * (c.cp_v - c.cp_i);
   FT ps = (ps_liquid && lam == FT(1)) ? *ps_liquid : psat_generic<FT, MP>(c, T, LH_0, dcp);
@@ -242,12 +242,15 @@ template <> __device__ __forceinline__ double LMath<double>::cbrt(double x) {
 }
 template <> __device__ __forceinline__ float LMath<float>::cbrt(float x) { return ::cbrtf(x); }
 
-// Table evaluation of a stability function (coflux_psi_table.h): z ∈ [2^KMIN, 2^KMAX) positive (−ζ for the unstable
-// tables, ζ for the stable one); which = 0 momentum, 1 scalar.  Degree-7 piecewise polynomials, error ≤ 3e-16·max(1,|ψ|).
-#define COFLUX_PSI_ROWS ((COFLUX_PSI_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
-__device__ __forceinline__ bool psi_tab_in_range(double z) { return z >= 9.313225746154785e-10 && z < 8192.0; }
-__device__ __forceinline__ bool psi_tab_in_range(float z) { return z >= 9.313225746154785e-10f && z < 8192.0f; }
-static_assert(COFLUX_PSI_KMIN == -30 && COFLUX_PSI_KMAX == 13, "psi_tab_in_range assumes [2^-30, 2^13)");
+// Table evaluation of a stability function of the sea-ice / Large–Yeager solves (Paulson, SHEBA: coflux_psi_table.h):
+// z ∈ [2^KMIN, 2^ICE_KMAX) positive (−ζ for the unstable table, ζ for the stable one); which = 0 momentum, 1 scalar.
+// Degree-7 piecewise polynomials, error ≤ 3e-16·max(1,|ψ|).  The range reaches 2²⁶: calm, strongly stratified ice cells
+// iterate through |ζ| of 10⁴ … 10⁷, and the closed forms they used to fall back to (cube root, two arctangents, three
+// logarithms, with a handful of lanes active) cost a fifth of the whole solve (measured, round 2).
+#define COFLUX_PSI_ROWS ((COFLUX_PSI_ICE_KMAX - COFLUX_PSI_KMIN) * COFLUX_PSI_NS)
+__device__ __forceinline__ bool psi_tab_in_range(double z) { return z >= 9.313225746154785e-10 && z < 67108864.0; }
+__device__ __forceinline__ bool psi_tab_in_range(float z) { return z >= 9.313225746154785e-10f && z < 67108864.0f; }
+static_assert(COFLUX_PSI_KMIN == -30 && COFLUX_PSI_ICE_KMAX == 26, "psi_tab_in_range assumes [2^-30, 2^26)");
 __device__ __forceinline__ double psi_tab_eval(const double (*tab)[2][8], double z, int which) {
   const long long bits = __double_as_longlong(z);
   const int hi = (int)(bits >> 32);

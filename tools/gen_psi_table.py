@@ -20,6 +20,7 @@ import numpy as np
 
 mp.mp.dps = 50
 KMIN, KMAX, NS, DEG = -30, 13, 16, 7
+KMAX_ICE = 26      # the Paulson / SHEBA tables of the sea-ice solve reach |ζ| < 2²⁶: calm, strongly stratified cells get there
 
 
 def conv(y):
@@ -104,9 +105,9 @@ def horner(c, t):
     return float(acc)
 
 
-def build(fu, ft, label):
+def build(fu, ft, label, kmax=None):
     rows, worst_u, worst_t = [], 0.0, 0.0
-    for k in range(KMIN, KMAX):
+    for k in range(KMIN, KMAX if kmax is None else kmax):
         for j in range(NS):
             a = mp.mpf(2) ** k * (1 + mp.mpf(j) / NS)
             b = mp.mpf(2) ** k * (1 + mp.mpf(j + 1) / NS)
@@ -132,19 +133,19 @@ def write_table(fh, rows, base):
 
 
 def main():
-    tables = [(psi_u, psi_t, "COFLUX_PSI_TABLE", "unstable Edson et al. (2013) ψ_u, ψ_θ on −ζ"),
-              (paulson_m, paulson_h, "COFLUX_PSI_PAULSON", "unstable Paulson (1970, γ = 16) ψ_m, ψ_h on −ζ"),
-              (sheba_m, sheba_h, "COFLUX_PSI_SHEBA", "stable Grachev et al. (2007) SHEBA ψ_m, ψ_h on ζ")]
+    tables = [(psi_u, psi_t, "COFLUX_PSI_TABLE", "unstable Edson et al. (2013) ψ_u, ψ_θ on −ζ", KMAX),
+              (paulson_m, paulson_h, "COFLUX_PSI_PAULSON", "unstable Paulson (1970, γ = 16) ψ_m, ψ_h on −ζ, up to 2^%d" % KMAX_ICE, KMAX_ICE),
+              (sheba_m, sheba_h, "COFLUX_PSI_SHEBA", "stable Grachev et al. (2007) SHEBA ψ_m, ψ_h on ζ, up to 2^%d" % KMAX_ICE, KMAX_ICE)]
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "climaocean.jl_b200", "csrc", "coflux_psi_table.h")
-    built = [(build(fu, ft, base), base, what) for fu, ft, base, what in tables]
+    built = [(build(fu, ft, base, kmax), base, what) for fu, ft, base, what, kmax in tables]
     with open(out, "w") as fh:
         fh.write("// GENERATED by tools/gen_psi_table.py — do not edit.\n")
         fh.write("// Piecewise degree-%d polynomials on [2^%d, 2^%d), %d sub-intervals per binade; max error relative to max(1,|ψ|)\n" % (DEG, KMIN, KMAX, NS))
         fh.write("// (40 points per interval, double Horner):\n")
         for (rows, wu, wt), base, what in built:
             fh.write("//   %-20s %s: %.2e, %.2e\n" % (base, what, wu, wt))
-        fh.write("#pragma once\n#define COFLUX_PSI_KMIN (%d)\n#define COFLUX_PSI_KMAX (%d)\n#define COFLUX_PSI_NS %d\n#define COFLUX_PSI_DEG %d\n"
-                 % (KMIN, KMAX, NS, DEG))
+        fh.write("#pragma once\n#define COFLUX_PSI_KMIN (%d)\n#define COFLUX_PSI_KMAX (%d)\n#define COFLUX_PSI_NS %d\n#define COFLUX_PSI_DEG %d\n#define COFLUX_PSI_ICE_KMAX (%d)\n"
+                 % (KMIN, KMAX, NS, DEG, KMAX_ICE))
         for (rows, wu, wt), base, what in built:
             write_table(fh, rows, base)
     for (rows, wu, wt), base, what in built:
