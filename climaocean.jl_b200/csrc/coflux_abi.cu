@@ -468,10 +468,12 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
   P.th.T_0 = (FT)t.reference_temperature; P.th.T_tr = (FT)t.triple_point_temperature; P.th.p_tr = (FT)t.triple_point_pressure;
   P.th.T_fr = (FT)t.water_freezing_temperature; P.th.T_in = (FT)t.total_ice_nucleation_temperature;
   P.th.Rd_over_Rv = P.th.R_d / P.th.R_v;
-  {   // as the device forms them (psat_generic): Δcp/R_v and fma(−Δcp, T_0, LH_0)/R_v in FT arithmetic
+  {   // as the device forms them (psat_generic; the library is built with -fmad=false, so the product is rounded before the
+      // subtraction — volatile keeps the host compiler from fusing it either): Δcp/R_v and (LH_0 − Δcp·T_0)/R_v in FT arithmetic
     const FT dl = P.th.cp_v - P.th.cp_l, di = P.th.cp_v - P.th.cp_i;
-    P.th.a_liq = dl / P.th.R_v; P.th.b_liq = std::fma(-dl, P.th.T_0, P.th.LH_v0) / P.th.R_v;
-    P.th.a_ice = di / P.th.R_v; P.th.b_ice = std::fma(-di, P.th.T_0, P.th.LH_s0) / P.th.R_v;
+    volatile FT pl = dl * P.th.T_0, pi = di * P.th.T_0;
+    P.th.a_liq = dl / P.th.R_v; P.th.b_liq = (P.th.LH_v0 - pl) / P.th.R_v;
+    P.th.a_ice = di / P.th.R_v; P.th.b_ice = (P.th.LH_s0 - pi) / P.th.R_v;
     P.th.inv_T_tr = (FT)1 / P.th.T_tr;
   }
   P.h = (FT)c.atmosphere.surface_layer_height; P.hbl = (FT)c.atmosphere.boundary_layer_height;

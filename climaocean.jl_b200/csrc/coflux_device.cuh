@@ -115,7 +115,7 @@ template <typename FT> struct ThermoC {
   FT R_d, R_v, eps, cp_d, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_0, T_tr, p_tr, T_fr, T_in;
   FT Rd_over_Rv;
   // constants of the Clausius–Clapeyron form for the pure phases, divided once on the host exactly as psat_generic divides
-  // them per call (same operands, same fused multiply-add, IEEE division): Δcp/R_v, (LH_0 − Δcp·T_0)/R_v, 1/T_tr
+  // them per call (same operands, same roundings, IEEE division): Δcp/R_v, (LH_0 − Δcp·T_0)/R_v, 1/T_tr
   FT a_liq, b_liq, a_ice, b_ice, inv_T_tr;
 };
 template <typename FT> struct Visc { int kind; FT nu, c0, c1, c2, c3; };
@@ -257,11 +257,15 @@ __device__ __forceinline__ double psi_tab_eval(const double (*tab)[2][8], double
   int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
   row = max(0, min(row, COFLUX_PSI_ROWS - 1));
   const double t = fma(2.0, __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL), -3.0);
-  const double2* q = reinterpret_cast<const double2*>(&tab[row][which][0]);
-  const double2 c0 = __ldg(q), c1 = __ldg(q + 1), c2 = __ldg(q + 2), c3 = __ldg(q + 3);
-  double a = fma(c3.y, t, c3.x);
-  a = fma(a, t, c2.y); a = fma(a, t, c2.x); a = fma(a, t, c1.y); a = fma(a, t, c1.x); a = fma(a, t, c0.y);
-  return fma(a, t, c0.x);
+  // two 256-bit loads (LDG.E.256, sm_100): a lane's polynomial is 64 B of its own table row, so 32 lanes read 32 different
+  // rows and the L1 data pipe, not latency, is what these gathers cost — half the requests of four 128-bit loads
+  const double* q = &tab[row][which][0];
+  double k0, k1, k2, k3, k4, k5, k6, k7;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k0), "=d"(k1), "=d"(k2), "=d"(k3) : "l"(q));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k4), "=d"(k5), "=d"(k6), "=d"(k7) : "l"(q + 4));
+  double a = fma(k7, t, k6);
+  a = fma(a, t, k5); a = fma(a, t, k4); a = fma(a, t, k3); a = fma(a, t, k2); a = fma(a, t, k1);
+  return fma(a, t, k0);
 }
 __device__ __forceinline__ float psi_tab_eval(const float (*tab)[2][8], float z, int which) {
   const int bits = __float_as_int(z);
