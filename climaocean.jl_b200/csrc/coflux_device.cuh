@@ -278,6 +278,29 @@ __device__ __forceinline__ float psi_tab_eval(const float (*tab)[2][8], float z,
   a = fmaf(a, t, c1.y); a = fmaf(a, t, c1.x); a = fmaf(a, t, c0.w); a = fmaf(a, t, c0.z); a = fmaf(a, t, c0.y);
   return fmaf(a, t, c0.x);
 }
+// both functions of one row at once (momentum and scalar share the argument, hence the row and t): one index computation,
+// the loads of both polynomials in flight together, two independent Horner chains.  Same operations per function as
+// psi_tab_eval → same bits.
+__device__ __forceinline__ void psi_tab_eval_pair(const double (*tab)[2][8], double z, double& pm, double& ps) {
+  const long long bits = __double_as_longlong(z);
+  const int hi = (int)(bits >> 32);
+  int row = (hi >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
+  row = max(0, min(row, COFLUX_PSI_ROWS - 1));
+  const double t = fma(2.0, __longlong_as_double(((bits & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL), -3.0);
+  const double* q = &tab[row][0][0];
+  double m0, m1, m2, m3, m4, m5, m6, m7, s0, s1, s2, s3, s4, s5, s6, s7;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(m0), "=d"(m1), "=d"(m2), "=d"(m3) : "l"(q));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(m4), "=d"(m5), "=d"(m6), "=d"(m7) : "l"(q + 4));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s0), "=d"(s1), "=d"(s2), "=d"(s3) : "l"(q + 8));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s4), "=d"(s5), "=d"(s6), "=d"(s7) : "l"(q + 12));
+  double a = fma(m7, t, m6), b = fma(s7, t, s6);
+  a = fma(a, t, m5); b = fma(b, t, s5); a = fma(a, t, m4); b = fma(b, t, s4); a = fma(a, t, m3); b = fma(b, t, s3);
+  a = fma(a, t, m2); b = fma(b, t, s2); a = fma(a, t, m1); b = fma(b, t, s1);
+  pm = fma(a, t, m0); ps = fma(b, t, s0);
+}
+__device__ __forceinline__ void psi_tab_eval_pair(const float (*tab)[2][8], float z, float& pm, float& ps) {
+  pm = psi_tab_eval(tab, z, 0); ps = psi_tab_eval(tab, z, 1);
+}
 template <typename FT> struct PsiTabs;
 template <> struct PsiTabs<double> {
   static __device__ __forceinline__ const double (*paulson())[2][8] { return COFLUX_PSI_PAULSON_F64; }
@@ -546,6 +569,15 @@ template <typename FT, int SURF> struct CellSolver {
     if (zz < FT(1)) return FT(-5) * zz;
     return which ? psi_scalar(stab, zz) : psi_momentum(stab, zz);
   }
+  // ψ_m and ψ_h at one argument (the same branches as psi_ice, taken once)
+  __device__ __forceinline__ void psi_ice_pair(int stab, FT zz, FT& pm, FT& ps) const {
+    if (zz < FT(0)) {
+      if (psi_tab_in_range(-zz)) { psi_tab_eval_pair(PsiTabs<FT>::paulson(), -zz, pm, ps); return; }
+    } else if (stab != COFLUX_STABILITY_LARGE_YEAGER) {
+      if (psi_tab_in_range(zz)) { psi_tab_eval_pair(PsiTabs<FT>::sheba(), zz, pm, ps); return; }
+    }
+    pm = psi_ice(stab, zz, 0); ps = psi_ice(stab, zz, 1);
+  }
   // compact pass for the sea-ice parameter sets (see init): same formulas as pass(), one code path
   __device__ __forceinline__ void pass_ice(const DevParams<FT>& P, const FluxP<FT>& F) {
     const FT g = P.g, h = P.h, kappa = F.kappa;
@@ -566,7 +598,8 @@ template <typename FT, int SURF> struct CellSolver {
     const FT invL = MP::div(kappa * bstar, u0 * u0);  // 1/L★ (0 when b★ = 0)
     const FT zeta = h * invL;
     const int stab = F.stability;
-    const FT psi_hm = psi_ice(stab, zeta, 0), psi_hs = psi_ice(stab, zeta, 1);
+    FT psi_hm, psi_hs;
+    psi_ice_pair(stab, zeta, psi_hm, psi_hs);
     const bool logform = (F.form == COFLUX_PROFILE_LOGARITHMIC);     // the COARE form drops the ψ(ℓ/L★) terms
     FT prof_u = lnh_lu - psi_hm;
     if (logform) prof_u += psi_ice(stab, F.mr.fixed * invL, 0);
