@@ -452,7 +452,8 @@ template <typename FT> struct SurfaceState { FT qs, dq, dtheta, T_v, q_vap, nu_m
 
 template <typename FT, int SURF, class MP = M<FT>>
 __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P, const FluxP<FT>& F,
-                                                          const Thermo<FT>& atm, FT pa, FT theta_a, FT x, FT Ts) {
+                                                          const Thermo<FT>& atm, FT pa, FT theta_a, FT x, FT Ts,
+                                                          bool need_viscosity = true) {
   const ThermoC<FT>& c = P.th;
   SurfaceState<FT> s;
   FT ps = (SURF == 0) ? psat_pure<FT, MP>(c, Ts, c.a_liq, c.b_liq) : psat_pure<FT, MP>(c, Ts, c.a_ice, c.b_ice);
@@ -463,9 +464,11 @@ __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P
   Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs, (SURF == 0) ? &ps : nullptr);
   s.T_v = surf.T_v;
   s.q_vap = surf.q_vap;
-  s.nu_m = air_viscosity(F.mr.visc, Ts);
-  s.nu_t = air_viscosity(F.tr.visc, Ts);
-  s.nu_q = air_viscosity(F.qr.visc, Ts);
+  if (need_viscosity) {            // (fixed roughness lengths never look at it: the sea-ice pass skips the three polynomials)
+    s.nu_m = air_viscosity(F.mr.visc, Ts);
+    s.nu_t = air_viscosity(F.tr.visc, Ts);
+    s.nu_q = air_viscosity(F.qr.visc, Ts);
+  } else { s.nu_m = s.nu_t = s.nu_q = FT(0); }
   return s;
 }
 
@@ -647,7 +650,7 @@ template <typename FT, int SURF> struct CellSolver {
     FT adT = M<FT>::min(F.skin_max_dT, M<FT>::abs(dT));
     FT sgn = (dT > FT(0)) ? FT(1) : ((dT < FT(0)) ? FT(-1) : FT(0));
     Ts = M<FT>::min(Ts + adT * sgn, Tm);
-    S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts);
+    S = surface_state<FT, SURF, MP>(P, F, atm, in.pa, theta_a, x, Ts, !ice_fast);
   }
   __device__ __forceinline__ void pass_generic(const DevParams<FT>& P, const FluxP<FT>& F) {
     const ThermoC<FT>& c = P.th;
