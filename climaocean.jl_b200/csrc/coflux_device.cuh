@@ -201,15 +201,25 @@ template <typename FT, class MP = M<FT>> __device__ __forceinline__ FT liquid_fr
   if (T <= c.T_in) return FT(0);
   return MP::div(T - c.T_in, c.T_fr - c.T_in);
 }
+// MLeanD forms pow(x, y) as exp(y·log x): the two saturation pressures of one temperature (pure phase at the surface, mixed
+// phase inside phase_equil_pTq) then share ln(T/T_tr) and 1/T_tr − 1/T — computed once by the caller, same operations,
+// same bits, one logarithm and two divisions less.  Other policies (powf) keep their own pow.
+template <class MP> struct PowIsExpLog { static constexpr bool value = false; };
+template <> struct PowIsExpLog<MLeanD> { static constexpr bool value = true; };
+template <typename FT> struct PsatT { FT lnT, rT; };
 // ps_liquid (optional): the saturation pressure over LIQUID water at this T, if the caller has it.  For T above freezing
 // the liquid fraction is exactly 1, LH_0 and Δcp below are then exactly the liquid constants, and the saturation pressure
 // computed here would be the same number, bit for bit — so it is reused instead of recomputed (a pow and an exp).
 template <typename FT, class MP = M<FT>> __device__ __forceinline__ Thermo<FT> phase_equil_pTq(const ThermoC<FT>& c, FT p, FT T, FT q,
-                                                                                               const FT* ps_liquid = nullptr) {
+                                                                                               const FT* ps_liquid = nullptr,
+                                                                                               const PsatT<FT>* tt = nullptr) {
   FT lam = liquid_fraction<FT, MP>(c, T);
   FT LH_0 = lam * c.LH_v0 + (FT(1) - lam) * c.LH_s0;
   FT dcp = lam * (c.cp_v - c.cp_l) + (FT(1) - lam) * (c.cp_v - c.cp_i);
-  FT ps = (ps_liquid && lam == FT(1)) ? *ps_liquid : psat_generic<FT, MP>(c, T, LH_0, dcp);
+  FT ps;
+  if (ps_liquid && lam == FT(1)) ps = *ps_liquid;
+  else if (PowIsExpLog<MP>::value && tt) ps = c.p_tr * MP::exp(MP::div(dcp, c.R_v) * tt->lnT) * MP::exp(MP::div(LH_0 - dcp * c.T_0, c.R_v) * tt->rT);
+  else ps = psat_generic<FT, MP>(c, T, LH_0, dcp);
   FT denom = p - ps;
   FT q_vs = (denom > FT(0)) ? MP::div(c.Rd_over_Rv * (FT(1) - q) * ps, denom) : M<FT>::inf();
   FT q_c = M<FT>::max(q - q_vs, FT(0));
@@ -456,12 +466,19 @@ __device__ __forceinline__ SurfaceState<FT> surface_state(const DevParams<FT>& P
                                                           bool need_viscosity = true) {
   const ThermoC<FT>& c = P.th;
   SurfaceState<FT> s;
-  FT ps = (SURF == 0) ? psat_pure<FT, MP>(c, Ts, c.a_liq, c.b_liq) : psat_pure<FT, MP>(c, Ts, c.a_ice, c.b_ice);
+  FT ps;
+  PsatT<FT> tt{FT(0), FT(0)};
+  if constexpr (PowIsExpLog<MP>::value) {
+    tt.lnT = MP::log(MP::div(Ts, c.T_tr)); tt.rT = c.inv_T_tr - MP::div(FT(1), Ts);
+    ps = c.p_tr * MP::exp(((SURF == 0) ? c.a_liq : c.a_ice) * tt.lnT) * MP::exp(((SURF == 0) ? c.b_liq : c.b_ice) * tt.rT);
+  } else {
+    ps = (SURF == 0) ? psat_pure<FT, MP>(c, Ts, c.a_liq, c.b_liq) : psat_pure<FT, MP>(c, Ts, c.a_ice, c.b_ice);
+  }
   FT qstar = MP::div(ps, atm.rho * c.R_v * Ts);
   s.qs = qstar * x;
   s.dq = atm.q_vap - s.qs;
   s.dtheta = theta_a - Ts;
-  Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs, (SURF == 0) ? &ps : nullptr);
+  Thermo<FT> surf = phase_equil_pTq<FT, MP>(c, pa, Ts, s.qs, (SURF == 0) ? &ps : nullptr, PowIsExpLog<MP>::value ? &tt : nullptr);
   s.T_v = surf.T_v;
   s.q_vap = surf.q_vap;
   if (need_viscosity) {            // (fixed roughness lengths never look at it: the sea-ice pass skips the three polynomials)
