@@ -848,7 +848,10 @@ static bool refill_v1() {
 // The sea-ice parameter sets that take CellSolver::pass_ice run the tile form of the solve (COFLUX_ICE_TILE=0: one cell
 // per thread).  The conditions are those of CellSolver::init's `ice_fast`, plus a skin temperature and a convergence stop.
 #ifndef COFLUX_ICE_TILE_CELLS
-#define COFLUX_ICE_TILE_CELLS 256
+#define COFLUX_ICE_TILE_CELLS 384   /* 3 cells per lane, 4 CTAs × 51 KB per SM.  Measured at 1/12°, 92 % ice cover, after the ψ-table work
+                                       of round 2 (256 / 320 / 384 cells, 4 CTAs; 448 × 3 CTAs): `:default` 11.10 / 10.89 / 11.07 / 11.60 ms,
+                                       `:corrected` 8.84 / 8.27 / 8.04 / 8.56 ms.  (Before that work the L1 the larger tiles take away
+                                       cost more than they gained: 16.9 ms at 256 against 17.0 at 384.) */
 #endif
 #ifndef COFLUX_ICE_QUEUE_CELLS
 #define COFLUX_ICE_QUEUE_CELLS 8192    /* most cells of one CTA of ice_queue_kernel (2-byte queue entries in shared memory) */
@@ -1112,9 +1115,8 @@ static int do_ai(coflux_ctx* c, const coflux_exchange_state* x, const coflux_oce
     CUDA_TRY(cudaGetDevice(&dev));
     if (!(configured >> (dev & 63) & 1ull)) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      // no shared-memory carve-out preference: the pass reads its log / exp / ψ tables from global memory through L1, and
-      // giving the L1 up costs more than larger tiles gain (measured, 1/12° Float64, 92 % ice cover: tile 256 at the
-      // default carve-out 16.9 ms; at the maximum carve-out tile 256 18.3 ms, 320 × 5 CTAs 17.8, 384 17.0, 512 × 3 CTAs 18.8)
+      // no shared-memory carve-out preference: the driver picks the smallest carve-out that fits 4 CTAs; the pass reads its
+      // log / exp / ψ tables from global memory through what is left of L1
       configured |= 1ull << (dev & 63);
     }
     kern<<<grid_for(a.ncell, TILE), 128, smem, st>>>(a);
