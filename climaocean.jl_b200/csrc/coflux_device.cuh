@@ -311,6 +311,29 @@ __device__ __forceinline__ void psi_tab_eval_pair(const double (*tab)[2][8], dou
 __device__ __forceinline__ void psi_tab_eval_pair(const float (*tab)[2][8], float z, float& pm, float& ps) {
   pm = psi_tab_eval(tab, z, 0); ps = psi_tab_eval(tab, z, 1);
 }
+// one function each at TWO arguments (ψ_m(ℓ_u/L★) and ψ_h(ℓ_q/L★) of the logarithmic profile form): both rows requested
+// before either polynomial is evaluated, two independent Horner chains.  Same operations per function → same bits.
+__device__ __forceinline__ void psi_tab_eval_two(const double (*tab)[2][8], double za, double zb, double& pa, double& pb) {
+  const long long ba = __double_as_longlong(za), bb = __double_as_longlong(zb);
+  int ra = ((int)(ba >> 32) >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4), rb = ((int)(bb >> 32) >> 16) - ((1023 + COFLUX_PSI_KMIN) << 4);
+  ra = max(0, min(ra, COFLUX_PSI_ROWS - 1)); rb = max(0, min(rb, COFLUX_PSI_ROWS - 1));
+  const double ta = fma(2.0, __longlong_as_double(((ba & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL), -3.0);
+  const double tb = fma(2.0, __longlong_as_double(((bb & 0x0000ffffffffffffLL) << 4) | 0x3ff0000000000000LL), -3.0);
+  const double* qa = &tab[ra][0][0];
+  const double* qb = &tab[rb][1][0];
+  double m0, m1, m2, m3, m4, m5, m6, m7, s0, s1, s2, s3, s4, s5, s6, s7;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(m0), "=d"(m1), "=d"(m2), "=d"(m3) : "l"(qa));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(m4), "=d"(m5), "=d"(m6), "=d"(m7) : "l"(qa + 4));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s0), "=d"(s1), "=d"(s2), "=d"(s3) : "l"(qb));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(s4), "=d"(s5), "=d"(s6), "=d"(s7) : "l"(qb + 4));
+  double a = fma(m7, ta, m6), b = fma(s7, tb, s6);
+  a = fma(a, ta, m5); b = fma(b, tb, s5); a = fma(a, ta, m4); b = fma(b, tb, s4); a = fma(a, ta, m3); b = fma(b, tb, s3);
+  a = fma(a, ta, m2); b = fma(b, tb, s2); a = fma(a, ta, m1); b = fma(b, tb, s1);
+  pa = fma(a, ta, m0); pb = fma(b, tb, s0);
+}
+__device__ __forceinline__ void psi_tab_eval_two(const float (*tab)[2][8], float za, float zb, float& pa, float& pb) {
+  pa = psi_tab_eval(tab, za, 0); pb = psi_tab_eval(tab, zb, 1);
+}
 template <typename FT> struct PsiTabs;
 template <> struct PsiTabs<double> {
   static __device__ __forceinline__ const double (*paulson())[2][8] { return COFLUX_PSI_PAULSON_F64; }
@@ -598,6 +621,15 @@ template <typename FT, int SURF> struct CellSolver {
     }
     pm = psi_ice(stab, zz, 0); ps = psi_ice(stab, zz, 1);
   }
+  // ψ_m(za) and ψ_h(zb), za and zb of one sign (ℓ_u/L★ and ℓ_q/L★)
+  __device__ __forceinline__ void psi_ice_two(int stab, FT za, FT zb, FT& pa, FT& pb) const {
+    if (za < FT(0) && zb < FT(0)) {
+      if (psi_tab_in_range(-za) && psi_tab_in_range(-zb)) { psi_tab_eval_two(PsiTabs<FT>::paulson(), -za, -zb, pa, pb); return; }
+    } else if (za > FT(0) && zb > FT(0) && stab != COFLUX_STABILITY_LARGE_YEAGER) {
+      if (psi_tab_in_range(za) && psi_tab_in_range(zb)) { psi_tab_eval_two(PsiTabs<FT>::sheba(), za, zb, pa, pb); return; }
+    }
+    pa = psi_ice(stab, za, 0); pb = psi_ice(stab, zb, 1);
+  }
   // compact pass for the sea-ice parameter sets (see init): same formulas as pass(), one code path
   __device__ __forceinline__ void pass_ice(const DevParams<FT>& P, const FluxP<FT>& F) {
     const FT g = P.g, h = P.h, kappa = F.kappa;
@@ -622,13 +654,17 @@ template <typename FT, int SURF> struct CellSolver {
     psi_ice_pair(stab, zeta, psi_hm, psi_hs);
     const bool logform = (F.form == COFLUX_PROFILE_LOGARITHMIC);     // the COARE form drops the ψ(ℓ/L★) terms
     FT prof_u = lnh_lu - psi_hm;
-    if (logform) prof_u += psi_ice(stab, F.mr.fixed * invL, 0);
+    FT pq = FT(0);
+    if (logform) {                                   // ψ_m(ℓ_u/L★) and ψ_h(ℓ_q/L★) together (the second is only used when χ_u > 0)
+      FT pu;
+      psi_ice_two(stab, F.mr.fixed * invL, F.qr.fixed * invL, pu, pq);
+      prof_u += pu;
+    }
     if (!(prof_u > FT(0))) {
       ustar = tstar = qstar = FT(0);
     } else {
       FT prof_q = lnh_lq - psi_hs, prof_t = lnh_lt - psi_hs;
       if (logform) {
-        const FT pq = psi_ice(stab, F.qr.fixed * invL, 1);
         prof_q += pq;
         prof_t += (F.tr.fixed == F.qr.fixed) ? pq : psi_ice(stab, F.tr.fixed * invL, 1);   // the same number, bit for bit
       }
