@@ -714,8 +714,10 @@ template <typename FT, int SURF> struct CellSolver {
     if (ly) {
       FT zeta = MP::div(kappa * bstar * h, u0 * u0);
       zeta = M<FT>::max(FT(-10), M<FT>::min(FT(10), zeta));
-      FT psim = psi_momentum(COFLUX_STABILITY_LARGE_YEAGER, zeta);
-      FT psih = psi_scalar(COFLUX_STABILITY_LARGE_YEAGER, zeta);
+      FT psim, psih;                           // the Large–Yeager pair inline: one table row for both (ζ < 0), −5ζ (ζ ≥ 0)
+      if (COFLUX_PSI_TABLES_V1 && zeta < FT(0) && psi_tab_in_range(-zeta)) psi_tab_eval_pair(PsiTabs<FT>::paulson(), -zeta, psim, psih);
+      else if (zeta >= FT(0)) psim = psih = -FT(5) * zeta;
+      else { psim = psi_momentum(COFLUX_STABILITY_LARGE_YEAGER, zeta); psih = psi_scalar(COFLUX_STABILITY_LARGE_YEAGER, zeta); }
       FT U10N = MP::div(U_ly, FT(1) + MP::div(rcdn_ly, kappa) * (lnh10 - psim));
       U10N = M<FT>::max(U10N, F.ly_umin);
       FT cdn = ly_cdn<FT, MP>(U10N);
