@@ -370,10 +370,11 @@ __device__ __forceinline__ int psi_table_row(float z, float& t) {
   return row;
 }
 template <typename FT> struct Coef8 { FT c[8]; };
-__device__ __forceinline__ Coef8<double> ld_coef8(const double* p) {       // 4 × LDG.128
-  const double2* q = reinterpret_cast<const double2*>(p);
-  const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-  return Coef8<double>{{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y}};
+__device__ __forceinline__ Coef8<double> ld_coef8(const double* p) {       // 2 × LDG.E.256 (sm_100): half the L1 requests of 4 × LDG.128
+  Coef8<double> k;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k.c[0]), "=d"(k.c[1]), "=d"(k.c[2]), "=d"(k.c[3]) : "l"(p));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(k.c[4]), "=d"(k.c[5]), "=d"(k.c[6]), "=d"(k.c[7]) : "l"(p + 4));
+  return k;
 }
 __device__ __forceinline__ Coef8<float> ld_coef8(const float* p) {         // 2 × LDG.128
   const float4* q = reinterpret_cast<const float4*>(p);
