@@ -41,7 +41,10 @@
  *     carries the base pointer of the parent, ELEMENT strides, and the halo offsets, so that the
  *     zero-based interior cell (i,j,k) lives at ptr[(i+off_i)*stride_i + (j+off_j)*stride_j +
  *     (k+off_k)*stride_k + n*stride_n].  Nothing is assumed compact.  Negative interior indices
- *     (halo cells) are legal wherever off_* allows.
+ *     (halo cells) are legal wherever off_* allows.  (Fast path: when all 2-D surface arrays of a call have
+ *     stride_i == 1 and one common stride_j — Oceananigans parents of one grid do — and the atmosphere series
+ *     likewise among themselves, the kernels share one element offset per cell; any other layout is served by
+ *     a kernel that addresses every array through its own strides, with the same results.)
  *   - element type of all floating-point arrays = the context dtype (COFLUX_F32 / COFLUX_F64).
  *   - no CPU fallback exists anywhere in this library.
  */
