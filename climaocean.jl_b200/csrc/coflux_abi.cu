@@ -479,6 +479,7 @@ template <typename FT> static DevParams<FT> make_dev_params(const coflux_config&
   P.h = (FT)c.atmosphere.surface_layer_height; P.hbl = (FT)c.atmosphere.boundary_layer_height;
   P.g = (FT)c.atmosphere.gravitational_acceleration;
   P.rho0 = (FT)c.ocean.reference_density; P.c0 = (FT)c.ocean.heat_capacity; P.rhof = (FT)c.ocean.freshwater_density;
+  P.rho0inv = (FT)1 / P.rho0; P.rhofinv = (FT)1 / P.rhof;
   P.Smin = (FT)c.ocean.minimum_salinity;
   FT alpha = (FT)0;
   for (int k = 0; k < 4; ++k) alpha += (FT)c.ocean.constituent_mass_fraction[k] / (FT)c.ocean.constituent_molar_mass[k];
@@ -1221,7 +1222,7 @@ static void fill_stress(const coflux_ctx* c, const coflux_ocean_surface* o, cons
   s.mask = o ? view2d(o->mask, 0, 1) : DArr{nullptr, 0, 0};
   s.taux = view2d(out->u, 0, es); s.tauy = view2d(out->v, 0, es);
   s.seam_west = nullptr;
-  s.rho0 = dev_params<FT>(c).rho0;
+  s.rho0 = dev_params<FT>(c).rho0; s.rho0inv = dev_params<FT>(c).rho0inv;
   s.cell0 = 0; s.cell1 = (long long)g.Nx * g.Ny;
   if (c->closure_on) fill_closure<FT>(c->closure, out, s.closure);
 }

@@ -153,6 +153,7 @@ template <typename FT> struct DevParams {
   FastConsts<FT> K;                // for the atmosphere–ocean parameters
   FT h, hbl, g;
   FT rho0, c0, rhof, Smin, wmf_alpha, T_offset;  // T_offset: 273.15 if ocean T in °C else 0
+  FT rho0inv, rhofinv;                           // 1/ρ₀, 1/ρ_f: divided once on the host (IEEE, the bits a per-cell division gives)
   FT sigma, alb_o, emis_o, emis_i, alb_i;
   int sw_pen, ice_albedo_kind;
   Ccsm3P<FT> ccsm3;

@@ -173,7 +173,7 @@ template <typename FT>
 __device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool act, FT conc, FT So, FT TsK, FT Qs, FT Ql,
                                                  FT Mp, FT Qc, FT Qv, FT Mv, FT Qio, FT salt_io, FT& JT, FT& JS, FT& Qu,
                                                  FT& Qal, FT& Qts, FT& J0, FT* parts = nullptr /* JTao, JTio, JSio */) {
-  const FT rho0inv = FT(1) / P.rho0, rhofinv = FT(1) / P.rhof;
+  const FT rho0inv = P.rho0inv, rhofinv = P.rhofinv;
   Qu = P.emis_o * P.sigma * TsK * TsK * TsK * TsK;
   Qal = -P.emis_o * Ql;
   Qts = -(FT(1) - P.alb_o) * Qs;
@@ -181,13 +181,13 @@ __device__ __forceinline__ void assemble_tracers(const DevParams<FT>& P, bool ac
   const FT SQ = Qu + Qc + Qv + Qal + Qss;
   FT SF = -Mp * rhofinv;
   SF += Mv * rhofinv;
-  const FT JTao = SQ * rho0inv / P.c0;
+  const FT JTao = LMath<FT>::div(SQ * rho0inv, P.c0);          // LMath::div: the lean division in Float64 (bit-identical to IEEE)
   FT JSao = -So * SF;
   if (So < P.Smin && JSao > FT(0)) JSao = FT(0);
-  const FT JTao_w = (FT(1) - conc) * JTao, JTio = Qio * rho0inv / P.c0, JSio = salt_io * conc;
+  const FT JTao_w = (FT(1) - conc) * JTao, JTio = LMath<FT>::div(Qio * rho0inv, P.c0), JSio = salt_io * conc;
   JT = JTao_w + JTio;
   JS = (FT(1) - conc) * JSao + JSio;
-  J0 = (FT(1) - conc) * Qts * rho0inv / P.c0;
+  J0 = LMath<FT>::div((FT(1) - conc) * Qts * rho0inv, P.c0);
   if (!act) { JT = JS = J0 = FT(0); Qu = Qal = Qts = FT(0); }
   if (parts) { parts[0] = act ? JTao_w : FT(0); parts[1] = act ? JTio : FT(0); parts[2] = act ? JSio : FT(0); }
 }
@@ -798,14 +798,14 @@ template <typename FT> struct StressArgs {
   DArr rtx, rty, conc, tx_io, ty_io, mask;
   DArr taux, tauy;
   const char* seam_west;   // ρτx of the west neighbour's last column (Ny elements), or nullptr
-  FT rho0;
+  FT rho0, rho0inv;        // rho0inv = 1/ρ₀, divided on the host
   ClosureArgs<FT> closure;
   DArr avg_tx, avg_ty;     // running time averages of τx, τy (optional)
   FT avg_T, avg_dt;
 };
 template <typename FT>
 __device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, int j, FT& tx, FT& ty) {
-  const FT rho0inv = FT(1) / a.rho0;
+  const FT rho0inv = a.rho0inv;
   const int iw = (a.wrap_x && i == 0) ? a.Nx - 1 : i - 1;
   const FT rtx_c = ldg<FT>(a.rtx, i, j);
   const FT rtx_w = (a.seam_west && i == 0) ? __ldg(reinterpret_cast<const FT*>(a.seam_west) + j) : ldg<FT>(a.rtx, iw, j);
@@ -829,7 +829,9 @@ __device__ __forceinline__ void assemble_stress(const StressArgs<FT>& a, int i, 
 template <typename FT> __global__ void __launch_bounds__(256) stress_kernel(const __grid_constant__ StressArgs<FT> a) {
   const long long idx = a.cell0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.cell1) return;
-  const int j = (int)(idx / a.Nx), i = (int)(idx - (long long)j * a.Nx);
+  int i, j;
+  if (a.cell1 < (1LL << 31)) { const unsigned u = (unsigned)idx, q = u / (unsigned)a.Nx; j = (int)q; i = (int)(u - q * (unsigned)a.Nx); }   // 32-bit division
+  else { j = (int)(idx / a.Nx); i = (int)(idx - (long long)j * a.Nx); }
   FT tx, ty;
   assemble_stress<FT>(a, i, j, tx, ty);
   stg<FT>(a.taux, i, j, tx);
