@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(128) flux_kernel(const __grid_constant__ FluxA
     CellOut<FT> o;
     if (SURF == 0) solve_cell<FT, 0>(P, P.ao, in, o);
     else solve_cell<FT, 1>(P, P.ai, in, o);
-    const FT dU = M<FT>::sqrt(o.du * o.du + o.dv * o.dv);
-    const FT taux = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.du / dU;
-    const FT tauy = (dU == FT(0)) ? dU : -o.ustar * o.ustar * o.dv / dU;
+    const FT dU = LMath<FT>::sqrt(o.du * o.du + o.dv * o.dv);      // LMath: the lean square root / division in Float64 (bit-identical to IEEE)
+    const FT taux = (dU == FT(0)) ? dU : LMath<FT>::div(-o.ustar * o.ustar * o.du, dU);
+    const FT tauy = (dU == FT(0)) ? dU : LMath<FT>::div(-o.ustar * o.ustar * o.dv, dU);
     const ThermoC<FT>& c = P.th;
     const FT LH = (SURF == 0) ? c.LH_v0 + (c.cp_v - c.cp_l) * (Ta - c.T_0) : c.LH_s0 + (c.cp_v - c.cp_i) * (Ta - c.T_0);
     Qv = -o.rho_a * o.ustar * o.qstar * LH;
