@@ -108,3 +108,36 @@ def test_slab_coordinates_carry_the_bits_of_the_global_grid(world):
             a, b = host.ocean[n].numpy(), ref.ocean[n].numpy()
             H = 7
             assert np.array_equal(a[:, :, H:-H], b[:, :, H + rank * nx:H + (rank + 1) * nx]), n
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_with_land_series_and_sea_ice_match_the_single_domain(world):
+    """Zero-message ring mode with the round-2 inputs: land freshwater series (their own source grid and fractional
+    indices), sea ice (concentration, ice–ocean terms) and a land mask.  Every slab, solved on its own by the oracle from
+    slab-local data, reproduces its columns of the single-domain solve bit for bit."""
+    import climaocean.jl_b200 as cj
+    from oracle import pyoracle
+    from tests.common import QUERY_TIME
+    pyoracle.set_threads(2)
+    Nx, Ny, Nz = 48, 18, 3
+    kw = dict(ring=1, with_land=True, with_ice=True, land_fraction=0.2)
+    full = cj.LatitudeLongitudeGrid((Nx, Ny, Nz), latitude=(-70.0, 70.0), halo=(4, 4, 2))
+    ref_host = cj.SurfaceFluxData.synthetic(full, **kw)
+    cfg = cj.default_config(Nx, Ny, Nz, 64)
+    inp, out = ref_host.update_bundles(True)
+    pyoracle.sea_ice_ocean_fluxes(cfg, ref_host.ocean_columns(), ref_host.sea_ice_state(), 600.0, ref_host.ice_ocean_fluxes())
+    pyoracle.update_state(cfg, inp, out, QUERY_TIME)
+    ref = ref_host.outputs()
+    nx = Nx // world
+    for rank in range(world):
+        g = full.slab(rank, world)
+        host = cj.SurfaceFluxData.synthetic(g, **kw)
+        c = cj.default_config(g.Nx, g.Ny, Nz, 64)
+        c.grid.ring = 1
+        c.grid.periodic_x = 0
+        i2, o2 = host.update_bundles(True)
+        pyoracle.sea_ice_ocean_fluxes(c, host.ocean_columns(), host.sea_ice_state(), 600.0, host.ice_ocean_fluxes())
+        pyoracle.update_state(c, i2, o2, QUERY_TIME)
+        got = host.outputs()
+        for k in ("exchange.Mp", "net.T", "net.S", "net.u", "net.v", "ao.latent_heat", "io.frazil_heat"):
+            assert np.array_equal(got[k], ref[k][:, rank * nx:(rank + 1) * nx]), (world, rank, k)
